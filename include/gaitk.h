@@ -1,0 +1,205 @@
+/*
+ * gaitk.h -- C-ABI of libgaitk.so: the B200 (sm_100a) implementation of the gait
+ * training hot path (per-modality temporal encoders + shared backbone + heads +
+ * losses + CAGrad/private backward + SGD + window gather/normalise).
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every device buffer
+ * is allocated and owned by the caller (PyTorch); the library never frees or
+ * keeps a pointer past the call.  All work is enqueued on the caller's CUDA
+ * stream (passed as void* == cudaStream_t), with no allocation, no host sync
+ * and no host read inside any call, so every entry is CUDA-graph capturable.
+ *
+ * Return value of every int entry: 0 = OK, >0 = cudaError_t, <0 = GAITK_E_*.
+ * gaitk_last_error() returns a thread-local message for the last failure.
+ * There is NO CPU fallback: a non-sm_100 device fails gaitk_plan_create with
+ * GAITK_E_ARCH.
+ *
+ * Each entry cites the reference interface (file:line, relative to the
+ * reference root) that it replaces.
+ */
+#ifndef GAITK_H
+#define GAITK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAITK_VERSION 100
+
+#define GAITK_E_BADARG (-1)
+#define GAITK_E_SHAPE  (-2)
+#define GAITK_E_DTYPE  (-3)
+#define GAITK_E_ARCH   (-4)
+#define GAITK_E_STATE  (-5)
+
+/* model families */
+#define GAITK_FAMILY_WEARGAIT 0   /* data/WearGait/weargait_encoders.py:116-189 WearGaitThreeModal */
+#define GAITK_FAMILY_FOG      1   /* train/feature_encoder.py:149-265 MultiModalMultiTaskModel   */
+
+#define GAITK_MAX_STREAMS 3
+#define GAITK_MAX_CLASSES 4
+#define GAITK_MAX_PASSES  6
+
+/* arithmetic of the conv/linear contractions */
+#define GAITK_DTYPE_F32  0        /* fp32 FFMA, parity 1e-5                           */
+#define GAITK_DTYPE_TF32 1        /* tensor-core tf32 inputs, fp32 accumulate, 1e-3   */
+
+typedef struct gaitk_model_desc {
+    int32_t family;               /* GAITK_FAMILY_*                                                   */
+    int32_t T;                    /* WearGait: win_len (weargait_train.py:655); FoG: pose_length      */
+    int32_t enc_out_ch;           /* WearGait C (:671); FoG skeleton_output_dim == sensor_out_channels*/
+    int32_t shared_out_ch;        /* S (:673 / configs.py shared_out_channels)                        */
+    int32_t backbone_dim;         /* bdim (:672)                                                      */
+    int32_t num_classes;          /* K                                                                */
+    int32_t use_norm;             /* TaskHead LayerNorm (weargait_encoders.py:33)                     */
+    int32_t use_cosine;           /* CosineLinear head (:19-28); implies norm                         */
+    int32_t synchronized;         /* one shared head (:133-136 / feature_encoder.py:195-202)          */
+    /* FoG / FBG only (configs.py:1-32) */
+    int32_t skel_in_dim;          /* skeleton_input_dim (21 FoG, 51 FBG)                              */
+    int32_t sensor_in_ch;         /* sensor_in_channels (6 / 3)                                       */
+    int32_t sensor_len;           /* sensor_length (426 / 65): pooled to sensor_out_len iff T_in == it*/
+    int32_t sensor_out_len;       /* SensorEncoder output_length (101)                                */
+    int32_t reserved[3];
+} gaitk_model_desc;
+
+/* One CE-family criterion: CE / weighted CE (weargait_train.py:121-130), GCL
+ * (classification_losses.py:79-109: scale s, margin m on the true class) and
+ * LDAM (:54-76: per-class margin).  loss = sum_b w[y_b] * nll_b / sum_b w[y_b],
+ * nll of softmax(scale * (z - margin[y]*onehot - logit_off)). */
+typedef struct gaitk_loss_desc {
+    float scale;                              /* s (1 for CE)                                   */
+    float margin[GAITK_MAX_CLASSES];          /* subtracted from the true-class logit           */
+    float cls_weight[GAITK_MAX_CLASSES];      /* class weights; all 1 when unweighted           */
+    int32_t nan_if_degenerate;                /* GCL with equal class counts: 0/0 at :104 -> NaN*/
+    int32_t reserved[2];
+} gaitk_loss_desc;
+
+typedef struct gaitk_plan gaitk_plan;
+
+int         gaitk_version(void);
+const char* gaitk_last_error(void);
+
+/* Plan = host metadata (shapes, parameter layout, launch geometry) for one model
+ * on one device.  Replaces the constructors WearGaitThreeModal.__init__
+ * (weargait_encoders.py:117-141) / MultiModalMultiTaskModel.__init__
+ * (feature_encoder.py:157-220). */
+int  gaitk_plan_create(const gaitk_model_desc* desc, int device, gaitk_plan** out);
+void gaitk_plan_destroy(gaitk_plan* plan);
+
+/* Canonical flat fp32 parameter layout == the reference's named_parameters()
+ * order (state_dict keys, de-aliased).  group: 0 = shared (CAGrad,
+ * get_shared_parameters :185-189 / feature_encoder.py:256-265), 1+s = private to
+ * stream s, -1 = never receives a gradient (enc_i.ln1). */
+int gaitk_param_count(const gaitk_plan* plan);
+int gaitk_param_info(const gaitk_plan* plan, int index, char* name, size_t name_cap,
+                     int64_t* offset, int64_t* numel, int32_t* group, int32_t* dims /*[4]*/);
+int64_t gaitk_param_total(const gaitk_plan* plan);        /* floats in the flat buffer        */
+int64_t gaitk_shared_total(const gaitk_plan* plan);       /* P = rows of G                    */
+int     gaitk_num_streams(const gaitk_plan* plan);
+int     gaitk_stream_in_dim(const gaitk_plan* plan, int stream);   /* channels of stream input */
+int     gaitk_stream_in_len(const gaitk_plan* plan, int stream);   /* rows of stream input     */
+
+/* Bytes of scratch (per-CTA partial gradients etc.) the step needs for a batch of B. */
+size_t gaitk_workspace_bytes(const gaitk_plan* plan, int B);
+
+/* forward: replaces model(xw, xi, xm) (weargait_encoders.py:148-156) /
+ * model(skeleton, sensor) (feature_encoder.py:222-254).
+ *   x[s]         (B, T_s, D_s) fp32, or a frame store when win_start[s] != NULL
+ *   win_start[s] optional int64[B]: first frame of each window in the frame store
+ *                (fused gather: dataloader_weargait.py:359-372 never materialised)
+ *   enabled_mask bit s clear => stream s sees zeros (weargait_train.py:355-358)
+ *   logits[s]    (B, K) fp32 out */
+int gaitk_forward(gaitk_plan* plan, const float* params, const float* const* x,
+                  const int64_t* const* win_start, int B, uint32_t enabled_mask,
+                  float* const* logits, int dtype, void* stream);
+
+/* criterion(logits, y): F.cross_entropy family (classification_losses.py:97-109,
+ * weargait_train.py:125-130).  loss_out[1], correct_out[1] (argmax == y count,
+ * weargait_train.py:313-315).  dlogits (B,K) optional: d loss / d logits. */
+int gaitk_loss(const float* logits, const int64_t* y, int B, int K, const gaitk_loss_desc* desc,
+               const float* logit_off, float* loss_out, int32_t* correct_out, float* dlogits,
+               void* stream);
+
+/* backward with external logit gradients (generic autograd path):
+ * d/dparams of sum_b <dlogits[s][b], logits[s][b]> for stream s, accumulated into
+ * grads (flat, same layout as params; += ).  Replaces loss.backward() through
+ * one stream.  dx[s] optional (B,T_s,D_s) input gradient (NULL to skip). */
+int gaitk_backward(gaitk_plan* plan, const float* params, const float* const* x,
+                   const int64_t* const* win_start, int B, uint32_t enabled_mask,
+                   const float* const* dlogits, float* grads, void* workspace, size_t workspace_bytes,
+                   int dtype, void* stream);
+
+/* Fused training step, phase 1 (replaces forward_batch + criteria + the n_task
+ * backward sweeps of CAGrad.get_weighted_loss multitask_weighting.py:680-688 +
+ * the private re-derivation weargait_train.py:218-242): one pass per stream over
+ * the batch that computes logits, losses, and ALL gradients, leaving
+ *   gbuf = [ G (P x n_tasks, column-major by task) | private grads (flat param layout, already
+ *            multiplied by private_mult) | loss[n] | correct[n] ]
+ * y[s] int64[B]; denom[s] = global sum_b w[y_b] (device float[1] per stream, see
+ * gaitk_loss_denominators) so that shards of a data-parallel batch add up.
+ * task_mask bit t clear => task t skipped (relaxed-input training with a dropped stream). */
+int gaitk_step_grads(gaitk_plan* plan, const float* params, const float* const* x,
+                     const int64_t* const* win_start, const int64_t* const* y, int B,
+                     const gaitk_loss_desc* loss /*[n_streams]*/, const float* const* logit_off,
+                     const float* denom /*device [n_streams]*/, uint32_t enabled_mask, uint32_t task_mask,
+                     float private_mult, float consistency_lambda, float* const* logits /*optional*/,
+                     float* gbuf, void* workspace, size_t workspace_bytes, int dtype, void* stream);
+int64_t gaitk_gbuf_floats(const gaitk_plan* plan);
+
+/* sum_b w[y_b] per stream from (global) label vectors -> denom[n_streams] (device). */
+int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_streams,
+                            const gaitk_loss_desc* loss, float* denom, void* stream);
+
+/* Fused training step, phase 2 (replaces CAGrad.cagrad + overwrite_grad +
+ * clip_grad_norm_ multitask_weighting.py:694-729,748-759,775 and
+ * torch.optim.SGD.step weargait_train.py:248,560): on-device Gram matrix, simplex
+ * solve, combine, clip, then SGD(momentum, weight decay) on the flat parameter
+ * buffer.  Runs identically on every rank after gbuf has been all-reduced.
+ * diag (optional, device float[16]): w[3], GTG[9], pre-clip norm, objective, iters. */
+int gaitk_step_update(gaitk_plan* plan, float* params, float* momentum, const float* gbuf,
+                      uint32_t task_mask, float cagrad_c, float max_norm, float lr, float mom,
+                      float weight_decay, float* grads_out /*optional flat*/, float* diag, void* stream);
+
+/* CAGrad alone on an explicit (P x n) column-major matrix (multitask_weighting.py:694-729). */
+int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float max_norm, float* shared_grad,
+                 float* diag, void* stream);
+
+/* SGD alone (torch.optim.SGD, momentum/dampening 0/no nesterov); has_grad (host
+ * uint8 per parameter of the plan) mirrors ".grad is None => skipped". */
+int gaitk_sgd(gaitk_plan* plan, float* params, const float* grads, float* momentum,
+              const uint8_t* has_grad, float lr, float mom, float weight_decay, void* stream);
+
+/* ---- data path --------------------------------------------------------------- */
+/* window_indices (dataloader_weargait.py:230-237): host integer arithmetic, bit exact.
+ * Writes up to cap (wid,start,stop) triples, returns the count. */
+int64_t gaitk_window_indices(int64_t n_frames, int64_t win, int64_t hop, int64_t* out, int64_t cap);
+
+/* per-channel sum, sum of squares (fp64) and count over finite values of a (N, D)
+ * fp64 frame matrix, accumulated into acc[3*D] (fit_stats_on_train :183-191). */
+int gaitk_stats_accumulate(const double* frames, int64_t N, int D, double* acc, void* stream);
+/* (mean, std) from acc (:205-209), std floored at 1e-6; device->device. */
+int gaitk_stats_finalize(const double* acc, int D, double* mean, double* stdv, void* stream);
+/* apply_stats (:212-227): NaN/Inf -> mean, (x-m)/max(s,1e-6), nan_to_num; fp64 in,
+ * fp32 out (the cast WearGaitSyncDataset.__getitem__ :361 does per sample). */
+int gaitk_normalize_frames(const double* frames, int64_t N, int D, const double* mean,
+                           const double* stdv, float* out, void* stream);
+/* gather B windows of T frames from a (N, D) fp32 frame store into (B, T, D); enabled==0 writes
+ * zeros (_maybe_zero weargait_train.py:355-358).  Replaces Dataset.__getitem__ + collate + H2D
+ * (dataloader_weargait.py:359-372). */
+int gaitk_window_gather(const float* frames, int D, const int64_t* win_start, int B, int T,
+                        int enabled, float* out, void* stream);
+/* FoG clip preparation (dataloader_fbg_fog.py:24-37,93-113): centre on joint 0, per-clip
+ * per-coordinate min-max, zero pad / trim to T_out; fp64 (L, J, 3) clips concatenated in `poses`
+ * with clip_start[i], clip_len[i]; out (n_clips, T_out, J*3) fp32. */
+int gaitk_fog_prepare_pose(const double* poses, const int64_t* clip_start, const int64_t* clip_len,
+                           int n_clips, int J, int T_out, float* out, void* stream);
+int gaitk_fog_prepare_sensor(const double* sens, const int64_t* clip_start, const int64_t* clip_len,
+                             int n_clips, int D, int T_out, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAITK_H */

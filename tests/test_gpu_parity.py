@@ -1,0 +1,406 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the golden vectors produced by the reference and
+against the CPU oracle on seeded inputs.  Tolerances: fp32 path 1e-5 relative (scale-relative for
+large-magnitude tensors); quantities downstream of the CAGrad simplex solve are compared at the
+tolerance SLSQP's own ftol=1e-6 stopping rule allows."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, sub
+
+pytestmark = pytest.mark.gpu
+
+WG_CASES = ["wg_sync_gcl", "wg_sync_gcl_drw", "wg_async_ce", "wg_async_gcl", "wg_sync_classwt_nc", "wg_sync_norm"]
+FOG_ASYNC = ["fog_async_gcl", "fog_async_ldam", "fbg_async_classwt"]
+FOG_ALL = ["fog_async_gcl", "fog_sync_gcl", "fog_async_ldam", "fog_sync_ce_nc", "fbg_async_classwt"]
+
+
+@pytest.fixture(scope="module")
+def gk():
+    import gaitk
+    assert torch.cuda.is_available()
+    return gaitk
+
+
+def close(a, b, rel=1e-5, what=""):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not a.size:
+        return
+    err = np.abs(a - b).max(); scale = max(np.abs(b).max(), 1e-30)
+    ok = np.allclose(a, b, rtol=rel, atol=rel * 1e-1) or err <= rel * scale
+    assert ok, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e} > {rel:g})"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def wg_model(gk, g):
+    meta = g["meta"]
+    m = gk.WearGaitThreeModal(synchronized=meta["synchronized"], use_norm=meta["use_norm"], use_cosine=meta["use_cosine"],
+                              **meta["model_kw"])
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}, strict=True)
+    return m.cuda()
+
+
+def wg_criteria(gk, meta):
+    crit = []
+    for c in meta["counts"]:
+        w = None
+        if meta["wm"] == "class_wt" or meta["drw"]:
+            wt = 1.0 / (torch.tensor(c, dtype=torch.float32) + 1e-8); w = (wt / wt.sum() * len(c)).cuda()
+        if meta["wm"] == "gcl":
+            crit.append(gk.GCLLoss(cls_num_list=c, m=0.2, s=25.0, noise_mul=0.0, weight=w))
+        else:
+            crit.append(gk.CrossEntropyLoss(weight=w))
+    return crit
+
+
+def grads_by_name(plan, flat):
+    flat = flat.cpu().numpy()
+    return {p.name: flat[p.offset:p.offset + p.numel].reshape(p.shape) for p in plan.params}
+
+
+@pytest.mark.parametrize("name", WG_CASES)
+def test_weargait_forward_matches_reference(gk, name):
+    g = load_golden(name)
+    m = wg_model(gk, g)
+    with torch.no_grad():
+        out = m(*[dev(g[f"x0_{j}"]) for j in range(3)])
+    close(torch.stack(out).cpu().numpy(), g["s0/logits"], 2e-5, "logits")
+
+
+@pytest.mark.parametrize("name", WG_CASES)
+def test_weargait_fused_step_matches_reference(gk, name):
+    g = load_golden(name); meta = g["meta"]
+    m = wg_model(gk, g)
+    step = gk.FusedTrainStep(m, wg_criteria(gk, meta), cagrad_c=meta["alpha"], private_mult=2.0)
+    for st in range(meta["steps"]):
+        i = st % 2
+        xs = [dev(g[f"x{i}_{j}"]) for j in range(3)]; ys = [dev(g[f"y{i}_{j}"]) for j in range(3)]
+        plan = m.set_window(xs[0].shape[1]).plan()
+        gout = torch.zeros(plan.NP, device="cuda")
+        loss, correct = step.step(xs, ys, grads_out=gout)
+        ref = sub(g, f"s{st}")
+        close(loss.cpu().numpy(), ref["losses"], 2e-5, "losses")
+        G = step._gbuf[:3 * plan.P].view(3, plan.P).t().cpu().numpy()
+        close(G, ref["G"], 5e-5, "G")
+        d = step.diag().cpu().numpy()
+        close(d[3:12].reshape(3, 3), ref["GTG"], 1e-4, "GTG")
+        # the device solve is exact; SLSQP stops at ftol 1e-6 -> compare weights loosely, objective strictly
+        import gait_oracle as O
+        f_ours = O.cagrad_objective(ref["GTG"], d[:3].astype(np.float64), meta["alpha"])
+        f_ref = O.cagrad_objective(ref["GTG"], ref["w"], meta["alpha"])
+        assert f_ours <= f_ref + 1e-6 * max(1.0, abs(f_ref)), (f_ours, f_ref)
+        got = grads_by_name(plan, gout)
+        for k, v in ref.items():
+            if not k.startswith("grad:"):
+                continue
+            nm = k[5:]
+            if nm not in got:
+                continue                      # aliases of the shared head
+            shared = next(p.group for p in plan.params if p.name == nm) == 0
+            close(got[nm], v, 3e-3 if shared else 5e-5, f"step {st} grad {nm}")
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+def reference_style_step(model, losses, opt, cagrad, private_twice):
+    """What step_cagrad_three (weargait_train.py:187-248) / process_batch (fbg_fog_train.py:146-152) do,
+    expressed with the public torch API only -- exercises the autograd bridge and the CAGrad drop-in."""
+    opt.zero_grad(set_to_none=True)
+    cagrad.backward(losses=losses, shared_parameters=list(model.get_shared_parameters()))
+    if private_twice:
+        groups = [model.walkway_parameters(), model.insole_parameters(), model.imu_parameters()]
+        for i, (L, priv) in enumerate(zip(losses, groups)):
+            gs = torch.autograd.grad(L, priv, retain_graph=i < 2, allow_unused=True)
+            for p, gg in zip(priv, gs):
+                if gg is not None:
+                    p.grad = gg if p.grad is None else p.grad.add_(gg)
+    opt.step()
+
+
+@pytest.mark.parametrize("name", ["wg_sync_gcl", "wg_async_ce", "wg_sync_classwt_nc"])
+def test_weargait_autograd_path_matches_reference(gk, name):
+    g = load_golden(name); meta = g["meta"]
+    m = wg_model(gk, g)
+    crit = wg_criteria(gk, meta)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    cag = gk.CAGrad(n_tasks=3, device=torch.device("cuda"), c=meta["alpha"])
+    for st in range(meta["steps"]):
+        i = st % 2
+        xs = [dev(g[f"x{i}_{j}"]) for j in range(3)]; ys = [dev(g[f"y{i}_{j}"]) for j in range(3)]
+        m.train()
+        lg = m(*xs)
+        L = [c(l, y) for c, l, y in zip(crit, lg, ys)]
+        ref = sub(g, f"s{st}")
+        close(torch.stack([l.detach() for l in L]).cpu().numpy(), ref["losses"], 2e-5, "losses")
+        reference_style_step(m, L, opt, cag, True)
+        named = dict(m.named_parameters())
+        for k, v in ref.items():
+            if k.startswith("grad:") and k[5:] in named:
+                nm = k[5:]
+                shared = any(named[nm] is p for p in m.get_shared_parameters())
+                close(named[nm].grad.cpu().numpy(), v, 3e-3 if shared else 5e-5, f"step {st} grad {nm}")
+        assert named["enc_i.ln1.weight"].grad is None and named["enc_i.ln1.bias"].grad is None
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+def fog_model(gk, g):
+    meta = g["meta"]; prm = meta["params"]
+    m = gk.MultiModalMultiTaskModel(
+        skeleton_input_dim=prm["skeleton_input_dim"], skeleton_output_dim=prm["skeleton_output_dim"],
+        sensor_in_channels=prm["sensor_in_channels"], sensor_out_channels=prm["sensor_out_channels"],
+        sensor_length=prm["sensor_length"], shared_out_channels=prm["shared_out_channels"], backbone_dim=prm["backbone_dim"],
+        taskhead_input_dim=prm["taskhead_input_dim"], num_classes=prm["num_classes"], use_norm=meta["use_nc"],
+        use_cosine=meta["use_nc"], synchronized_loading=meta["synchronized"])
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}, strict=True)
+    return m.cuda()
+
+
+def fog_criteria(gk, meta):
+    out = []
+    for c in (meta["sk_counts"], meta["se_counts"]):
+        wt = 1.0 / (torch.tensor(c, dtype=torch.float32) + 1e-8); w = (wt / wt.sum() * len(c)).cuda()
+        if meta["wm"] == "gcl":
+            out.append(gk.GCLLoss(cls_num_list=c, m=0.2, s=25.0, noise_mul=0.0, weight=None))
+        elif meta["wm"] == "ldam":
+            out.append(gk.LDAMLoss(cls_num_list=c, max_m=0.5, s=30.0, weight=w))
+        elif meta["wm"] == "class_wt":
+            out.append(gk.CrossEntropyLoss(weight=w))
+        else:
+            out.append(gk.CrossEntropyLoss())
+    return out
+
+
+@pytest.mark.parametrize("name", FOG_ALL)
+def test_fog_forward_matches_reference(gk, name):
+    g = load_golden(name)
+    m = fog_model(gk, g)
+    with torch.no_grad():
+        ls, lt = m(dev(g["sk0"]), dev(g["se0"]))
+    close(torch.stack([ls, lt]).cpu().numpy(), g["s0/logits"], 2e-5, "logits")
+
+
+@pytest.mark.parametrize("name", FOG_ASYNC)
+def test_fog_fused_step_matches_reference(gk, name):
+    g = load_golden(name); meta = g["meta"]
+    m = fog_model(gk, g)
+    step = gk.FusedTrainStep(m, fog_criteria(gk, meta), cagrad_c=meta["alpha"], private_mult=1.0)
+    for st in range(meta["steps"]):
+        i = st % 2
+        xs = [dev(g[f"sk{i}"]), dev(g[f"se{i}"])]; ys = [dev(g[f"ys{i}"]), dev(g[f"yt{i}"])]
+        plan = m.set_window(xs[0].shape[1]).plan()
+        gout = torch.zeros(plan.NP, device="cuda")
+        loss, correct = step.step(xs, ys, grads_out=gout)
+        ref = sub(g, f"s{st}")
+        close(loss.cpu().numpy(), ref["losses"], 2e-5, "losses")
+        assert correct.cpu().numpy().round().astype(int).tolist() == ref["correct"][:2].tolist()
+        got = grads_by_name(plan, gout)
+        for k, v in ref.items():
+            if k.startswith("grad:") and k[5:] in got:
+                nm = k[5:]
+                shared = next(p.group for p in plan.params if p.name == nm) == 0
+                close(got[nm], v, 3e-3 if shared else 5e-5, f"step {st} grad {nm}")
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+@pytest.mark.parametrize("name", ["fog_sync_gcl", "fog_sync_ce_nc", "fog_async_gcl"])
+def test_fog_autograd_path_matches_reference(gk, name):
+    """Sync FoG adds the symmetric-KL consistency term (fbg_fog_train.py:81-89,121-124), which couples the two
+    streams: it runs through the autograd bridge (forward kernels + per-task backward kernels)."""
+    import torch.nn.functional as F
+    g = load_golden(name); meta = g["meta"]
+    m = fog_model(gk, g)
+    crit = fog_criteria(gk, meta)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    cag = gk.CAGrad(n_tasks=2, device=torch.device("cuda"), c=meta["alpha"], max_norm=1.0)
+    for st in range(meta["steps"]):
+        i = st % 2
+        ls, lt = m(dev(g[f"sk{i}"]), dev(g[f"se{i}"]))
+        l1 = crit[0](ls, dev(g[f"ys{i}"])); l2 = crit[1](lt, dev(g[f"yt{i}"]))
+        if meta["synchronized"] and meta["wm"] == "gcl":
+            kl1 = F.kl_div(F.log_softmax(ls, 1), F.softmax(lt, 1), reduction="batchmean")
+            kl2 = F.kl_div(F.log_softmax(lt, 1), F.softmax(ls, 1), reduction="batchmean")
+            cons = kl1 + kl2
+            l1 = l1 + 0.5 * meta["cons_lambda"] * cons; l2 = l2 + 0.5 * meta["cons_lambda"] * cons
+        ref = sub(g, f"s{st}")
+        close(torch.stack([l1.detach(), l2.detach()]).cpu().numpy(), ref["losses"], 2e-5, "losses")
+        reference_style_step(m, [l1, l2], opt, cag, False)
+        named = dict(m.named_parameters())
+        shared_ids = {id(p) for p in m.get_shared_parameters()}
+        for k, v in ref.items():
+            if k.startswith("grad:"):
+                nm = k[5:]
+                close(named[nm].grad.cpu().numpy(), v, 3e-3 if id(named[nm]) in shared_ids else 5e-5, f"step {st} grad {nm}")
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+def test_cagrad_solver_vs_slsqp_corpus(gk):
+    """On-device exact simplex solve vs the reference's SLSQP answers (golden): never a worse objective,
+    combined gradient within SLSQP's own stopping slack."""
+    import gait_oracle as O
+    g = load_golden("cagrad_corpus")
+    cag = gk.CAGrad(n_tasks=3, device=torch.device("cuda"))
+    worst = 0.0
+    for G, gref, wref, (n, alpha) in zip(g["G"], g["g"], g["w"], g["n_alpha"]):
+        n = int(n); alpha = float(alpha)
+        Gd = dev(G[:, :n].T.copy())
+        out, diag = cag.cagrad_device(Gd, alpha=alpha, max_norm=0.0)
+        out = out.cpu().numpy() / n; d = diag.cpu().numpy()
+        A = (G[:, :n].T.astype(np.float32) @ G[:, :n].astype(np.float32))
+        f_ours = O.cagrad_objective(A, d[:n].astype(np.float64), alpha); f_ref = O.cagrad_objective(A, wref[:n], alpha)
+        assert f_ours <= f_ref + 1e-6 * max(1.0, abs(f_ref)), (f_ours, f_ref, d[:n], wref[:n])
+        rel = np.abs(out - gref).max() / max(np.abs(gref).max(), 1e-30)
+        worst = max(worst, rel)
+    assert worst < 5e-3, worst
+
+
+def test_masks_match_reference(gk):
+    g = load_golden("wg_masks")
+    m = gk.WearGaitThreeModal(synchronized=True)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}, strict=True)
+    m = m.cuda().eval()
+    xs = [dev(g[f"x{j}"]) for j in range(3)]; y = dev(g["y"])
+    for i, (nm, mask) in enumerate(zip(g["mask_names"], g["mask_table"])):
+        with torch.no_grad():
+            # (a) the reference's way: zero-filled tensors through the ordinary forward (weargait_train.py:355-382)
+            lg_a = m(*[x if u else torch.zeros_like(x) for x, u in zip(xs, mask)])
+            # (b) the mask flag consumed by the kernel (no zero tensors materialised)
+            lg_b = m(*xs, enabled=tuple(bool(u) for u in mask))
+        for a, b in zip(lg_a, lg_b):
+            assert torch.equal(a, b)
+        probs = [torch.softmax(l, 1) for l, u in zip(lg_b, mask) if u]
+        acc = 100.0 * float(((sum(probs) / len(probs)).argmax(1) == y).sum()) / y.numel()
+        assert abs(acc - float(g["acc_sync"][i])) < 1e-9, (nm, acc, g["acc_sync"][i])
+
+
+def test_fused_step_matches_oracle_random(gk):
+    """Seeded random batch at a size the oracle finishes in seconds (B=200, ragged last tile)."""
+    import gait_oracle as O
+    torch.manual_seed(3)
+    m = gk.WearGaitThreeModal(synchronized=False).cuda()
+    state = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    B = 201
+    xs, y = O.synth_weargait_batch(B, seed=9)
+    r = np.random.default_rng(1); ys = [y, r.permutation(y), r.permutation(y)]
+    counts = [[40, 90], [55, 60], [20, 30]]
+    crit = [gk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in counts]
+    step = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0)
+    p = O.canonical_params(state, False); bufs = {}
+    for it in range(2):
+        loss, correct = step.step([dev(x) for x in xs], [dev(v) for v in ys])
+        ex = O.weargait_train_step(p, bufs, [torch.from_numpy(x) for x in xs], [torch.from_numpy(v) for v in ys],
+                                   synchronized=False, wm="gcl", counts=counts, alpha=0.5)
+        close(loss.cpu().numpy(), ex["losses"], 5e-5, "loss")
+        ref_correct = [int((l.argmax(1) == torch.from_numpy(v)).sum()) for l, v in zip(ex["logits"], ys)]
+        assert correct.cpu().numpy().round().astype(int).tolist() == ref_correct
+    for k, v in m.state_dict().items():
+        if k in p:
+            close(v.cpu().numpy(), p[k].detach().numpy(), 2e-5, k)
+
+
+def test_data_path_matches_reference(gk):
+    import ctypes as C
+    g = load_golden("data_path")
+    L = gk.lib()
+    st = gk._lib.stream_handle
+    sids = [str(s) for s in g["sids"]]; train = [str(s) for s in g["train"]]
+    # A2: statistics over the train subjects, then normalisation, on the device
+    for mod, D, lo in (("insole", 13, 0), ("imu", 24, 13)):
+        acc = torch.zeros(3 * D, dtype=torch.float64, device="cuda")
+        for s in train:
+            x = dev(g[f"raw/{s}/{mod}"])
+            gk._lib.check(L.gaitk_stats_accumulate(x.data_ptr(), x.shape[0], D, acc.data_ptr(), st()))
+        mean = torch.empty(D, dtype=torch.float64, device="cuda"); std = torch.empty_like(mean)
+        gk._lib.check(L.gaitk_stats_finalize(acc.data_ptr(), D, mean.data_ptr(), std.data_ptr(), st()))
+        np.testing.assert_allclose(mean.cpu().numpy(), g["stat_mean"][lo:lo + D], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(std.cpu().numpy(), g["stat_std"][lo:lo + D], rtol=1e-12)
+        # normalise with the REFERENCE statistics -> float32 windows must be bit exact
+        mean = dev(g["stat_mean"][lo:lo + D].copy()); std = dev(g["stat_std"][lo:lo + D].copy())
+        for split in ("train", "test"):
+            keys = [str(k) for k in g[f"{split}_keys/{mod}"]]
+            for s in sids:
+                mine = [k for k in keys if k.startswith(s + "|")]
+                if not mine:
+                    continue
+                x = dev(g[f"raw/{s}/{mod}"])
+                out = torch.empty(x.shape, dtype=torch.float32, device="cuda")
+                gk._lib.check(L.gaitk_normalize_frames(x.data_ptr(), x.shape[0], D, mean.data_ptr(), std.data_ptr(),
+                                                       out.data_ptr(), st()))
+                nwin = int(L.gaitk_window_indices(x.shape[0], 64, 64, None, 0))
+                assert nwin == len(mine)
+                starts = torch.arange(nwin, dtype=torch.int64, device="cuda") * 64
+                win = torch.empty(nwin, 64, D, dtype=torch.float32, device="cuda")
+                gk._lib.check(L.gaitk_window_gather(out.data_ptr(), D, starts.data_ptr(), nwin, 64, 1, win.data_ptr(), st()))
+                for wid in range(nwin):
+                    ref = g[f"{split}_win/{mod}"][keys.index(f"{s}|{mod}|{wid}")].astype(np.float32)
+                    assert np.array_equal(win[wid].cpu().numpy(), ref), (s, mod, wid)
+    # masked gather writes zeros
+    z = torch.ones(2, 64, 13, device="cuda"); fr = torch.rand(200, 13, device="cuda")
+    ws = torch.tensor([0, 64], dtype=torch.int64, device="cuda")
+    gk._lib.check(L.gaitk_window_gather(fr.data_ptr(), 13, ws.data_ptr(), 2, 64, 0, z.data_ptr(), st()))
+    assert float(z.abs().sum()) == 0.0
+    # A5: FoG clip preparation, float32 bit exact
+    for i in range(3):
+        pose = g[f"fog_pose_in{i}"]; sens = g[f"fog_sens_in{i}"]
+        o = torch.empty(1, 101, 21, device="cuda"); cs = torch.zeros(1, dtype=torch.int64, device="cuda")
+        cl = torch.tensor([pose.shape[0]], dtype=torch.int64, device="cuda")
+        gk._lib.check(L.gaitk_fog_prepare_pose(dev(pose).data_ptr(), cs.data_ptr(), cl.data_ptr(), 1, 7, 101, o.data_ptr(), st()))
+        assert np.array_equal(o[0].cpu().numpy(), g[f"fog_pose_out{i}"])
+        o2 = torch.empty(1, 426, 6, device="cuda"); cl2 = torch.tensor([sens.shape[0]], dtype=torch.int64, device="cuda")
+        gk._lib.check(L.gaitk_fog_prepare_sensor(dev(sens).data_ptr(), cs.data_ptr(), cl2.data_ptr(), 1, 6, 426, o2.data_ptr(), st()))
+        assert np.array_equal(o2[0].cpu().numpy(), g[f"fog_sens_out{i}"])
+
+
+def test_fused_gather_equals_dense(gk):
+    """win_start path (windows read straight from the frame store) == materialised batch."""
+    torch.manual_seed(0)
+    m = gk.WearGaitThreeModal().cuda()
+    N = 5000
+    stores = [torch.rand(N, 2, device="cuda"), torch.randn(N, 13, device="cuda"), torch.randn(N, 24, device="cuda")]
+    B = 37
+    ws = (torch.randperm(N // 64, device="cuda")[:B] * 64).to(torch.int64)
+    dense = [torch.stack([s[int(w):int(w) + 64] for w in ws.cpu()]) for s in stores]
+    m.set_window(64)
+    a = m.plan().forward(m.flat_params(), dense)
+    b = m.plan().forward(m.flat_params(), stores, win_start=[ws, ws, ws])
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
+def test_data_parallel_shards_add_up(gk):
+    """Two half-batches with global denominators reduce (sum of gbuf) to the full-batch step: the
+    property the NCCL all-reduce relies on."""
+    import gait_oracle as O
+    torch.manual_seed(1)
+    m = gk.WearGaitThreeModal().cuda()
+    B = 256
+    xs, y = O.synth_weargait_batch(B, seed=4)
+    xs = [dev(x) for x in xs]; y = dev(y)
+    w = torch.tensor([1.7, 0.3], device="cuda")
+    crit = [gk.GCLLoss(cls_num_list=[30, 70], m=0.2, s=25, noise_mul=0.0, weight=w) for _ in range(3)]
+    step = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, process_group=False)
+    plan = m.set_window(64).plan()
+    g_full = torch.zeros(plan.NP, device="cuda")
+    step.step(xs, [y] * 3, update=False, grads_out=g_full)
+    full = step._gbuf.clone()
+    acc = torch.zeros_like(full)
+    for h in range(2):
+        sl = slice(h * B // 2, (h + 1) * B // 2)
+        step.step([x[sl].contiguous() for x in xs], [y[sl].contiguous()] * 3, ys_global=[y] * 3, update=False,
+                  grads_out=torch.zeros(plan.NP, device="cuda"))
+        acc += step._gbuf
+    close(acc.cpu().numpy(), full.cpu().numpy(), 2e-5, "gbuf")

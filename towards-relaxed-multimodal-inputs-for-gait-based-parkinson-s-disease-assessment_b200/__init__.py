@@ -1,0 +1,13 @@
+"""gaitk -- B200 (sm_100a) implementation of the gait training hot path behind the reference's own
+module API.  See DESIGN.md / INTEGRATION.md at the repository root."""
+from . import _lib
+from ._lib import GaitkError, lib
+from .plan import Plan, FlatParamModule
+from .weargait_encoders import WearGaitThreeModal
+from .feature_encoder import MultiModalMultiTaskModel
+from .classification_losses import GCLLoss, LDAMLoss, CrossEntropyLoss, make_loss_desc, criterion_spec
+from .multitask_weighting import CAGrad
+from .fused_step import FusedTrainStep
+
+__all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "MultiModalMultiTaskModel",
+           "GCLLoss", "LDAMLoss", "CrossEntropyLoss", "make_loss_desc", "criterion_spec", "CAGrad", "FusedTrainStep"]

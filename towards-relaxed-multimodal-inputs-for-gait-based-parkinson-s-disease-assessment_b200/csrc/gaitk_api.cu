@@ -1,0 +1,725 @@
+// gaitk_api.cu -- libgaitk.so: plan, parameter layout, launch geometry and the C-ABI of include/gaitk.h.
+// No torch headers, no allocation or synchronisation inside any entry (CUDA-graph capturable).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/gaitk.h"
+#include "stream_kernel.cuh"
+#include "update_kernels.cuh"
+
+using namespace gaitk;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail((int)e_, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+#define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail((int)e_, "kernel launch: %s", cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------------------------------ plan
+struct ParamInfo {
+    std::string name; long long off; int numel; int group; int dims[4]; int shared_off;
+};
+typedef void (*StreamKernelFn)(const StreamArgs, const SmemPlan);
+
+struct StreamPlan {
+    int enc, CIN, T_in, T, W, rows_in, rows, halo, RBi, RB, pool_sensor;
+    int H, C, S, NFL, KT1, skip_identity;
+    StreamKernelFn fn;
+    SmemPlan sp; GradOff go; int NGP; size_t smem_bytes; int ctas_per_sm;
+    int p_w1, p_b1, p_w2, p_b2, p_wsk, p_bsk, p_lng, p_lnb, p_hng, p_hnb, p_hw, p_hb;   // param indices (-1 = none)
+    int nseg; Seg seg[MAX_SEG];
+};
+
+struct gaitk_plan {
+    gaitk_model_desc d; int device; int sm_count;
+    std::vector<ParamInfo> params; long long NP; int P;
+    int n_streams; StreamPlan st[GAITK_MAX_STREAMS];
+    int p_wbb, p_bbb;
+    int NF;
+};
+
+static int add_param(gaitk_plan* pl, const std::string& name, int group, int d0, int d1 = 0, int d2 = 0) {
+    ParamInfo p; p.name = name; p.off = pl->NP; p.group = group;
+    p.dims[0] = d0; p.dims[1] = d1; p.dims[2] = d2; p.dims[3] = 0;
+    p.numel = d0 * (d1 ? d1 : 1) * (d2 ? d2 : 1);
+    p.shared_off = -1;
+    if (group == 0) { p.shared_off = pl->P; pl->P += p.numel; }
+    pl->NP += p.numel;
+    pl->params.push_back(p);
+    return (int)pl->params.size() - 1;
+}
+
+// kernel instantiations -------------------------------------------------------------------
+template <class Cfg> static StreamKernelFn kfn() { return &stream_kernel<Cfg>; }
+
+struct KernelKey { int enc, CIN, KT1, H, C, S, NFL; };
+static StreamKernelFn find_kernel(const KernelKey& k) {
+#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_) \
+        return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
+    // WearGait defaults (weargait_train.py:655-673): C=12, H=24, S=16, bdim=8
+    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
+    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
+    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
+    // FoG (configs.py:17-31) and FBG (:2-16)
+    GK_CASE(ENC_LINEAR_LN_RELU, 21, 1, 0, 6, 16, 4)
+    GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)
+    GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
+    GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
+#undef GK_CASE
+    return nullptr;
+}
+
+static int round_rb(int rows, int halo) {          // rows per chunk, == 1 (mod 8): conflict-free chunk planes
+    int rb = rows + 2 * halo;
+    while (rb % 8 != 1) ++rb;
+    return rb;
+}
+
+static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, int T_in, int T, int pool_sensor) {
+    StreamPlan& sp = pl->st[s];
+    const gaitk_model_desc& d = pl->d;
+    sp.enc = enc; sp.CIN = CIN; sp.KT1 = KT1; sp.H = H; sp.C = d.enc_out_ch; sp.S = d.shared_out_ch;
+    sp.T_in = T_in; sp.T = T; sp.pool_sensor = pool_sensor;
+    sp.skip_identity = (enc == ENC_INSOLE && H == sp.C);
+    const int NF = d.backbone_dim * d.shared_out_ch;
+    if (NF % 32 != 0 || NF > 512) return fail(GAITK_E_SHAPE, "backbone_dim*shared_out_ch = %d must be a multiple of 32 (<= 512)", NF);
+    if (sp.S % 4 != 0) return fail(GAITK_E_SHAPE, "shared_out_ch must be a multiple of 4");
+    sp.NFL = NF / 32;
+    const int Tmax = std::max(T, T_in);
+    sp.W = (pool_sensor || Tmax > NT / 2) ? 1 : std::min(WMAX, NT / Tmax);
+    sp.rows = T * sp.W; sp.rows_in = T_in * sp.W; sp.halo = 2 * sp.W;
+    sp.RB = round_rb(sp.rows, sp.halo); sp.RBi = round_rb(sp.rows_in, sp.halo);
+    KernelKey key = {enc, CIN, KT1, H, sp.C, sp.S, sp.NFL};
+    sp.fn = find_kernel(key);
+    if (!sp.fn)
+        return fail(GAITK_E_SHAPE, "no sm_100a kernel instantiated for stream %d (enc=%d Cin=%d k=%d H=%d C=%d S=%d NF=%d); "
+                    "supported: WearGait C=12/S=16/bdim=8, FoG and FBG defaults", s, enc, CIN, KT1, H, sp.C, sp.S, NF);
+    // ---- shared memory plan (floats)
+    const int CI4 = (CIN + 3) / 4, C4 = (sp.C + 3) / 4, CP = C4 * 4, H4 = (H + 3) / 4, S4 = sp.S / 4;
+    const int O1 = (enc == ENC_INSOLE) ? H4 * 4 : CP;
+    SmemPlan& m = sp.sp; memset(&m, 0, sizeof(m));
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
+    m.X = take(CI4 * sp.RBi * 4);
+    if (enc == ENC_INSOLE) { m.HA = take(H4 * sp.RB * 4); m.D1 = take(H4 * sp.RB * 4); }
+    m.XH = take(C4 * sp.RB * 4);
+    if (enc == ENC_CONV_GELU_LN || enc == ENC_INSOLE) m.D = take(C4 * sp.RB * 4);
+    m.F = take(C4 * sp.RB * 4);
+    m.RSTD = take(sp.RB);
+    m.Z = take(S4 * sp.RB * 4);
+    if (enc == ENC_CONV_POOL) m.A = take(C4 * sp.RBi * 4);
+    m.W1F = take(KT1 * CI4 * 4 * O1); m.B1 = take(O1);
+    if (enc == ENC_INSOLE) { m.W2F = take(3 * H4 * 4 * CP); m.B2 = take(CP); m.W2D = take(3 * CP * H4 * 4); }
+    m.LNG = take(CP); m.LNB = take(CP);
+    m.WBF = take(3 * CP * sp.S); m.BB = take(sp.S); m.WBD = take(3 * sp.S * CP);
+    m.HW = take(KMAX * NF); m.HB = take(KMAX); m.HNG = take(NF); m.HNB = take(NF); m.INW = take(KMAX);
+    m.P = take(WMAX * NF); m.DP = take(WMAX * NF); m.LOGIT = take(WMAX * KMAX);
+    m.BINS = take(2 * d.backbone_dim + 4 * T + 2 * T_in + 8);
+    int nblk_max = std::max(std::max(KT1 * CI4 * (O1 / 4), 3 * C4 * S4), enc == ENC_INSOLE ? 3 * H4 * C4 : 0);
+    m.STAGE = take(16 * std::max(std::max(NF, 256), std::max(nblk_max, NT)));
+    m.total = o;
+    sp.smem_bytes = (size_t)o * sizeof(float);
+    if (sp.smem_bytes > 227 * 1024)
+        return fail(GAITK_E_SHAPE, "stream %d needs %zu B of shared memory (> 227 KB)", s, sp.smem_bytes);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)sp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_bytes));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)sp.fn, NT, sp.smem_bytes));
+    if (occ < 1) return fail(GAITK_E_SHAPE, "stream %d kernel does not fit on an SM", s);
+    sp.ctas_per_sm = occ;
+    return 0;
+}
+
+// stream-local gradient layout + reduce segments
+static void layout_stream_grads(gaitk_plan* pl, int s) {
+    StreamPlan& sp = pl->st[s];
+    GradOff& go = sp.go; memset(&go, 0xff, sizeof(go));     // all -1
+    int o = 0; sp.nseg = 0;
+    auto seg = [&](int pidx, int& field) {
+        if (pidx < 0) { field = -1; return; }
+        const ParamInfo& p = pl->params[pidx];
+        field = o;
+        Seg sg; sg.src = o; sg.len = p.numel; sg.shared_off = p.shared_off; sg.param_off = (int)p.off;
+        sp.seg[sp.nseg++] = sg;
+        o += (p.numel + 3) / 4 * 4;
+    };
+    seg(sp.p_w1, go.w1); seg(sp.p_b1, go.b1); seg(sp.p_w2, go.w2); seg(sp.p_b2, go.b2);
+    seg(sp.p_wsk, go.wsk); seg(sp.p_bsk, go.bsk); seg(sp.p_lng, go.lng); seg(sp.p_lnb, go.lnb);
+    seg(pl->p_wbb, go.wbb); seg(pl->p_bbb, go.bbb);
+    seg(sp.p_hng, go.hng); seg(sp.p_hnb, go.hnb); seg(sp.p_hw, go.hw); seg(sp.p_hb, go.hb);
+    go.total = o;
+    sp.NGP = o + 4;
+}
+
+extern "C" int gaitk_version(void) { return GAITK_VERSION; }
+extern "C" const char* gaitk_last_error(void) { return g_err; }
+
+extern "C" int gaitk_plan_create(const gaitk_model_desc* desc, int device, gaitk_plan** out) {
+    if (!desc || !out) return fail(GAITK_E_BADARG, "null argument");
+    *out = nullptr;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GAITK_E_ARCH, "device %d is sm_%d%d; libgaitk is built for sm_100a only (no fallback path)", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    const gaitk_model_desc& d = *desc;
+    if (d.num_classes < 2 || d.num_classes > KMAX) return fail(GAITK_E_SHAPE, "num_classes must be in [2,%d]", KMAX);
+    if (d.T < 1 || d.enc_out_ch < 1 || d.shared_out_ch < 1 || d.backbone_dim < 1) return fail(GAITK_E_SHAPE, "bad dims");
+    if (d.backbone_dim > d.T) return fail(GAITK_E_SHAPE, "backbone_dim > T");
+    gaitk_plan* pl = new gaitk_plan();
+    pl->d = d; pl->device = device; pl->sm_count = prop.multiProcessorCount; pl->NP = 0; pl->P = 0;
+    const int C = d.enc_out_ch, S = d.shared_out_ch, K = d.num_classes, NF = d.backbone_dim * S;
+    pl->NF = NF;
+    const bool norm = d.use_norm || d.use_cosine, cosn = d.use_cosine != 0, sync = d.synchronized != 0;
+    int rc = 0;
+    auto head = [&](const std::string& pre, int group, StreamPlan& sp) {
+        sp.p_hng = sp.p_hnb = sp.p_hb = -1;
+        if (norm) { sp.p_hng = add_param(pl, pre + "norm.weight", group, NF); sp.p_hnb = add_param(pl, pre + "norm.bias", group, NF); }
+        sp.p_hw = add_param(pl, pre + "fc.weight", group, K, NF);
+        if (!cosn) sp.p_hb = add_param(pl, pre + "fc.bias", group, K);
+    };
+    for (int s = 0; s < GAITK_MAX_STREAMS; ++s) {
+        StreamPlan& sp = pl->st[s];
+        sp.p_w1 = sp.p_b1 = sp.p_w2 = sp.p_b2 = sp.p_wsk = sp.p_bsk = sp.p_lng = sp.p_lnb = sp.p_hng = sp.p_hnb = sp.p_hw = sp.p_hb = -1;
+    }
+    if (d.family == GAITK_FAMILY_WEARGAIT) {
+        // named_parameters() order of WearGaitThreeModal (weargait_encoders.py:121-141)
+        pl->n_streams = 3;
+        const int H = 2 * C;
+        StreamPlan &w = pl->st[0], &i = pl->st[1], &m = pl->st[2];
+        w.p_w1 = add_param(pl, "enc_w.conv.weight", 1, C, 2, 3); w.p_b1 = add_param(pl, "enc_w.conv.bias", 1, C);
+        w.p_lng = add_param(pl, "enc_w.ln.weight", 1, C); w.p_lnb = add_param(pl, "enc_w.ln.bias", 1, C);
+        i.p_w1 = add_param(pl, "enc_i.conv1.weight", 2, H, 13, 5); i.p_b1 = add_param(pl, "enc_i.conv1.bias", 2, H);
+        add_param(pl, "enc_i.ln1.weight", -1, H); add_param(pl, "enc_i.ln1.bias", -1, H);     // constructed, never used (:81,:93-101)
+        i.p_w2 = add_param(pl, "enc_i.conv2.weight", 2, C, H, 3); i.p_b2 = add_param(pl, "enc_i.conv2.bias", 2, C);
+        i.p_lng = add_param(pl, "enc_i.ln2.weight", 2, C); i.p_lnb = add_param(pl, "enc_i.ln2.bias", 2, C);
+        i.p_wsk = add_param(pl, "enc_i.skip.weight", 2, C, H, 1); i.p_bsk = add_param(pl, "enc_i.skip.bias", 2, C);
+        m.p_w1 = add_param(pl, "enc_m.conv.weight", 3, C, 24, 3); m.p_b1 = add_param(pl, "enc_m.conv.bias", 3, C);
+        m.p_lng = add_param(pl, "enc_m.ln.weight", 3, C); m.p_lnb = add_param(pl, "enc_m.ln.bias", 3, C);
+        pl->p_wbb = add_param(pl, "backbone.conv.weight", 0, S, C, 3); pl->p_bbb = add_param(pl, "backbone.conv.bias", 0, S);
+        if (sync) {
+            head("head_w.", 0, w);
+            i.p_hng = m.p_hng = w.p_hng; i.p_hnb = m.p_hnb = w.p_hnb; i.p_hw = m.p_hw = w.p_hw; i.p_hb = m.p_hb = w.p_hb;
+        } else {
+            head("head_w.", 1, w); head("head_i.", 2, i); head("head_m.", 3, m);
+        }
+        if ((rc = plan_stream(pl, 0, ENC_CONV_GELU_LN, 2, 3, 0, d.T, d.T, 0))) { delete pl; return rc; }
+        if ((rc = plan_stream(pl, 1, ENC_INSOLE, 13, 5, H, d.T, d.T, 0))) { delete pl; return rc; }
+        if ((rc = plan_stream(pl, 2, ENC_CONV_GELU_LN, 24, 3, 0, d.T, d.T, 0))) { delete pl; return rc; }
+    } else if (d.family == GAITK_FAMILY_FOG) {
+        // named_parameters() order of MultiModalMultiTaskModel (feature_encoder.py:175-216)
+        pl->n_streams = 2;
+        StreamPlan &k = pl->st[0], &e = pl->st[1];
+        k.p_w1 = add_param(pl, "skeleton_encoder.fc1.weight", 1, C, d.skel_in_dim); k.p_b1 = add_param(pl, "skeleton_encoder.fc1.bias", 1, C);
+        k.p_lng = add_param(pl, "skeleton_encoder.ln1.weight", 1, C); k.p_lnb = add_param(pl, "skeleton_encoder.ln1.bias", 1, C);
+        e.p_w1 = add_param(pl, "sensor_encoder.conv1d.weight", 2, C, d.sensor_in_ch, 3); e.p_b1 = add_param(pl, "sensor_encoder.conv1d.bias", 2, C);
+        pl->p_wbb = add_param(pl, "backbone.conv1d.weight", 0, S, C, 3); pl->p_bbb = add_param(pl, "backbone.conv1d.bias", 0, S);
+        if (sync) {
+            head("task_head_shared.", 0, k);
+            e.p_hng = k.p_hng; e.p_hnb = k.p_hnb; e.p_hw = k.p_hw; e.p_hb = k.p_hb;
+        } else {
+            head("task_head_skel.", 1, k); head("task_head_sensor.", 2, e);
+        }
+        if (d.sensor_out_len != d.T) { delete pl; return fail(GAITK_E_SHAPE, "sensor_out_len (%d) must equal pose length T (%d)", d.sensor_out_len, d.T); }
+        if ((rc = plan_stream(pl, 0, ENC_LINEAR_LN_RELU, d.skel_in_dim, 1, 0, d.T, d.T, 0))) { delete pl; return rc; }
+        // SensorEncoder pools only when the input length equals sensor_length (feature_encoder.py:55); the
+        // backbone then sees sensor_out_len rows.  (A sensor clip of any other length is not produced by the
+        // reference pipeline: pad_or_trim fixes it to sensor_length.)
+        if ((rc = plan_stream(pl, 1, ENC_CONV_POOL, d.sensor_in_ch, 3, 0, d.sensor_len, d.sensor_out_len, 1))) { delete pl; return rc; }
+    } else {
+        delete pl; return fail(GAITK_E_BADARG, "unknown family %d", d.family);
+    }
+    if ((int)pl->params.size() > MAX_PARAMS) { delete pl; return fail(GAITK_E_SHAPE, "too many parameters"); }
+    for (int s = 0; s < pl->n_streams; ++s) layout_stream_grads(pl, s);
+    *out = pl;
+    return 0;
+}
+
+extern "C" void gaitk_plan_destroy(gaitk_plan* plan) { delete plan; }
+extern "C" int gaitk_param_count(const gaitk_plan* p) { return p ? (int)p->params.size() : 0; }
+extern "C" int64_t gaitk_param_total(const gaitk_plan* p) { return p ? p->NP : 0; }
+extern "C" int64_t gaitk_shared_total(const gaitk_plan* p) { return p ? p->P : 0; }
+extern "C" int gaitk_num_streams(const gaitk_plan* p) { return p ? p->n_streams : 0; }
+extern "C" int gaitk_stream_in_dim(const gaitk_plan* p, int s) { return (p && s >= 0 && s < p->n_streams) ? p->st[s].CIN : 0; }
+extern "C" int gaitk_stream_in_len(const gaitk_plan* p, int s) { return (p && s >= 0 && s < p->n_streams) ? p->st[s].T_in : 0; }
+extern "C" int64_t gaitk_gbuf_floats(const gaitk_plan* p) { return p ? (int64_t)MAXT * p->P + p->NP + 8 : 0; }
+
+extern "C" int gaitk_param_info(const gaitk_plan* p, int index, char* name, size_t cap, int64_t* offset, int64_t* numel,
+                                int32_t* group, int32_t* dims) {
+    if (!p || index < 0 || index >= (int)p->params.size()) return fail(GAITK_E_BADARG, "bad parameter index");
+    const ParamInfo& q = p->params[index];
+    if (name && cap) { strncpy(name, q.name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (offset) *offset = q.off;
+    if (numel) *numel = q.numel;
+    if (group) *group = q.group;
+    if (dims) for (int i = 0; i < 4; ++i) dims[i] = q.dims[i];
+    return 0;
+}
+
+static int stream_grid(const gaitk_plan* pl, const StreamPlan& sp, int B) {
+    const int ntiles = (B + sp.W - 1) / sp.W;
+    return std::max(1, std::min(ntiles, pl->sm_count * sp.ctas_per_sm));
+}
+static size_t stream_ws_floats(const gaitk_plan* pl, const StreamPlan& sp, int B) {
+    return (size_t)stream_grid(pl, sp, B) * sp.NGP;
+}
+extern "C" size_t gaitk_workspace_bytes(const gaitk_plan* pl, int B) {
+    if (!pl) return 0;
+    size_t mx = 0;
+    for (int s = 0; s < pl->n_streams; ++s) mx = std::max(mx, stream_ws_floats(pl, pl->st[s], B));
+    return mx * sizeof(float) + 256;
+}
+
+static const float* pp(const float* params, const gaitk_plan* pl, int idx) { return idx < 0 ? nullptr : params + pl->params[idx].off; }
+
+static void fill_args(const gaitk_plan* pl, int s, const float* params, const float* x, const int64_t* ws, int B,
+                      int mode, int zero_input, StreamArgs& a) {
+    const StreamPlan& sp = pl->st[s];
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.win_start = (const long long*)ws; a.B = B; a.T_in = sp.T_in; a.T = sp.T; a.W = sp.W;
+    a.bdim = pl->d.backbone_dim; a.K = pl->d.num_classes; a.NF = pl->NF;
+    a.rows_in = sp.rows_in; a.rows = sp.rows; a.halo = sp.halo; a.RBi = sp.RBi; a.RB = sp.RB;
+    a.mode = mode; a.zero_input = zero_input; a.pool_sensor = sp.pool_sensor;
+    a.w1 = pp(params, pl, sp.p_w1); a.b1 = pp(params, pl, sp.p_b1); a.w2 = pp(params, pl, sp.p_w2); a.b2 = pp(params, pl, sp.p_b2);
+    a.wsk = pp(params, pl, sp.p_wsk); a.bsk = pp(params, pl, sp.p_bsk); a.lng = pp(params, pl, sp.p_lng); a.lnb = pp(params, pl, sp.p_lnb);
+    a.wbb = pp(params, pl, pl->p_wbb); a.bbb = pp(params, pl, pl->p_bbb);
+    a.hng = pp(params, pl, sp.p_hng); a.hnb = pp(params, pl, sp.p_hnb); a.hw = pp(params, pl, sp.p_hw); a.hb = pp(params, pl, sp.p_hb);
+    a.head_norm = sp.p_hng >= 0; a.head_cos = pl->d.use_cosine != 0; a.skip_identity = sp.skip_identity;
+    a.scale = 1.f; for (int k = 0; k < KMAX; ++k) { a.margin[k] = 0.f; a.cls_w[k] = 1.f; }
+    a.go = sp.go; a.NGP = sp.NGP;
+}
+
+static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int grid, cudaStream_t st) {
+    const StreamPlan& sp = pl->st[s];
+    sp.fn<<<grid, NT, sp.smem_bytes, st>>>(a, sp.sp);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gaitk_forward(gaitk_plan* pl, const float* params, const float* const* x, const int64_t* const* win_start,
+                             int B, uint32_t enabled_mask, float* const* logits, int dtype, void* stream) {
+    if (!pl || !params || !x || !logits) return fail(GAITK_E_BADARG, "null argument");
+    if (dtype != GAITK_DTYPE_F32) return fail(GAITK_E_DTYPE, "dtype %d not available in this build", dtype);
+    if (B <= 0) return 0;
+    for (int s = 0; s < pl->n_streams; ++s) {
+        if (!logits[s]) continue;
+        StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_FWD, !(enabled_mask & (1u << s)), a);
+        a.logits = logits[s];
+        int rc = launch_stream(pl, s, a, stream_grid(pl, pl->st[s], B), (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static void set_loss(StreamArgs& a, const gaitk_loss_desc& L, int K) {
+    a.scale = L.scale; a.nan_degenerate = L.nan_if_degenerate;
+    for (int k = 0; k < KMAX; ++k) { a.margin[k] = k < K ? L.margin[k] : 0.f; a.cls_w[k] = k < K ? L.cls_weight[k] : 0.f; }
+}
+
+static int launch_reduce(const gaitk_plan* pl, int s, const float* partial, int grid, float* gbuf, int task, float mult,
+                         int stat_slot, cudaStream_t st) {
+    const StreamPlan& sp = pl->st[s];
+    ReduceArgs R; memset(&R, 0, sizeof(R));
+    R.partial = partial; R.grid = grid; R.NGP = sp.NGP; R.NG = sp.go.total; R.nseg = sp.nseg;
+    for (int i = 0; i < sp.nseg; ++i) R.seg[i] = sp.seg[i];
+    R.gbuf = gbuf; R.P = pl->P; R.NP = pl->NP; R.task = task; R.private_mult = mult; R.stat_slot = stat_slot;
+    const int n = R.NG + 2;
+    reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(R);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float* const* x, const int64_t* const* win_start,
+                                const int64_t* const* y, int B, const gaitk_loss_desc* loss, const float* const* logit_off,
+                                const float* denom, uint32_t enabled_mask, uint32_t task_mask, float private_mult,
+                                float consistency_lambda, float* const* logits, float* gbuf, void* workspace,
+                                size_t workspace_bytes, int dtype, void* stream) {
+    if (!pl || !params || !x || !y || !loss || !denom || !gbuf || !workspace) return fail(GAITK_E_BADARG, "null argument");
+    if (dtype != GAITK_DTYPE_F32) return fail(GAITK_E_DTYPE, "dtype %d not available in this build", dtype);
+    if (consistency_lambda != 0.f)
+        return fail(GAITK_E_BADARG, "consistency term couples the streams: use gaitk_forward + gaitk_backward per task");
+    if (workspace_bytes < gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(gbuf, 0, (size_t)gaitk_gbuf_floats(pl) * sizeof(float), st));
+    if (B <= 0) return 0;
+    for (int s = 0; s < pl->n_streams; ++s) {
+        if (!(task_mask & (1u << s))) continue;
+        StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_FUSED, !(enabled_mask & (1u << s)), a);
+        set_loss(a, loss[s], pl->d.num_classes);
+        a.y = (const long long*)y[s]; a.denom = denom + s;
+        a.logit_off = logit_off ? logit_off[s] : nullptr;
+        a.logits = logits ? logits[s] : nullptr;
+        a.partial = (float*)workspace;
+        const int grid = stream_grid(pl, pl->st[s], B);
+        int rc = launch_stream(pl, s, a, grid, st);
+        if (rc) return rc;
+        if ((rc = launch_reduce(pl, s, (const float*)workspace, grid, gbuf, s, private_mult, s, st))) return rc;
+    }
+    return 0;
+}
+
+static int accumulate_grads(const gaitk_plan* pl, const float* gbuf, float* grads, cudaStream_t st);
+
+extern "C" int gaitk_backward(gaitk_plan* pl, const float* params, const float* const* x, const int64_t* const* win_start,
+                              int B, uint32_t enabled_mask, const float* const* dlogits, float* grads, void* workspace,
+                              size_t workspace_bytes, int dtype, void* stream) {
+    if (!pl || !params || !x || !dlogits || !grads || !workspace) return fail(GAITK_E_BADARG, "null argument");
+    if (dtype != GAITK_DTYPE_F32) return fail(GAITK_E_DTYPE, "dtype %d not available in this build", dtype);
+    // scratch: [gbuf | partials]
+    const size_t gb = (size_t)gaitk_gbuf_floats(pl) * sizeof(float);
+    if (workspace_bytes < gb + gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* gbuf = (float*)workspace; float* partial = (float*)((char*)workspace + ((gb + 255) / 256) * 256);
+    CUDA_TRY(cudaMemsetAsync(gbuf, 0, gb, st));
+    if (B <= 0) return 0;
+    for (int s = 0; s < pl->n_streams; ++s) {
+        if (!dlogits[s]) continue;
+        StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_BWD_EXT, !(enabled_mask & (1u << s)), a);
+        a.dlogits_ext = dlogits[s]; a.partial = partial;
+        const int grid = stream_grid(pl, pl->st[s], B);
+        int rc = launch_stream(pl, s, a, grid, st);
+        if (rc) return rc;
+        // all shared contributions land in task column 0 with unit coefficient
+        if ((rc = launch_reduce(pl, s, partial, grid, gbuf, 0, 1.0f, -1, st))) return rc;
+    }
+    // grads += [shared from G column 0 | private]
+    return accumulate_grads(pl, gbuf, grads, st);
+}
+
+__global__ void accumulate_grads_kernel(const float* gbuf, float* grads, const UpdateArgs U) {
+    const float* G = gbuf; const float* PG = gbuf + (size_t)MAXT * U.P;
+    for (int ip = 0; ip < U.nparams; ++ip) {
+        const ParamSeg s = U.ps[ip];
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.numel; e += gridDim.x * blockDim.x)
+            grads[s.off + e] += s.shared_off >= 0 ? G[s.shared_off + e] : PG[s.off + e];
+    }
+}
+static void fill_param_segs(const gaitk_plan* pl, UpdateArgs& U, const uint8_t* has_grad) {
+    U.nparams = (int)pl->params.size(); U.P = pl->P; U.NP = pl->NP;
+    for (int i = 0; i < U.nparams; ++i) {
+        const ParamInfo& p = pl->params[i];
+        U.ps[i].off = p.off; U.ps[i].numel = p.numel; U.ps[i].shared_off = p.shared_off;
+        U.ps[i].has_grad = has_grad ? (has_grad[i] != 0) : (p.group >= 0);
+    }
+}
+static int accumulate_grads(const gaitk_plan* pl, const float* gbuf, float* grads, cudaStream_t st) {
+    UpdateArgs U; memset(&U, 0, sizeof(U)); fill_param_segs(pl, U, nullptr);
+    accumulate_grads_kernel<<<8, 256, 0, st>>>(gbuf, grads, U);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gaitk_step_update(gaitk_plan* pl, float* params, float* momentum, const float* gbuf, uint32_t task_mask,
+                                 float cagrad_c, float max_norm, float lr, float mom, float weight_decay, float* grads_out,
+                                 float* diag, void* stream) {
+    if (!pl || !gbuf) return fail(GAITK_E_BADARG, "null argument");
+    const bool do_sgd = params && momentum;
+    if (!do_sgd && !grads_out) return fail(GAITK_E_BADARG, "nothing to do: pass params+momentum and/or grads_out");
+    task_mask &= (1u << pl->n_streams) - 1u;
+    if (!task_mask) return fail(GAITK_E_BADARG, "empty task mask");
+    UpdateArgs U; memset(&U, 0, sizeof(U)); fill_param_segs(pl, U, nullptr);
+    // a stream whose task is masked out contributes no private gradients either: those parameters are skipped
+    for (int i = 0; i < U.nparams; ++i) {
+        const int g = pl->params[i].group;
+        if (g >= 1 && !(task_mask & (1u << (g - 1)))) U.ps[i].has_grad = 0;
+    }
+    U.params = params; U.momentum = momentum; U.gbuf = gbuf; U.grads_out = grads_out; U.diag = diag;
+    U.task_mask = task_mask; U.n_tasks_max = pl->n_streams; U.alpha = cagrad_c; U.max_norm = max_norm;
+    U.lr = lr; U.mom = mom; U.wd = weight_decay; U.do_sgd = do_sgd ? 1 : 0;
+    cagrad_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(U);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float max_norm, float* shared_grad, float* diag, void* stream) {
+    if (!G || !shared_grad || P <= 0 || n_tasks < 1 || n_tasks > MAXT) return fail(GAITK_E_BADARG, "bad argument");
+    // G is (n_tasks x P) task-major; reuse the update kernel with one pseudo-parameter covering all of G
+    if (n_tasks < MAXT) {
+        // the kernel addresses task t at G + t*P, which holds for any n_tasks <= MAXT
+    }
+    UpdateArgs U; memset(&U, 0, sizeof(U));
+    U.gbuf = G; U.P = P; U.NP = 0; U.nparams = 1;
+    U.ps[0].off = 0; U.ps[0].numel = P; U.ps[0].shared_off = 0; U.ps[0].has_grad = 1;
+    U.grads_out = shared_grad; U.diag = diag; U.task_mask = (1u << n_tasks) - 1u; U.n_tasks_max = n_tasks;
+    U.alpha = c; U.max_norm = max_norm; U.do_sgd = 0;
+    cagrad_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(U);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void sgd_flat_kernel(float* params, const float* grads, float* momentum, const UpdateArgs U) {
+    for (int ip = 0; ip < U.nparams; ++ip) {
+        const ParamSeg s = U.ps[ip];
+        if (!s.has_grad) continue;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.numel; e += gridDim.x * blockDim.x) {
+            const float p = params[s.off + e];
+            const float g = fmaf(U.wd, p, grads[s.off + e]);
+            const float b = fmaf(U.mom, momentum[s.off + e], g);
+            momentum[s.off + e] = b;
+            params[s.off + e] = p - U.lr * b;
+        }
+    }
+}
+extern "C" int gaitk_sgd(gaitk_plan* pl, float* params, const float* grads, float* momentum, const uint8_t* has_grad,
+                         float lr, float mom, float weight_decay, void* stream) {
+    if (!pl || !params || !grads || !momentum) return fail(GAITK_E_BADARG, "null argument");
+    UpdateArgs U; memset(&U, 0, sizeof(U)); fill_param_segs(pl, U, has_grad);
+    U.lr = lr; U.mom = mom; U.wd = weight_decay;
+    sgd_flat_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(params, grads, momentum, U);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ losses
+struct LossArgs { float scale; float margin[KMAX]; float cls_w[KMAX]; int nan_degenerate; };
+
+// one CTA; deterministic tree reduction
+__global__ void __launch_bounds__(256) loss_kernel(const float* logits, const long long* y, int B, int K, LossArgs L,
+                                                   const float* logit_off, float* loss_out, int* correct_out, float* dlogits) {
+    __shared__ double sh[3][256];
+    double num = 0, den = 0, cor = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) den += (double)L.cls_w[(int)y[b]];
+    sh[0][threadIdx.x] = den; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; __syncthreads(); }
+    const float inv_denom = 1.0f / (float)sh[0][0];
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int yy = (int)y[b];
+        float zz[KMAX]; float mx = -INFINITY, best = -INFINITY; int am = 0;
+        for (int k = 0; k < K; ++k) {
+            float z = logits[(size_t)b * K + k];
+            if (z > best) { best = z; am = k; }
+            if (logit_off) z -= logit_off[(size_t)b * K + k];
+            if (k == yy) z -= L.margin[k];
+            z *= L.scale;
+            if (L.nan_degenerate) z = __int_as_float(0x7fc00000);
+            zz[k] = z; mx = fmaxf(mx, z);
+        }
+        float se = 0.f;
+        for (int k = 0; k < K; ++k) se += expf(zz[k] - mx);
+        const float lse = mx + logf(se);
+        const float wy = L.cls_w[yy];
+        num += (double)(wy * (lse - zz[yy]));
+        cor += (am == yy) ? 1.0 : 0.0;
+        if (dlogits)
+            for (int k = 0; k < K; ++k)
+                dlogits[(size_t)b * K + k] = L.scale * wy * inv_denom * (expf(zz[k] - lse) - (k == yy ? 1.f : 0.f));
+    }
+    sh[1][threadIdx.x] = num; sh[2][threadIdx.x] = cor; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (loss_out) loss_out[0] = (float)(sh[1][0] / sh[0][0]);
+        if (correct_out) correct_out[0] = (int)(sh[2][0] + 0.5);
+    }
+}
+
+extern "C" int gaitk_loss(const float* logits, const int64_t* y, int B, int K, const gaitk_loss_desc* desc, const float* logit_off,
+                          float* loss_out, int32_t* correct_out, float* dlogits, void* stream) {
+    if (!logits || !y || !desc || B <= 0 || K < 2 || K > KMAX) return fail(GAITK_E_BADARG, "bad argument");
+    LossArgs L; L.scale = desc->scale; L.nan_degenerate = desc->nan_if_degenerate;
+    for (int k = 0; k < KMAX; ++k) { L.margin[k] = desc->margin[k]; L.cls_w[k] = desc->cls_weight[k]; }
+    loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)y, B, K, L, logit_off, loss_out, correct_out, dlogits);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+struct DenomArgs { const long long* y[GAITK_MAX_STREAMS]; int count[GAITK_MAX_STREAMS]; float cls_w[GAITK_MAX_STREAMS][KMAX]; int n; };
+__global__ void __launch_bounds__(256) denom_kernel(DenomArgs D, float* denom) {
+    __shared__ double sh[256];
+    const int s = blockIdx.x;
+    double acc = 0;
+    for (int b = threadIdx.x; b < D.count[s]; b += blockDim.x) {
+        const int yy = (int)D.y[s][b];
+        acc += (double)(yy == 0 ? D.cls_w[s][0] : yy == 1 ? D.cls_w[s][1] : yy == 2 ? D.cls_w[s][2] : D.cls_w[s][3]);
+    }
+    sh[threadIdx.x] = acc; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) denom[s] = (float)sh[0];
+}
+extern "C" int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_streams, const gaitk_loss_desc* loss,
+                                       float* denom, void* stream) {
+    if (!y || !counts || !loss || !denom || n_streams < 1 || n_streams > GAITK_MAX_STREAMS) return fail(GAITK_E_BADARG, "bad argument");
+    DenomArgs D; memset(&D, 0, sizeof(D)); D.n = n_streams;
+    for (int s = 0; s < n_streams; ++s) {
+        D.y[s] = (const long long*)y[s]; D.count[s] = counts[s];
+        for (int k = 0; k < KMAX; ++k) D.cls_w[s][k] = loss[s].cls_weight[k];
+    }
+    denom_kernel<<<n_streams, 256, 0, (cudaStream_t)stream>>>(D, denom);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ data path
+extern "C" int64_t gaitk_window_indices(int64_t n_frames, int64_t win, int64_t hop, int64_t* out, int64_t cap) {
+    if (n_frames <= 0 || win <= 0 || hop <= 0 || n_frames < win) return 0;
+    int64_t n = 0;
+    for (int64_t w = 0; w + win <= n_frames; w += hop, ++n)
+        if (out && n < cap) { out[3 * n] = n; out[3 * n + 1] = w; out[3 * n + 2] = w + win; }
+    return n;
+}
+
+// per-channel sum / sum of squares / count over finite values.  One CTA per channel group keeps the
+// accumulation order fixed (deterministic), threads stride over frames (coalesced across channels).
+__global__ void __launch_bounds__(256) stats_kernel(const double* __restrict__ f, long long N, int D, double* acc) {
+    __shared__ double sh[3][256];
+    const int d = blockIdx.x;
+    double s = 0, ss = 0, n = 0;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+        const double v = f[i * D + d];
+        if (isfinite(v)) { s += v; ss = fma(v, v, ss); n += 1.0; }
+    }
+    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ss; sh[2][threadIdx.x] = n; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) for (int j = 0; j < 3; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { acc[d] += sh[0][0]; acc[D + d] += sh[1][0]; acc[2 * D + d] += sh[2][0]; }
+}
+extern "C" int gaitk_stats_accumulate(const double* frames, int64_t N, int D, double* acc, void* stream) {
+    if (!frames || !acc || D <= 0) return fail(GAITK_E_BADARG, "bad argument");
+    if (N <= 0) return 0;
+    stats_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(frames, N, D, acc);
+    LAUNCH_CHECK();
+    return 0;
+}
+__global__ void stats_finalize_kernel(const double* acc, int D, double* mean, double* stdv) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const double n = acc[2 * D + d];
+    if (n <= 0) { mean[d] = 0.0; stdv[d] = -1.0; return; }        // no statistics: channel passes through
+    const double m = acc[d] / n;
+    double var = acc[D + d] / n - m * m; if (var < 0) var = 0;
+    double sd = sqrt(var); if (sd < 1e-6) sd = 1e-6;
+    mean[d] = m; stdv[d] = sd;
+}
+extern "C" int gaitk_stats_finalize(const double* acc, int D, double* mean, double* stdv, void* stream) {
+    if (!acc || !mean || !stdv || D <= 0) return fail(GAITK_E_BADARG, "bad argument");
+    stats_finalize_kernel<<<(D + 63) / 64, 64, 0, (cudaStream_t)stream>>>(acc, D, mean, stdv);
+    LAUNCH_CHECK();
+    return 0;
+}
+__global__ void normalize_kernel(const double* __restrict__ f, long long total, int D, const double* __restrict__ mean,
+                                 const double* __restrict__ stdv, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        double v = f[i];
+        const double s = stdv[d];
+        if (s < 0) { out[i] = (float)v; continue; }                 // channel without statistics
+        const double m = mean[d];
+        const double mm = isfinite(m) ? m : 0.0;
+        if (!isfinite(v)) v = mm;
+        const double se = (isfinite(s) && s > 1e-6) ? s : 1e-6;
+        double z = __ddiv_rn(__dsub_rn(v, mm), se);
+        if (!isfinite(z)) z = 0.0;
+        out[i] = (float)z;
+    }
+}
+extern "C" int gaitk_normalize_frames(const double* frames, int64_t N, int D, const double* mean, const double* stdv, float* out, void* stream) {
+    if (!frames || !mean || !stdv || !out || D <= 0) return fail(GAITK_E_BADARG, "bad argument");
+    if (N <= 0) return 0;
+    const long long total = (long long)N * D;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, total, D, mean, stdv, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+// one window per (blockIdx.x + k*gridDim.x); the T*D floats of a window are contiguous in both source and destination
+__global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ frames, int D, const long long* __restrict__ ws,
+                                                     int B, int T, int enabled, float* __restrict__ out) {
+    const int per = T * D;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* src = frames + (size_t)ws[b] * D;
+        float* dst = out + (size_t)b * per;
+        const bool vec = ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) && (per % 4 == 0);
+        if (!enabled) {
+            for (int i = threadIdx.x; i < per; i += blockDim.x) dst[i] = 0.f;
+        } else if (vec) {
+            const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = threadIdx.x; i < per / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        } else {
+            for (int i = threadIdx.x; i < per; i += blockDim.x) dst[i] = __ldg(src + i);
+        }
+    }
+}
+extern "C" int gaitk_window_gather(const float* frames, int D, const int64_t* win_start, int B, int T, int enabled, float* out, void* stream) {
+    if (!frames || !win_start || !out || D <= 0 || T <= 0) return fail(GAITK_E_BADARG, "bad argument");
+    if (B <= 0) return 0;
+    gather_kernel<<<std::min(B, 148 * 8), 256, 0, (cudaStream_t)stream>>>(frames, D, (const long long*)win_start, B, T, enabled, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+// FoG pose clip: subtract joint 0, per-coordinate min-max over (L, J) of the CENTRED clip, pad/trim to T_out.
+// One CTA per clip.  fp64 arithmetic in the reference's operation order, then cast to fp32.
+__global__ void __launch_bounds__(128) fog_pose_kernel(const double* __restrict__ poses, const long long* __restrict__ cs,
+                                                       const long long* __restrict__ cl, int J, int T_out, float* __restrict__ out) {
+    __shared__ double smin[3][128], smax[3][128];
+    const int c = blockIdx.x;
+    const double* p = poses + (size_t)cs[c] * J * 3;
+    const long long L = cl[c];
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (long long i = threadIdx.x; i < L * J; i += blockDim.x) {
+        const long long t = i / J;
+        for (int k = 0; k < 3; ++k) {
+            const double v = p[i * 3 + k] - p[t * J * 3 + k];
+            mn[k] = fmin(mn[k], v); mx[k] = fmax(mx[k], v);
+        }
+    }
+    for (int k = 0; k < 3; ++k) { smin[k][threadIdx.x] = mn[k]; smax[k][threadIdx.x] = mx[k]; }
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) for (int k = 0; k < 3; ++k) {
+            smin[k][threadIdx.x] = fmin(smin[k][threadIdx.x], smin[k][threadIdx.x + o]);
+            smax[k][threadIdx.x] = fmax(smax[k][threadIdx.x], smax[k][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    float* o_ = out + (size_t)c * T_out * J * 3;
+    for (long long i = threadIdx.x; i < (long long)T_out * J; i += blockDim.x) {
+        const long long t = i / J;
+        for (int k = 0; k < 3; ++k) {
+            double v = 0.0;
+            if (t < L) {
+                const double cen = __dsub_rn(p[i * 3 + k], p[t * J * 3 + k]);
+                v = __ddiv_rn(__dsub_rn(cen, smin[k][0]), __dadd_rn(__dsub_rn(smax[k][0], smin[k][0]), 1e-6));
+            }
+            o_[i * 3 + k] = (float)v;
+        }
+    }
+}
+extern "C" int gaitk_fog_prepare_pose(const double* poses, const int64_t* clip_start, const int64_t* clip_len, int n_clips, int J,
+                                      int T_out, float* out, void* stream) {
+    if (!poses || !clip_start || !clip_len || !out || J <= 0 || T_out <= 0) return fail(GAITK_E_BADARG, "bad argument");
+    if (n_clips <= 0) return 0;
+    fog_pose_kernel<<<n_clips, 128, 0, (cudaStream_t)stream>>>(poses, (const long long*)clip_start, (const long long*)clip_len, J, T_out, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+__global__ void __launch_bounds__(128) fog_sensor_kernel(const double* __restrict__ sens, const long long* __restrict__ cs,
+                                                         const long long* __restrict__ cl, int D, int T_out, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    const double* p = sens + (size_t)cs[c] * D;
+    const long long L = cl[c];
+    float* o_ = out + (size_t)c * T_out * D;
+    for (long long i = threadIdx.x; i < (long long)T_out * D; i += blockDim.x) o_[i] = (i / D < L) ? (float)p[i] : 0.f;
+}
+extern "C" int gaitk_fog_prepare_sensor(const double* sens, const int64_t* clip_start, const int64_t* clip_len, int n_clips, int D,
+                                        int T_out, float* out, void* stream) {
+    if (!sens || !clip_start || !clip_len || !out || D <= 0 || T_out <= 0) return fail(GAITK_E_BADARG, "bad argument");
+    if (n_clips <= 0) return 0;
+    fog_sensor_kernel<<<n_clips, 128, 0, (cudaStream_t)stream>>>(sens, (const long long*)clip_start, (const long long*)clip_len, D, T_out, out);
+    LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,135 @@
+"""Drop-in for the reference's ``train/feature_encoder.py`` :7-265 (2-stream FoG / FBG model): same class
+names, constructor signatures, attribute names, ``state_dict`` keys and seeded initial weights; the
+arithmetic runs in the fused sm_100a kernels of libgaitk.so."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .plan import FlatParamModule, run_streams
+
+
+class CosineLinear(nn.Module):
+    """feature_encoder.py:7-24."""
+    def __init__(self, in_features: int, out_features: int, eps: float = 1e-8):
+        super().__init__()
+        self.weight = nn.Parameter(torch.Tensor(out_features, in_features))
+        nn.init.xavier_uniform_(self.weight)
+        self.eps = eps
+
+
+class SensorEncoder(nn.Module):
+    """feature_encoder.py:27-58 (parameter container)."""
+    def __init__(self, in_channels: int, out_channels: int, sensor_length: int = None, output_length: int = 101):
+        super().__init__()
+        self.d2_sensor_length = sensor_length
+        self.output_length = output_length
+        self.conv1d = nn.Conv1d(in_channels=in_channels, out_channels=out_channels, kernel_size=3, stride=1, padding=1)
+        self.pool = nn.AdaptiveAvgPool1d(output_length)
+
+
+class SkeletonMLP(nn.Module):
+    """feature_encoder.py:61-77."""
+    def __init__(self, input_dim: int, output_dim: int):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim, output_dim)
+        self.ln1 = nn.LayerNorm(output_dim)
+        self.relu = nn.ReLU()
+
+
+class SharedBackbone(nn.Module):
+    """feature_encoder.py:80-109."""
+    def __init__(self, in_channels: int, shared_out_channels: int = 16, backbone_dim: int = 8):
+        super().__init__()
+        self.conv1d = nn.Conv1d(in_channels=in_channels, out_channels=shared_out_channels, kernel_size=3, stride=1, padding=1)
+        self.relu = nn.ReLU()
+        self.pool = nn.AdaptiveAvgPool1d(backbone_dim)
+
+
+class TaskHead(nn.Module):
+    """feature_encoder.py:112-146."""
+    def __init__(self, input_dim: int, num_classes: int, use_norm: bool = False, use_cosine: bool = False):
+        super().__init__()
+        self.use_cosine = use_cosine
+        if use_cosine:
+            self.norm = nn.LayerNorm(input_dim); self.fc = CosineLinear(input_dim, num_classes)
+        elif use_norm:
+            self.norm = nn.LayerNorm(input_dim); self.fc = nn.Linear(input_dim, num_classes)
+        else:
+            self.norm = None; self.fc = nn.Linear(input_dim, num_classes)
+
+
+class MultiModalMultiTaskModel(FlatParamModule):
+    """feature_encoder.py:149-265.  forward(x_skel (B,T,Dskel), x_sensor (B,Tsens,Csens)) ->
+    (logits_skel, logits_sensor)."""
+
+    def __init__(self, skeleton_input_dim: int, skeleton_output_dim: int, sensor_in_channels: int,
+                 sensor_out_channels: int, sensor_length: int, shared_out_channels: int, backbone_dim: int,
+                 taskhead_input_dim: int, num_classes: int, use_norm: bool = False, use_cosine: bool = False,
+                 synchronized_loading: bool = False):
+        super().__init__()
+        if skeleton_output_dim != sensor_out_channels:
+            raise _lib.GaitkError("skeleton_output_dim must equal sensor_out_channels (one shared backbone)")
+        if taskhead_input_dim != shared_out_channels * backbone_dim:
+            raise _lib.GaitkError("taskhead_input_dim must equal shared_out_channels * backbone_dim")
+        self.skeleton_encoder = SkeletonMLP(input_dim=skeleton_input_dim, output_dim=skeleton_output_dim)
+        self.sensor_encoder = SensorEncoder(in_channels=sensor_in_channels, out_channels=sensor_out_channels,
+                                            sensor_length=sensor_length)
+        self.backbone = SharedBackbone(in_channels=sensor_out_channels, shared_out_channels=shared_out_channels,
+                                       backbone_dim=backbone_dim)
+        self.synchronized_loading = synchronized_loading
+        if synchronized_loading:
+            self.task_head_shared = TaskHead(taskhead_input_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+        else:
+            self.task_head_skel = TaskHead(taskhead_input_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+            self.task_head_sensor = TaskHead(taskhead_input_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+        self.use_skeleton_only = False
+        self.use_sensor_only = False
+        self._cfg = dict(skel_in_dim=skeleton_input_dim, enc_out_ch=skeleton_output_dim, sensor_in_ch=sensor_in_channels,
+                         sensor_len=sensor_length, shared_out_ch=shared_out_channels, backbone_dim=backbone_dim,
+                         num_classes=num_classes, use_norm=bool(use_norm), use_cosine=bool(use_cosine))
+        self._T = None
+
+    def _plan_kwargs(self):
+        if self._T is None:
+            raise _lib.GaitkError("pose length unknown: call the model on a batch first")
+        c = self._cfg
+        return dict(family=_lib.FAMILY_FOG, T=self._T, enc_out_ch=c["enc_out_ch"], shared_out_ch=c["shared_out_ch"],
+                    backbone_dim=c["backbone_dim"], num_classes=c["num_classes"], use_norm=c["use_norm"],
+                    use_cosine=c["use_cosine"], synchronized=self.synchronized_loading, skel_in_dim=c["skel_in_dim"],
+                    sensor_in_ch=c["sensor_in_ch"], sensor_len=c["sensor_len"],
+                    sensor_out_len=self.sensor_encoder.output_length)
+
+    def set_window(self, T: int):
+        if self._T != T:
+            self._T = int(T)
+            object.__setattr__(self, "_plan", None); object.__setattr__(self, "_flat", None)
+        return self
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        object.__setattr__(self, "_flat", None)
+        return out
+
+    def forward(self, x_skel, x_sensor):
+        self.set_window(x_skel.shape[1])
+        if x_sensor.shape[1] != self._cfg["sensor_len"]:
+            raise _lib.GaitkError(f"sensor clips must have sensor_length={self._cfg['sensor_len']} frames "
+                                  "(create_fusion_loaders pads/trims to it, dataloader_fbg_fog.py:135,158)")
+        if x_skel.shape[1] != self.sensor_encoder.output_length:
+            raise _lib.GaitkError("pose length must equal the sensor encoder's pooled length (101)")
+        if self.use_skeleton_only:
+            ls, _ = run_streams(self, [x_skel, None], 0b11)
+            return ls, None
+        if self.use_sensor_only:
+            _, lt = run_streams(self, [None, x_sensor], 0b11)
+            return None, lt
+        ls, lt = run_streams(self, [x_skel, x_sensor], 0b11)
+        return ls, lt
+
+    def get_shared_parameters(self):
+        shared = list(self.backbone.parameters())
+        if self.synchronized_loading:
+            shared += list(self.task_head_shared.parameters())
+        return shared

@@ -1,0 +1,129 @@
+"""FusedTrainStep -- the fast path for one training step of the reference trainers.
+
+Equivalent, on identical inputs, to ``forward_batch`` -> three criteria -> ``step_cagrad_three`` ->
+``optimizer.step()`` of ``train/weargait_train.py`` :163-248,305-311 (private_mult = 2) or to
+``process_batch(train=True)`` of ``train/fbg_fog_train.py`` :46-152 (private_mult = 1), but as
+
+    gaitk_step_grads   one fused kernel per stream (forward + loss + whole backward, inputs read once)
+    [all-reduce]       one NCCL all-reduce of the ~26 KB gradient buffer when data-parallel
+    gaitk_step_update  single-CTA Gram + simplex solve + combine + clip + SGD
+
+with no host synchronisation; loss / accuracy stay on the device until the caller reads them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import LossDesc, check, lib, ptr_array, stream_handle
+from .classification_losses import criterion_spec
+from .plan import FlatParamModule
+
+
+class FusedTrainStep:
+    def __init__(self, model: FlatParamModule, criterions: Sequence, *, cagrad_c: float, max_norm: float = 1.0,
+                 lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, private_mult: float = 2.0,
+                 process_group=None, consistency_lambda: float = 0.0):
+        self.model = model; self.criterions = list(criterions)
+        self.cagrad_c = float(cagrad_c); self.max_norm = float(max_norm)
+        self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
+        self.private_mult = float(private_mult); self.pg = process_group
+        self.consistency_lambda = float(consistency_lambda)
+        self._mom = None; self._gbuf = None; self._denom = None; self._diag = None
+        self._pinned = {}; self._dev_in = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, plan):
+        dev = plan.device
+        if self._gbuf is None or self._gbuf.numel() != plan.gbuf_floats or self._gbuf.device != dev:
+            self._gbuf = torch.zeros(plan.gbuf_floats, dtype=torch.float32, device=dev)
+            self._denom = torch.ones(4, dtype=torch.float32, device=dev)
+            self._diag = torch.zeros(16, dtype=torch.float32, device=dev)
+        if self._mom is None or self._mom.numel() != plan.NP or self._mom.device != dev:
+            self._mom = torch.zeros(plan.NP, dtype=torch.float32, device=dev)
+        return self._gbuf, self._denom, self._diag, self._mom
+
+    @property
+    def momentum_buffer(self):
+        return self._mom
+
+    def stats(self):
+        """(losses[n_streams], correct[n_streams]) device tensors of the last step."""
+        plan = self.model.plan()
+        st = self._gbuf[3 * plan.P + plan.NP:]
+        return st[0:plan.n_streams], st[4:4 + plan.n_streams]
+
+    def diag(self):
+        return self._diag
+
+    # ------------------------------------------------------------------ step
+    def step(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], *, enabled: Sequence[bool] = None,
+             tasks: Sequence[bool] = None, ys_global: Optional[Sequence[torch.Tensor]] = None,
+             win_start: Optional[Sequence[torch.Tensor]] = None, logits_out: Optional[Sequence] = None,
+             update: bool = True, grads_out: Optional[torch.Tensor] = None):
+        """xs[s]: (B, T_s, D_s) CUDA fp32 (or frame stores with win_start[s] int64[B]); ys[s]: int64[B].
+        ys_global: label vectors of the WHOLE data-parallel batch (defaults to ys) -- they fix the
+        weighted-mean denominators so that shards add up to the single-GPU step."""
+        model = self.model
+        n = len(xs)
+        if hasattr(model, "set_window") and (win_start is None or win_start[0] is None):
+            model.set_window(xs[0].shape[1])
+        plan = model.plan(); flat = model.flat_params()
+        gbuf, denom, diag, mom = self._buffers(plan)
+        K = plan.K
+        descs = (LossDesc * _lib.MAX_STREAMS)()
+        offs = []
+        for s in range(n):
+            d, off_fn = criterion_spec(self.criterions[s], K)
+            descs[s] = d
+            offs.append(None)          # logit noise is only defined through the criterion call path
+            if getattr(self.criterions[s], "noise_mul", 0) not in (0, 0.0):
+                raise _lib.GaitkError("FusedTrainStep supports noise_mul == 0 (the trainers' default); use the autograd path")
+        B = plan._check_inputs(xs, win_start)
+        enabled_mask = 0b111 if enabled is None else sum(1 << s for s, e in enumerate(enabled) if e)
+        task_mask = ((1 << n) - 1) if tasks is None else sum(1 << s for s, e in enumerate(tasks) if e)
+        yg = ys if ys_global is None else ys_global
+        st = stream_handle()
+        counts = (C.c_int * n)(*[int(y.numel()) for y in yg])
+        check(lib().gaitk_loss_denominators(ptr_array([y.data_ptr() for y in yg]), counts, n, descs, denom.data_ptr(), st),
+              "gaitk_loss_denominators")
+        ws = plan.workspace(B)
+        check(lib().gaitk_step_grads(plan.handle, flat.data_ptr(), ptr_array([x.data_ptr() for x in xs]),
+                                     None if win_start is None else ptr_array([0 if w is None else w.data_ptr() for w in win_start]),
+                                     ptr_array([y.data_ptr() for y in ys]), B, descs, None, denom.data_ptr(), enabled_mask,
+                                     task_mask, self.private_mult, self.consistency_lambda,
+                                     None if logits_out is None else ptr_array([0 if l is None else l.data_ptr() for l in logits_out]),
+                                     gbuf.data_ptr(), ws.data_ptr(), ws.numel(), _lib.DTYPE_F32, st), "gaitk_step_grads")
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                   and torch.distributed.get_world_size() > 1 and self.pg is not False):
+            torch.distributed.all_reduce(gbuf, group=self.pg if self.pg not in (None, False) else None)
+        check(lib().gaitk_step_update(plan.handle, flat.data_ptr() if update else None, mom.data_ptr() if update else None,
+                                      gbuf.data_ptr(), task_mask, self.cagrad_c, self.max_norm, self.lr, self.momentum,
+                                      self.weight_decay, None if grads_out is None else grads_out.data_ptr(),
+                                      diag.data_ptr(), st), "gaitk_step_update")
+        return self.stats()
+
+    # ------------------------------------------------------------------ end-to-end (host batch) entry
+    def step_host(self, xs_host: Sequence[torch.Tensor], ys_host: Sequence[torch.Tensor], **kw):
+        """The call a trainer makes with a DataLoader batch: pinned host tensors in, H2D copies on the
+        current stream, fused step, and a device->host read of (loss, correct)."""
+        dev = self.model.plan().device if self.model._plan is not None else torch.device("cuda", torch.cuda.current_device())
+        xs = [self._to_dev(("x", i), x, dev) for i, x in enumerate(xs_host)]
+        same = all(y is ys_host[0] for y in ys_host)
+        if same:
+            y0 = self._to_dev(("y", 0), ys_host[0], dev); ys = [y0] * len(ys_host)
+        else:
+            ys = [self._to_dev(("y", i), y, dev) for i, y in enumerate(ys_host)]
+        loss, correct = self.step(xs, ys, **kw)
+        out = torch.cat([loss, correct]).to("cpu", non_blocking=False)
+        return out
+
+    def _to_dev(self, key, t, dev):
+        buf = self._dev_in.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, device=dev); self._dev_in[key] = buf
+        buf.copy_(t, non_blocking=True)
+        return buf

@@ -1,0 +1,216 @@
+"""Drop-in for the reference's ``data/WearGait/weargait_encoders.py`` (:19-189): same class names,
+constructor signatures, attribute names, ``state_dict`` keys/shapes and -- because the same torch
+modules are instantiated in the same order -- the same seeded initial weights.  The arithmetic does not
+run in these modules: ``WearGaitThreeModal.forward`` hands the three (B,T,D) streams to the fused
+sm_100a kernels of libgaitk.so through ``plan.run_streams``.
+
+Sub-modules stay callable the way ``weargait_train._single_logits_and_labels`` (:262-270) calls them
+(``model.head_w(model.backbone(model.enc_w(x)).flatten(1))``): an encoder returns a deferred token, the
+head resolves it with one fused single-stream launch.
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .plan import FlatParamModule, run_streams
+
+
+class _Deferred:
+    """Token for 'stream s of `owner` applied to x' travelling enc -> backbone -> .flatten(1) -> head."""
+    def __init__(self, owner, stream, x, stage="enc"):
+        self.owner, self.stream, self.x, self.stage = owner, stream, x, stage
+
+    def flatten(self, start_dim=1):
+        return self
+
+
+class _Part(nn.Module):
+    _owner = None
+    _stream = None
+
+    def _bind(self, owner, stream):
+        object.__setattr__(self, "_owner", weakref.ref(owner)); object.__setattr__(self, "_stream", stream)
+
+
+class CosineLinear(nn.Module):
+    """weargait_encoders.py:19-28."""
+    def __init__(self, in_features: int, out_features: int, eps: float = 1e-8):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        nn.init.xavier_uniform_(self.weight)
+        self.eps = eps
+
+
+class TaskHead(_Part):
+    """weargait_encoders.py:30-37."""
+    def __init__(self, input_dim: int, num_classes: int, use_norm: bool = False, use_cosine: bool = False):
+        super().__init__()
+        self.norm = nn.LayerNorm(input_dim) if (use_norm or use_cosine) else None
+        self.fc = CosineLinear(input_dim, num_classes) if use_cosine else nn.Linear(input_dim, num_classes)
+
+    def forward(self, d):
+        if not isinstance(d, _Deferred) or d.stage != "backbone":
+            raise _lib.GaitkError("TaskHead consumes the deferred output of backbone(enc(x)).flatten(1); "
+                                  "call the model (or model.forward_stream) instead of isolated sub-modules")
+        owner = d.owner
+        if not owner.synchronized and owner._heads[d.stream] is not self:
+            raise _lib.GaitkError("this head belongs to another stream")
+        return owner.forward_stream(d.stream, d.x)
+
+
+class WalkwayEncoder(_Part):
+    """weargait_encoders.py:40-52."""
+    def __init__(self, out_ch: int):
+        super().__init__()
+        self.conv = nn.Conv1d(2, out_ch, kernel_size=3, padding=1)
+        self.act = nn.GELU()
+        self.ln = nn.LayerNorm(out_ch)
+
+    def forward(self, x):
+        return _Deferred(self._owner(), self._stream, x)
+
+
+class IMUEncoderShallow(_Part):
+    """weargait_encoders.py:54-69."""
+    def __init__(self, in_ch: int, out_ch: int, pool_len=None):
+        super().__init__()
+        if pool_len:
+            raise _lib.GaitkError("pool_len is not supported (the reference trainer always passes None, weargait_train.py:468)")
+        self.pool_len = pool_len
+        self.conv = nn.Conv1d(in_ch, out_ch, kernel_size=3, padding=1)
+        self.act = nn.GELU()
+        self.ln = nn.LayerNorm(out_ch)
+        self.pool = None
+
+    def forward(self, x):
+        return _Deferred(self._owner(), self._stream, x)
+
+
+class InsoleEncoderDeep(_Part):
+    """weargait_encoders.py:71-101 (``ln1`` is constructed and never applied, as in the reference)."""
+    def __init__(self, in_ch: int, out_ch: int, hidden_ch=None, pool_len=None):
+        super().__init__()
+        if pool_len:
+            raise _lib.GaitkError("pool_len is not supported (the reference trainer always passes None)")
+        self.pool_len = pool_len
+        h = hidden_ch or max(out_ch, 2 * out_ch)
+        self.conv1 = nn.Conv1d(in_ch, h, kernel_size=5, padding=2)
+        self.act1 = nn.GELU()
+        self.ln1 = nn.LayerNorm(h)
+        self.conv2 = nn.Conv1d(h, out_ch, kernel_size=3, padding=1)
+        self.act2 = nn.GELU()
+        self.ln2 = nn.LayerNorm(out_ch)
+        self.skip = nn.Conv1d(h, out_ch, kernel_size=1) if h != out_ch else nn.Identity()
+        self.pool = None
+
+    def forward(self, x):
+        return _Deferred(self._owner(), self._stream, x)
+
+
+class SharedBackbone(_Part):
+    """weargait_encoders.py:103-113."""
+    def __init__(self, in_ch: int, out_ch: int = 16, bdim: int = 8):
+        super().__init__()
+        self.conv = nn.Conv1d(in_ch, out_ch, kernel_size=3, padding=1)
+        self.act = nn.ReLU()
+        self.pool = nn.AdaptiveAvgPool1d(bdim)
+
+    def forward(self, d):
+        if not isinstance(d, _Deferred) or d.stage != "enc":
+            raise _lib.GaitkError("SharedBackbone consumes the deferred output of an encoder of the same model")
+        return _Deferred(d.owner, d.stream, d.x, "backbone")
+
+
+class WearGaitThreeModal(FlatParamModule):
+    """weargait_encoders.py:116-189.  forward(x_walk (B,T,2), x_insole (B,T,13), x_imu (B,T,24)) ->
+    (lw, li, lm), each (B, K) fp32 and autograd-connected to every parameter."""
+
+    def __init__(self, *, enc_out_ch=12, backbone_dim=8, shared_out_ch=16, num_classes=2, use_norm=False,
+                 use_cosine=False, synchronized=True, pool_len=None):
+        super().__init__()
+        self.enc_w = WalkwayEncoder(out_ch=enc_out_ch)
+        self.enc_i = InsoleEncoderDeep(in_ch=13, out_ch=enc_out_ch, hidden_ch=enc_out_ch * 2, pool_len=pool_len)
+        self.enc_m = IMUEncoderShallow(in_ch=24, out_ch=enc_out_ch, pool_len=pool_len)
+        self.backbone = SharedBackbone(in_ch=enc_out_ch, out_ch=shared_out_ch, bdim=backbone_dim)
+        feat_dim = shared_out_ch * backbone_dim
+        self.synchronized = synchronized
+        if synchronized:
+            shared = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+            self.head_w = self.head_i = self.head_m = shared
+            self._shared_head = shared
+        else:
+            self.head_w = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+            self.head_i = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+            self.head_m = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+            self._shared_head = None
+        self._cfg = dict(enc_out_ch=enc_out_ch, backbone_dim=backbone_dim, shared_out_ch=shared_out_ch,
+                         num_classes=num_classes, use_norm=bool(use_norm), use_cosine=bool(use_cosine))
+        self._T = None
+        for s, e in enumerate((self.enc_w, self.enc_i, self.enc_m)):
+            e._bind(self, s)
+        self.backbone._bind(self, None)
+        for s, h in enumerate((self.head_w, self.head_i, self.head_m)):
+            h._bind(self, s)
+        object.__setattr__(self, "_heads", (self.head_w, self.head_i, self.head_m))
+
+    # ---- plan plumbing
+    def _plan_kwargs(self):
+        if self._T is None:
+            raise _lib.GaitkError("window length unknown: call the model on a batch first")
+        c = self._cfg
+        return dict(family=_lib.FAMILY_WEARGAIT, T=self._T, enc_out_ch=c["enc_out_ch"], shared_out_ch=c["shared_out_ch"],
+                    backbone_dim=c["backbone_dim"], num_classes=c["num_classes"], use_norm=c["use_norm"],
+                    use_cosine=c["use_cosine"], synchronized=self.synchronized)
+
+    def set_window(self, T: int):
+        if self._T != T:
+            self._T = int(T)
+            object.__setattr__(self, "_plan", None); object.__setattr__(self, "_flat", None)
+        return self
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        object.__setattr__(self, "_flat", None)      # .to()/.cuda()/.float() re-materialise parameters
+        return out
+
+    # ---- forward
+    def forward(self, x_walk, x_insole, x_imu, enabled=(True, True, True)):
+        self.set_window(x_walk.shape[1])
+        mask = sum(1 << s for s, e in enumerate(enabled) if e)
+        lw, li, lm = run_streams(self, [x_walk, x_insole, x_imu], mask)
+        return lw, li, lm
+
+    def forward_stream(self, stream: int, x):
+        """One branch only: enc_s -> backbone -> head_s (weargait_train.py:262-270)."""
+        self.set_window(x.shape[1])
+        xs = [None, None, None]; xs[stream] = x
+        return run_streams(self, xs, 0b111)[stream]
+
+    # ---- parameter groups (weargait_encoders.py:159-189)
+    def walkway_parameters(self):
+        params = list(self.enc_w.parameters())
+        if not self.synchronized:
+            params += list(self.head_w.parameters())
+        return params
+
+    def insole_parameters(self):
+        params = list(self.enc_i.parameters())
+        if not self.synchronized:
+            params += list(self.head_i.parameters())
+        return params
+
+    def imu_parameters(self):
+        params = list(self.enc_m.parameters())
+        if not self.synchronized:
+            params += list(self.head_m.parameters())
+        return params
+
+    def get_shared_parameters(self):
+        params = list(self.backbone.parameters())
+        if self._shared_head is not None:
+            params += list(self._shared_head.parameters())
+        return params
