@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- gait windows / second per training step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1      # reference arm: CPU port on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- WearGait full multimodal training step, sync
+loader semantics (one label per window, shared head), GCL (m=0.2, s=25), CAGrad c=0.5, SGD(momentum 0.9,
+wd 1e-4); B windows of (64,2)+(64,13)+(64,24) fp32 per GPU (weak scaling), synthetic data of
+WearGait shape, random-init weights.  A step = gather-free fused forward + 3 losses +
+CAGrad/private backward + (all-reduce) + SGD over one batch.
+
+`value` : inputs resident in HBM, CUDA-event timing on the launching stream, max over ranks.
+`e2e`   : the same step through the public API with pinned HOST buffers: H2D copies of the batch and a
+          D2H read of (loss, correct) every step inside the timed region.
+`roofline`: the dominant kernel (the insole stream kernel) timed live with CUDA events; algorithmic
+          bytes = its input bytes read once per window.
+`cpu_baseline`: the oracle port (oracle/gait_oracle.py, torch-CPU ops as the reference dispatches)
+          on a bounded sample; rank 0, N=1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "oracle"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np
+import torch
+
+METRIC = "gait windows/sec per train step"
+UNIT = "windows/s"
+T, DIMS = 64, (2, 13, 24)
+BYTES_PER_WINDOW = T * sum(DIMS) * 4 + 8          # fp32 inputs read once + one int64 label
+COUNTS = [[400, 600]] * 3                          # p(PD) = 0.6 -> unequal class counts (GCL needs them)
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index; self.rows = []; self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth(B, seed):
+    import gait_oracle as O
+    return O.synth_weargait_batch(B, T=T, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_step_time(B: int, steps: int, warmup: int, threads: int):
+    """One reference training step (forward_batch + 3 criteria + step_cagrad_three + SGD,
+    weargait_train.py:163-248,305-311) restated by the oracle with the same torch-CPU / SciPy calls."""
+    import gait_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    import gaitk                                       # only to obtain reference-identical initial weights
+    m = gaitk.WearGaitThreeModal()
+    state = {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}
+    p = O.canonical_params(state, True); bufs = {}
+    xs, y = synth(B, 1)
+    xt = [torch.from_numpy(x) for x in xs]; yt = [torch.from_numpy(y)] * 3
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.weargait_train_step(p, bufs, xt, yt, synchronized=True, wm="gcl", counts=COUNTS, alpha=0.5)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.cpu_batch
+    times = cpu_port_step_time(B, args.steps, max(args.warmup, 1), threads)
+    total = sum(times); val = B * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "cpu_sample_batch": B, "timing": "time.perf_counter around each step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} steps of B={B} windows (bounded sample of the per-GPU batch), torch {torch.__version__} CPU"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(B):
+    return (f"WearGait 3-stream multimodal train step (configs[1]): B={B} windows/GPU of (64,2)+(64,13)+(64,24) fp32, "
+            "sync labels, GCL m=0.2 s=25, CAGrad c=0.5, SGD mom 0.9 wd 1e-4")
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    import gaitk
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)                               # identical replicas on every rank
+    model = gaitk.WearGaitThreeModal().to(dev)
+    crit = [gaitk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in COUNTS]
+    for c in crit:
+        c.consume_rng = False
+    step = gaitk.FusedTrainStep(model, crit, cagrad_c=0.5, max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
+                                private_mult=2.0, process_group=None if world > 1 else False)
+    # synthetic batches: NBUF distinct batches per rank (each 10 KB/window -> B=32768 is 327 MB >> 126 MB L2)
+    NBUF = 2
+    host = []
+    for i in range(NBUF):
+        xs, y = synth(B, 1000 * rank + i)
+        host.append(([torch.from_numpy(x).pin_memory() for x in xs], torch.from_numpy(y).pin_memory()))
+    devb = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in host]
+    # global label vectors (all ranks' labels; cheap) fix the weighted-mean denominators
+    def global_labels(i):
+        if world == 1:
+            return None
+        ys = [torch.from_numpy(synth_labels_only(B, 1000 * r + i)).to(dev) for r in range(world)]
+        g = torch.cat(ys); return [g, g, g]
+
+    def synth_labels_only(Bn, seed):
+        return synth(Bn, seed)[1]
+    yglob = [global_labels(i) for i in range(NBUF)]
+    l2_flush = None
+    if B * BYTES_PER_WINDOW < 2 * 126e6:               # small batches: flush L2 between steps instead
+        l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        xs, y = devb[i % NBUF]
+        if l2_flush is not None:
+            l2_flush.fill_(i & 0xff)
+        step.step(xs, [y, y, y], ys_global=yglob[i % NBUF])
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        one_step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if l2_flush is not None:                           # subtract nothing: the flush is part of the timed loop; report it
+        pass
+    clocks = sampler.stop()
+    loss, correct = step.stats(); loss = loss.cpu().tolist()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H of (loss, correct), every step
+    for i in range(min(args.warmup, 3)):
+        xs, y = host[i % NBUF]; step.step_host(xs, [y, y, y], ys_global=yglob[i % NBUF])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        xs, y = host[i % NBUF]
+        out = step.step_host(xs, [y, y, y], ys_global=yglob[i % NBUF])
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t2.item()) * 1e-3)
+    h2d = B * T * sum(DIMS) * 4 + B * 8
+    d2h = 6 * 4
+
+    # ---- dominant kernel, timed alone with CUDA events on the launching stream (rank 0)
+    roof = None; per_stream = {}
+    if rank == 0:
+        peak, peak_src = peaks()
+        names = ("walkway", "insole", "imu")
+        scratch = torch.empty(model.plan().NP, dtype=torch.float32, device=dev)
+        for s in range(3):
+            tasks = [k == s for k in range(3)]
+            xs, y = devb[0]
+            for _ in range(2):
+                step.step(xs, [y, y, y], tasks=tasks, update=False, grads_out=scratch)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a.record()
+            for r in range(reps):
+                xs, y = devb[r % NBUF]
+                step.step(xs, [y, y, y], tasks=tasks, update=False, grads_out=scratch)
+            b.record(); torch.cuda.synchronize()
+            per_stream[names[s]] = a.elapsed_time(b) / reps
+        dom = max(per_stream, key=per_stream.get)
+        s = names.index(dom)
+        alg = B * (T * DIMS[s] * 4 + 8)
+        ach = alg / (per_stream[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": f"stream_kernel<{dom}> (fused fwd+loss+bwd)", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": per_stream[dom], "algorithmic_bytes_per_launch": alg,
+                "note": "fp32 FFMA path is issue-bound, not HBM-bound (DESIGN.md section 4); the launch also contains a "
+                        "~2 us reduce kernel and the single-CTA update kernel",
+                "per_stream_ms": per_stream,
+                "step_hbm_gbs": B * BYTES_PER_WINDOW / (ms_max / args.steps * 1e-3) / 1e9}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        times = cpu_port_step_time(args.cpu_batch, 3, 1, threads)
+        cpu = {"value": args.cpu_batch * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{len(times)} steps of B={args.cpu_batch} windows (bounded sample), oracle port, torch {torch.__version__} CPU"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(B), "parallelism": f"dp{world}", "global_batch": world * B,
+                       "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
+                       "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 8 * args.steps,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "final_losses": loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gaitk", choices=["gaitk", "reference"])
+    ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gaitk" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

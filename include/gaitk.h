@@ -47,6 +47,10 @@ extern "C" {
 #define GAITK_DTYPE_F32  0        /* fp32 FFMA, parity 1e-5                           */
 #define GAITK_DTYPE_TF32 1        /* tensor-core tf32 inputs, fp32 accumulate, 1e-3   */
 
+/* simplex solver inside CAGrad */
+#define GAITK_SOLVER_SLSQP 0      /* restatement of SciPy SLSQP's iteration (reference parity; default) */
+#define GAITK_SOLVER_EXACT 1      /* true optimum (closed-form line minima + bisection)                 */
+
 typedef struct gaitk_model_desc {
     int32_t family;               /* GAITK_FAMILY_*                                                   */
     int32_t T;                    /* WearGait: win_len (weargait_train.py:655); FoG: pose_length      */
@@ -161,11 +165,18 @@ int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_st
  * diag (optional, device float[16]): w[3], GTG[9], pre-clip norm, objective, iters. */
 int gaitk_step_update(gaitk_plan* plan, float* params, float* momentum, const float* gbuf,
                       uint32_t task_mask, float cagrad_c, float max_norm, float lr, float mom,
-                      float weight_decay, float* grads_out /*optional flat*/, float* diag, void* stream);
+                      float weight_decay, float* grads_out /*optional flat*/, float* diag, int solver, void* stream);
 
 /* CAGrad alone on an explicit (P x n) column-major matrix (multitask_weighting.py:694-729). */
 int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float max_norm, float* shared_grad,
-                 float* diag, void* stream);
+                 float* diag, int solver, void* stream);
+
+/* The simplex solve alone, evaluated ON THE HOST by the same code the device runs (unit tests / debugging):
+ * gram3x3 = fp32 G^T G with leading dimension 3; solver GAITK_SOLVER_SLSQP restates SciPy's SLSQP iteration
+ * (scipy.optimize.minimize call site multitask_weighting.py:717), GAITK_SOLVER_EXACT is the true optimum.
+ * Returns SLSQP's exit mode (0 converged, 8, 9), w_out[n_tasks] (float64). */
+int gaitk_cagrad_solve_host(const float* gram3x3, int n_tasks, float alpha, int solver, double* w_out,
+                            int* iters_out);
 
 /* SGD alone (torch.optim.SGD, momentum/dampening 0/no nesterov); has_grad (host
  * uint8 per parameter of the plan) mirrors ".grad is None => skipped". */

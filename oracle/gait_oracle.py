@@ -409,8 +409,15 @@ def step_gradients(p: Params, losses: Sequence[torch.Tensor], shared_keys: Seque
     plus extras (G, GG, w, pre-clip norm).
     """
     n = len(losses)
-    shared = [p[k] for k in shared_keys]
-    G = torch.stack([flat_grads(L, shared) for L in losses], 1)
+    keys = list(p.keys())
+    leaves = [p[k] for k in keys]
+    # n full-graph sweeps (losses[i].backward(retain_graph=True) :680-688): shared columns AND the
+    # accumulation into every other leaf come out of the same sweep
+    sweeps = [torch.autograd.grad(L, leaves, retain_graph=True, allow_unused=True) for L in losses]
+    sh = set(shared_keys)
+    idx = {k: i for i, k in enumerate(keys)}
+    G = torch.stack([torch.cat([(torch.zeros_like(p[k]) if sw[idx[k]] is None else sw[idx[k]]).reshape(-1)
+                                for k in shared_keys]) for sw in sweeps], 1)
     g, GG, w = cagrad_combine(G, alpha)
     g = g * n
     norm = float(g.norm())
@@ -420,18 +427,22 @@ def step_gradients(p: Params, losses: Sequence[torch.Tensor], shared_keys: Seque
     off = 0
     for k in shared_keys:
         cnt = p[k].numel(); grads[k] = g[off:off + cnt].view_as(p[k]).clone(); off += cnt
-    others = [k for k in p if k not in set(shared_keys)]
-    for k in others:
+    for k in keys:
+        if k in sh:
+            continue
         acc = None
-        for L in losses:
-            (gk,) = torch.autograd.grad(L, [p[k]], retain_graph=True, allow_unused=True)
+        for sw in sweeps:
+            gk = sw[idx[k]]
             if gk is not None:
                 acc = gk.clone() if acc is None else acc + gk
         grads[k] = acc
     if private_twice:
-        for L, keys in zip(losses, private_keys):
-            for k in keys:
-                (gk,) = torch.autograd.grad(L, [p[k]], retain_graph=True, allow_unused=True)
+        # torch.autograd.grad(L_k, private_k) once more per stream (weargait_train.py:218-242)
+        for L, pk in zip(losses, private_keys):
+            if not pk:
+                continue
+            gs = torch.autograd.grad(L, [p[k] for k in pk], retain_graph=True, allow_unused=True)
+            for k, gk in zip(pk, gs):
                 if gk is not None:
                     grads[k] = gk.clone() if grads[k] is None else grads[k] + gk
     return grads, {"G": G, "GTG": GG, "weights": w, "norm": norm}

@@ -88,11 +88,8 @@ def test_weargait_fused_step_matches_reference(gk, name):
         close(G, ref["G"], 5e-5, "G")
         d = step.diag().cpu().numpy()
         close(d[3:12].reshape(3, 3), ref["GTG"], 1e-4, "GTG")
-        # the device solve is exact; SLSQP stops at ftol 1e-6 -> compare weights loosely, objective strictly
-        import gait_oracle as O
-        f_ours = O.cagrad_objective(ref["GTG"], d[:3].astype(np.float64), meta["alpha"])
-        f_ref = O.cagrad_objective(ref["GTG"], ref["w"], meta["alpha"])
-        assert f_ours <= f_ref + 1e-6 * max(1.0, abs(f_ref)), (f_ours, f_ref)
+        # the device runs a restatement of SLSQP's own iteration -> the simplex weights match SciPy's
+        assert np.abs(d[:3] - ref["w"]).max() < 2e-4, (d[:3], ref["w"])
         got = grads_by_name(plan, gout)
         for k, v in ref.items():
             if not k.startswith("grad:"):
@@ -101,7 +98,7 @@ def test_weargait_fused_step_matches_reference(gk, name):
             if nm not in got:
                 continue                      # aliases of the shared head
             shared = next(p.group for p in plan.params if p.name == nm) == 0
-            close(got[nm], v, 3e-3 if shared else 5e-5, f"step {st} grad {nm}")
+            close(got[nm], v, 2e-4 if shared else 5e-5, f"step {st} grad {nm}")
         sd = m.state_dict()
         for k, v in ref.items():
             if k.startswith("param:"):
@@ -144,7 +141,7 @@ def test_weargait_autograd_path_matches_reference(gk, name):
             if k.startswith("grad:") and k[5:] in named:
                 nm = k[5:]
                 shared = any(named[nm] is p for p in m.get_shared_parameters())
-                close(named[nm].grad.cpu().numpy(), v, 3e-3 if shared else 5e-5, f"step {st} grad {nm}")
+                close(named[nm].grad.cpu().numpy(), v, 2e-4 if shared else 5e-5, f"step {st} grad {nm}")
         assert named["enc_i.ln1.weight"].grad is None and named["enc_i.ln1.bias"].grad is None
         sd = m.state_dict()
         for k, v in ref.items():
@@ -207,7 +204,7 @@ def test_fog_fused_step_matches_reference(gk, name):
             if k.startswith("grad:") and k[5:] in got:
                 nm = k[5:]
                 shared = next(p.group for p in plan.params if p.name == nm) == 0
-                close(got[nm], v, 3e-3 if shared else 5e-5, f"step {st} grad {nm}")
+                close(got[nm], v, 2e-4 if shared else 5e-5, f"step {st} grad {nm}")
         sd = m.state_dict()
         for k, v in ref.items():
             if k.startswith("param:"):
@@ -241,31 +238,40 @@ def test_fog_autograd_path_matches_reference(gk, name):
         for k, v in ref.items():
             if k.startswith("grad:"):
                 nm = k[5:]
-                close(named[nm].grad.cpu().numpy(), v, 3e-3 if id(named[nm]) in shared_ids else 5e-5, f"step {st} grad {nm}")
+                close(named[nm].grad.cpu().numpy(), v, 2e-4 if id(named[nm]) in shared_ids else 5e-5, f"step {st} grad {nm}")
         sd = m.state_dict()
         for k, v in ref.items():
             if k.startswith("param:"):
                 close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
 
 
-def test_cagrad_solver_vs_slsqp_corpus(gk):
-    """On-device exact simplex solve vs the reference's SLSQP answers (golden): never a worse objective,
-    combined gradient within SLSQP's own stopping slack."""
+def test_cagrad_device_vs_scipy_corpus(gk):
+    """gaitk_cagrad (Gram + SLSQP restatement + combine on the device) against what the reference's
+    CAGrad.cagrad returned (golden).  Weights always; the combined gradient wherever the reference's own
+    formula is well conditioned (lambda = c / ||G w|| explodes when G w ~ 0)."""
     import gait_oracle as O
     g = load_golden("cagrad_corpus")
     cag = gk.CAGrad(n_tasks=3, device=torch.device("cuda"))
-    worst = 0.0
+    worst_w = worst_g = 0.0; n_g = 0
     for G, gref, wref, (n, alpha) in zip(g["G"], g["g"], g["w"], g["n_alpha"]):
         n = int(n); alpha = float(alpha)
-        Gd = dev(G[:, :n].T.copy())
-        out, diag = cag.cagrad_device(Gd, alpha=alpha, max_norm=0.0)
+        Gn = G[:, :n].astype(np.float32)
+        if (Gn.T @ Gn).max() > 1e6:
+            continue                                  # SciPy's LSQ sub-solver breaks down there (cagrad_solver.cuh)
+        out, diag = cag.cagrad_device(dev(Gn.T.copy()), alpha=alpha, max_norm=0.0)
         out = out.cpu().numpy() / n; d = diag.cpu().numpy()
-        A = (G[:, :n].T.astype(np.float32) @ G[:, :n].astype(np.float32))
-        f_ours = O.cagrad_objective(A, d[:n].astype(np.float64), alpha); f_ref = O.cagrad_objective(A, wref[:n], alpha)
-        assert f_ours <= f_ref + 1e-6 * max(1.0, abs(f_ref)), (f_ours, f_ref, d[:n], wref[:n])
-        rel = np.abs(out - gref).max() / max(np.abs(gref).max(), 1e-30)
-        worst = max(worst, rel)
-    assert worst < 5e-3, worst
+        worst_w = max(worst_w, np.abs(d[:n] - wref[:n]).max())
+        gw = Gn.astype(np.float64) @ wref[:n]
+        if np.linalg.norm(gw) > 1e-2 * np.linalg.norm(Gn):
+            worst_g = max(worst_g, np.abs(out - gref).max() / max(np.abs(gref).max(), 1e-30)); n_g += 1
+        # exact mode: never a worse objective than SLSQP
+        cag.solver = gk._lib.SOLVER_EXACT
+        _, d2 = cag.cagrad_device(dev(Gn.T.copy()), alpha=alpha, max_norm=0.0)
+        cag.solver = gk._lib.SOLVER_SLSQP
+        A = (torch.from_numpy(Gn).t().mm(torch.from_numpy(Gn))).numpy()
+        f2 = O.cagrad_objective(A, d2.cpu().numpy()[:n].astype(np.float64), alpha); fr = O.cagrad_objective(A, wref[:n], alpha)
+        assert f2 <= fr + 1e-6 * max(1.0, abs(fr))
+    assert worst_w < 2e-4 and n_g > 40 and worst_g < 5e-4, (worst_w, worst_g, n_g)
 
 
 def test_masks_match_reference(gk):

@@ -62,3 +62,65 @@ def test_no_cpu_fallback():
         m(torch.zeros(2, 64, 2), torch.zeros(2, 64, 13), torch.zeros(2, 64, 24))
     with pytest.raises(gaitk.GaitkError):
         gaitk.CrossEntropyLoss()(torch.zeros(2, 2), torch.zeros(2, dtype=torch.long))
+
+
+def _solve_host(A32, n, alpha, solver=0):
+    import gaitk
+    L = gaitk.lib()
+    a = np.zeros((3, 3), np.float32); a[:n, :n] = A32
+    w = (C.c_double * 3)(); it = C.c_int()
+    mode = L.gaitk_cagrad_solve_host(a.ctypes.data_as(C.POINTER(C.c_float)), n, float(alpha), solver, w, C.byref(it))
+    return np.array(w[:n]), mode, it.value
+
+
+def test_slsqp_restatement_matches_scipy_golden_corpus():
+    """The C++ SLSQP restatement (identical code runs on the device) against the weights the reference's
+    SciPy call produced (golden).  Parity range: Gram entries <= 1e6 (see cagrad_solver.cuh)."""
+    g = load_golden("cagrad_corpus")
+    worst = 0.0; checked = 0
+    for G, wref, (n, alpha) in zip(g["G"], g["w"], g["n_alpha"]):
+        n = int(n); Gn = G[:, :n].astype(np.float32)
+        A = (torch.from_numpy(Gn).t().mm(torch.from_numpy(Gn))).numpy()
+        if A.max() > 1e6:
+            continue
+        w, mode, it = _solve_host(A, n, alpha)
+        assert mode == 0
+        worst = max(worst, np.abs(w - wref[:n]).max()); checked += 1
+    assert checked >= 60 and worst < 2e-4, (checked, worst)
+
+
+def test_slsqp_restatement_matches_scipy_random():
+    import gait_oracle as O
+    rng = np.random.default_rng(7)
+    errs = []
+    for t in range(300):
+        n = int(rng.choice([2, 3])); P = int(rng.choice([8, 24, 300]))
+        G = rng.standard_normal((P, n)).astype(np.float32)
+        kind = t % 8
+        if kind == 1: G[:, 1] = G[:, 0] * 0.7
+        elif kind == 2: G[:, -1] = -G[:, 0] + 0.05 * G[:, -1]
+        elif kind == 3: G *= 1e-3
+        elif kind == 4: G[:, 0] *= 6
+        elif kind == 5: G[:, -1] = 0
+        elif kind == 6: G = np.abs(G)
+        elif kind == 7: G *= 10 ** rng.uniform(-3, 1.2)
+        alpha = float(rng.choice([0.5, 0.1, 0.4, 1.0]))
+        _, A, wref = O.cagrad_combine(torch.from_numpy(G), alpha)
+        if A.max() > 1e6:
+            continue
+        w, mode, it = _solve_host(A, n, alpha)
+        errs.append(np.abs(w - wref).max())
+    errs = np.array(errs)
+    assert errs.max() < 5e-4 and np.quantile(errs, 0.95) < 1e-5, (errs.max(), np.quantile(errs, 0.95))
+
+
+def test_exact_solver_never_worse_than_slsqp():
+    import gait_oracle as O
+    g = load_golden("cagrad_corpus")
+    for G, wref, (n, alpha) in zip(g["G"], g["w"], g["n_alpha"]):
+        n = int(n); Gn = G[:, :n].astype(np.float32)
+        A = (torch.from_numpy(Gn).t().mm(torch.from_numpy(Gn))).numpy()
+        w, _, _ = _solve_host(A, n, alpha, solver=1)
+        assert abs(w.sum() - 1) < 1e-12 and (w >= 0).all()
+        f_ours = O.cagrad_objective(A, w, float(alpha)); f_ref = O.cagrad_objective(A, wref[:n], float(alpha))
+        assert f_ours <= f_ref + 1e-9 * max(1.0, abs(f_ref))

@@ -17,12 +17,13 @@ LIB_PATH = Path(os.environ.get("GAITK_LIB", _HERE / "libgaitk.so"))
 MAX_STREAMS, MAX_CLASSES = 3, 4
 FAMILY_WEARGAIT, FAMILY_FOG = 0, 1
 DTYPE_F32, DTYPE_TF32 = 0, 1
+SOLVER_SLSQP, SOLVER_EXACT = 0, 1
 
 EXPORTS = [
     "gaitk_version", "gaitk_last_error", "gaitk_plan_create", "gaitk_plan_destroy", "gaitk_param_count",
     "gaitk_param_info", "gaitk_param_total", "gaitk_shared_total", "gaitk_num_streams", "gaitk_stream_in_dim",
     "gaitk_stream_in_len", "gaitk_workspace_bytes", "gaitk_forward", "gaitk_loss", "gaitk_backward",
-    "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_cagrad",
+    "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_cagrad", "gaitk_cagrad_solve_host",
     "gaitk_sgd", "gaitk_window_indices", "gaitk_stats_accumulate", "gaitk_stats_finalize",
     "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
 ]
@@ -79,9 +80,11 @@ def lib():
     L.gaitk_step_grads.restype = i32
     L.gaitk_loss_denominators.argtypes = [pp, C.POINTER(C.c_int), i32, C.POINTER(LossDesc), vp, vp]
     L.gaitk_loss_denominators.restype = i32
-    L.gaitk_step_update.argtypes = [vp, vp, vp, vp, u32, f32, f32, f32, f32, f32, vp, vp, vp]
+    L.gaitk_step_update.argtypes = [vp, vp, vp, vp, u32, f32, f32, f32, f32, f32, vp, vp, i32, vp]
     L.gaitk_step_update.restype = i32
-    L.gaitk_cagrad.argtypes = [vp, i32, i32, f32, f32, vp, vp, vp]; L.gaitk_cagrad.restype = i32
+    L.gaitk_cagrad.argtypes = [vp, i32, i32, f32, f32, vp, vp, i32, vp]; L.gaitk_cagrad.restype = i32
+    L.gaitk_cagrad_solve_host.argtypes = [C.POINTER(C.c_float), i32, f32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.gaitk_cagrad_solve_host.restype = i32
     L.gaitk_sgd.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint8), f32, f32, f32, vp]; L.gaitk_sgd.restype = i32
     L.gaitk_window_indices.argtypes = [i64, i64, i64, C.POINTER(i64), i64]; L.gaitk_window_indices.restype = i64
     L.gaitk_stats_accumulate.argtypes = [vp, i64, i32, vp, vp]; L.gaitk_stats_accumulate.restype = i32

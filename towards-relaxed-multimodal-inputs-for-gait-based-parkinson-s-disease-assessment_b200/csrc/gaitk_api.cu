@@ -421,7 +421,7 @@ static int accumulate_grads(const gaitk_plan* pl, const float* gbuf, float* grad
 
 extern "C" int gaitk_step_update(gaitk_plan* pl, float* params, float* momentum, const float* gbuf, uint32_t task_mask,
                                  float cagrad_c, float max_norm, float lr, float mom, float weight_decay, float* grads_out,
-                                 float* diag, void* stream) {
+                                 float* diag, int solver, void* stream) {
     if (!pl || !gbuf) return fail(GAITK_E_BADARG, "null argument");
     const bool do_sgd = params && momentum;
     if (!do_sgd && !grads_out) return fail(GAITK_E_BADARG, "nothing to do: pass params+momentum and/or grads_out");
@@ -435,26 +435,33 @@ extern "C" int gaitk_step_update(gaitk_plan* pl, float* params, float* momentum,
     }
     U.params = params; U.momentum = momentum; U.gbuf = gbuf; U.grads_out = grads_out; U.diag = diag;
     U.task_mask = task_mask; U.n_tasks_max = pl->n_streams; U.alpha = cagrad_c; U.max_norm = max_norm;
-    U.lr = lr; U.mom = mom; U.wd = weight_decay; U.do_sgd = do_sgd ? 1 : 0;
+    U.lr = lr; U.mom = mom; U.wd = weight_decay; U.do_sgd = do_sgd ? 1 : 0; U.solver = solver;
     cagrad_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(U);
     LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float max_norm, float* shared_grad, float* diag, void* stream) {
+extern "C" int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float max_norm, float* shared_grad, float* diag, int solver,
+                            void* stream) {
     if (!G || !shared_grad || P <= 0 || n_tasks < 1 || n_tasks > MAXT) return fail(GAITK_E_BADARG, "bad argument");
-    // G is (n_tasks x P) task-major; reuse the update kernel with one pseudo-parameter covering all of G
-    if (n_tasks < MAXT) {
-        // the kernel addresses task t at G + t*P, which holds for any n_tasks <= MAXT
-    }
+    // G is (n_tasks x P) task-major (the kernel addresses task t at G + t*P); one pseudo-parameter covers all of G
     UpdateArgs U; memset(&U, 0, sizeof(U));
     U.gbuf = G; U.P = P; U.NP = 0; U.nparams = 1;
     U.ps[0].off = 0; U.ps[0].numel = P; U.ps[0].shared_off = 0; U.ps[0].has_grad = 1;
     U.grads_out = shared_grad; U.diag = diag; U.task_mask = (1u << n_tasks) - 1u; U.n_tasks_max = n_tasks;
-    U.alpha = c; U.max_norm = max_norm; U.do_sgd = 0;
+    U.alpha = c; U.max_norm = max_norm; U.do_sgd = 0; U.solver = solver;
     cagrad_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(U);
     LAUNCH_CHECK();
     return 0;
+}
+
+// host-side evaluation of the simplex solve (same code the device runs): unit tests and A/B debugging
+extern "C" int gaitk_cagrad_solve_host(const float* gram3x3, int n_tasks, float alpha, int solver, double* w_out, int* iters_out) {
+    if (!gram3x3 || !w_out || n_tasks < 1 || n_tasks > MAXT) return fail(GAITK_E_BADARG, "bad argument");
+    double c = 0; int it = 0;
+    const int mode = cagrad_weights(gram3x3, n_tasks, alpha, solver, w_out, &c, &it);
+    if (iters_out) *iters_out = it;
+    return mode;
 }
 
 __global__ void sgd_flat_kernel(float* params, const float* grads, float* momentum, const UpdateArgs U) {

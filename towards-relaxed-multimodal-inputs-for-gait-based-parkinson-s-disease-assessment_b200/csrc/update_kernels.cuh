@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "cagrad_solver.cuh"
+
 namespace gaitk {
 
 constexpr int MAX_SEG = 16;
@@ -53,90 +55,13 @@ __global__ void reduce_partials_kernel(const ReduceArgs R) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// CAGrad dual:  minimise  f(w) = w^T A b + c * sqrt(w^T A w + 1e-8)  over the simplex,
-// b = 1/n, A = G^T G (multitask_weighting.py:699-717).  The reference hands this to SciPy SLSQP
-// (ftol 1e-6); here it is solved to double precision on the device: every 1-D restriction of f
-// has a closed-form minimiser, and the n = 3 case is a bisection on the derivative of the
-// (convex) partial minimum.
-struct Quad3 { double A[3][3]; double Ab[3]; double c; };
-
-__device__ inline double cg_obj(const Quad3& q, const double* w, int n) {
-    double lin = 0, quad = 0;
-    for (int i = 0; i < n; ++i) { lin += w[i] * q.Ab[i]; for (int j = 0; j < n; ++j) quad += w[i] * q.A[i][j] * w[j]; }
-    return lin + q.c * sqrt(quad + 1e-8);
-}
-__device__ inline void cg_grad(const Quad3& q, const double* w, int n, double* g) {
-    double Aw[3] = {0, 0, 0}, quad = 0;
-    for (int i = 0; i < n; ++i) { for (int j = 0; j < n; ++j) Aw[i] += q.A[i][j] * w[j]; }
-    for (int i = 0; i < n; ++i) quad += w[i] * Aw[i];
-    const double r = q.c / sqrt(quad + 1e-8);
-    for (int i = 0; i < n; ++i) g[i] = q.Ab[i] + r * Aw[i];
-}
-// argmin over tau in [0,1] of f(p + tau * d)
-__device__ inline double cg_line_min(const Quad3& q, const double* p, const double* d, int n) {
-    double a1 = 0, q0 = 1e-8, q1 = 0, q2 = 0;
-    for (int i = 0; i < n; ++i) {
-        a1 += d[i] * q.Ab[i];
-        for (int j = 0; j < n; ++j) { q0 += p[i] * q.A[i][j] * p[j]; q1 += p[i] * q.A[i][j] * d[j]; q2 += d[i] * q.A[i][j] * d[j]; }
-    }
-    if (q2 < 0) q2 = 0;
-    const double c = q.c;
-    // h(tau) = a1 tau + c sqrt(q2 tau^2 + 2 q1 tau + q0);  h'(+-inf) = a1 +- c sqrt(q2)
-    const double lim = c * sqrt(q2);
-    if (!(fabs(a1) < lim)) {                    // no interior stationary point (also q2 == 0)
-        if (q2 <= 0) return a1 > 0 ? 0.0 : (a1 < 0 ? 1.0 : 0.0);
-        // monotone: pick the end with the smaller derivative sign
-        return a1 > 0 ? 0.0 : 1.0;
-    }
-    const double rho = -a1 / c;                 // (q2 tau + q1) / sqrt(Q) at the stationary point
-    double disc = q0 * q2 - q1 * q1; if (disc < 0) disc = 0;
-    const double m = (rho >= 0 ? 1.0 : -1.0) * fabs(rho) * sqrt(disc / (q2 - rho * rho));
-    double tau = (m - q1) / q2;
-    return tau < 0 ? 0.0 : (tau > 1 ? 1.0 : tau);
-}
-
-__device__ inline void cg_solve(const Quad3& q, int n, double* w, int* iters) {
-    *iters = 0;
-    if (n == 1) { w[0] = 1; return; }
-    if (n == 2) {
-        const double p[3] = {0, 1, 0}, d[3] = {1, -1, 0};
-        const double t = cg_line_min(q, p, d, 2);
-        w[0] = t; w[1] = 1 - t; return;
-    }
-    // n == 3: w = (u, (1-u) tau, (1-u)(1-tau)); phi(u) = min_tau f is convex, phi'(u) = g0 - tau g1 - (1-tau) g2
-    auto eval = [&](double u, double* wo) -> double {
-        const double p[3] = {u, 0, 1 - u}, d[3] = {0, 1 - u, -(1 - u)};
-        const double t = (1 - u > 0) ? cg_line_min(q, p, d, 3) : 0.0;
-        wo[0] = u; wo[1] = (1 - u) * t; wo[2] = (1 - u) * (1 - t);
-        double g[3]; cg_grad(q, wo, 3, g);
-        return g[0] - t * g[1] - (1 - t) * g[2];
-    };
-    double wl[3], wh[3];
-    double lo = 0, hi = 1;
-    const double dlo = eval(0.0, wl);
-    if (dlo >= 0) { w[0] = wl[0]; w[1] = wl[1]; w[2] = wl[2]; return; }
-    // at u == 1 the inner problem is degenerate; probe just inside
-    const double dhi = eval(1.0 - 1e-12, wh);
-    if (dhi <= 0) { w[0] = 1; w[1] = 0; w[2] = 0; return; }
-    double wm[3];
-    for (int it = 0; it < 64; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        const double dm = eval(mid, wm);
-        if (dm > 0) hi = mid; else lo = mid;
-        ++*iters;
-        if (hi - lo < 1e-15) break;
-    }
-    eval(0.5 * (lo + hi), w);
-}
-
 struct ParamSeg { long long off; int numel; int shared_off; int has_grad; };
 struct UpdateArgs {
     float* params; float* momentum; const float* gbuf; float* grads_out; float* diag;
     int P; long long NP; int nparams; ParamSeg ps[MAX_PARAMS];
     unsigned task_mask; int n_tasks_max;
     float alpha, max_norm, lr, mom, wd;
-    int do_sgd;
+    int do_sgd, solver;
 };
 
 // block-wide sum of doubles (blockDim.x multiple of 32, <= 1024)
@@ -175,19 +100,17 @@ __global__ void __launch_bounds__(1024) cagrad_update_kernel(const UpdateArgs U)
     }
     for (int i = 0; i < 6; ++i) gg[i] = block_sum_d(gg[i], shd);
     if (tid == 0) {
-        Quad3 q;
         // the reference forms GG in fp32 (torch mm) and hands the fp32 values to SciPy
         const float a[3][3] = {{(float)gg[0], (float)gg[1], (float)gg[2]}, {(float)gg[1], (float)gg[3], (float)gg[4]},
                                {(float)gg[2], (float)gg[4], (float)gg[5]}};
-        double mean = 0;
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { q.A[i][j] = (double)a[i][j]; mean += (double)a[i][j]; }
-        mean /= (double)(n * n);
-        const float g0 = sqrtf((float)mean + 1e-8f);
-        const double c = (double)(U.alpha * g0 + 1e-8f);
+        Quad3 q;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) q.A[i][j] = (double)a[i][j];
+        double w[3] = {0, 0, 0}; double c = 0; int iters = 0;
+        cagrad_weights(&a[0][0], n, U.alpha, U.solver, w, &c, &iters);
         q.c = c;
         for (int i = 0; i < n; ++i) { q.Ab[i] = 0; for (int j = 0; j < n; ++j) q.Ab[i] += q.A[i][j] / n; }
-        double w[3] = {0, 0, 0}; int iters = 0;
-        cg_solve(q, n, w, &iters);
+        // gw = G w with w cast to fp32 as torch.Tensor(w_cpu) does (:719)
+        for (int i = 0; i < n; ++i) w[i] = (double)(float)w[i];
         double gw2 = 0;
         for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) gw2 += w[i] * q.A[i][j] * w[j];
         const double lam = c / (sqrt(gw2 > 0 ? gw2 : 0) + 1e-8);

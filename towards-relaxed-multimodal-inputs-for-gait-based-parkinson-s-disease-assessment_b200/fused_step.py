@@ -26,12 +26,12 @@ from .plan import FlatParamModule
 class FusedTrainStep:
     def __init__(self, model: FlatParamModule, criterions: Sequence, *, cagrad_c: float, max_norm: float = 1.0,
                  lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, private_mult: float = 2.0,
-                 process_group=None, consistency_lambda: float = 0.0):
+                 process_group=None, consistency_lambda: float = 0.0, solver: int = _lib.SOLVER_SLSQP):
         self.model = model; self.criterions = list(criterions)
         self.cagrad_c = float(cagrad_c); self.max_norm = float(max_norm)
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
         self.private_mult = float(private_mult); self.pg = process_group
-        self.consistency_lambda = float(consistency_lambda)
+        self.consistency_lambda = float(consistency_lambda); self.solver = int(solver)
         self._mom = None; self._gbuf = None; self._denom = None; self._diag = None
         self._pinned = {}; self._dev_in = {}
 
@@ -103,7 +103,7 @@ class FusedTrainStep:
         check(lib().gaitk_step_update(plan.handle, flat.data_ptr() if update else None, mom.data_ptr() if update else None,
                                       gbuf.data_ptr(), task_mask, self.cagrad_c, self.max_norm, self.lr, self.momentum,
                                       self.weight_decay, None if grads_out is None else grads_out.data_ptr(),
-                                      diag.data_ptr(), st), "gaitk_step_update")
+                                      diag.data_ptr(), self.solver, st), "gaitk_step_update")
         return self.stats()
 
     # ------------------------------------------------------------------ end-to-end (host batch) entry

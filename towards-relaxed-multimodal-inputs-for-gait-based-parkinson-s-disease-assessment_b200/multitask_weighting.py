@@ -40,8 +40,8 @@ class _LazyExtras(dict):
 
 
 class CAGrad:
-    def __init__(self, n_tasks, device: torch.device = None, c=0.4, max_norm=1.0):
-        self.n_tasks = n_tasks; self.device = device; self.c = c; self.max_norm = max_norm
+    def __init__(self, n_tasks, device: torch.device = None, c=0.4, max_norm=1.0, solver: int = _lib.SOLVER_SLSQP):
+        self.n_tasks = n_tasks; self.device = device; self.c = c; self.max_norm = max_norm; self.solver = solver
         self._G = None; self._g = None; self._diag = None
 
     def parameters(self) -> List[torch.Tensor]:
@@ -63,7 +63,7 @@ class CAGrad:
         Gc = G.contiguous().float()
         check(lib().gaitk_cagrad(Gc.data_ptr(), P, n, float(self.c if alpha is None else alpha),
                                  float(self.max_norm if max_norm is None else max_norm), g.data_ptr(), diag.data_ptr(),
-                                 stream_handle()), "gaitk_cagrad")
+                                 int(self.solver), stream_handle()), "gaitk_cagrad")
         return g, diag
 
     def get_weighted_loss(self, losses, shared_parameters, **kwargs):
@@ -83,7 +83,7 @@ class CAGrad:
                 off += n
                 p.grad = None
         check(lib().gaitk_cagrad(G.data_ptr(), P, self.n_tasks, float(self.c), float(self.max_norm), g.data_ptr(),
-                                 diag.data_ptr(), stream_handle()), "gaitk_cagrad")
+                                 diag.data_ptr(), int(self.solver), stream_handle()), "gaitk_cagrad")
         off = 0
         for p, n in zip(shared, dims):
             p.grad = g[off:off + n].view_as(p).clone()
