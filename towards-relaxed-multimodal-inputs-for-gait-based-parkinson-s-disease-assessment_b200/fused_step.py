@@ -46,6 +46,15 @@ class FusedTrainStep:
             self._mom = torch.zeros(plan.NP, dtype=torch.float32, device=dev)
         return self._gbuf, self._denom, self._diag, self._mom
 
+    def _distributed(self) -> bool:
+        """process_group=False: never; a group: always; None: whenever a default group with >1 ranks exists."""
+        if self.pg is False:
+            return False
+        if self.pg is not None:
+            return True
+        d = torch.distributed
+        return d.is_available() and d.is_initialized() and d.get_world_size() > 1
+
     @property
     def momentum_buffer(self):
         return self._mom
@@ -97,8 +106,7 @@ class FusedTrainStep:
                                      task_mask, self.private_mult, self.consistency_lambda,
                                      None if logits_out is None else ptr_array([0 if l is None else l.data_ptr() for l in logits_out]),
                                      gbuf.data_ptr(), ws.data_ptr(), ws.numel(), _lib.DTYPE_F32, st), "gaitk_step_grads")
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                   and torch.distributed.get_world_size() > 1 and self.pg is not False):
+        if self._distributed():
             torch.distributed.all_reduce(gbuf, group=self.pg if self.pg not in (None, False) else None)
         check(lib().gaitk_step_update(plan.handle, flat.data_ptr() if update else None, mom.data_ptr() if update else None,
                                       gbuf.data_ptr(), task_mask, self.cagrad_c, self.max_norm, self.lr, self.momentum,
