@@ -169,7 +169,8 @@ def run_gpu(args):
     for c in crit:
         c.consume_rng = False
     step = gaitk.FusedTrainStep(model, crit, cagrad_c=0.5, max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
-                                private_mult=2.0, process_group=None if world > 1 else False)
+                                private_mult=2.0, process_group=None if world > 1 else False,
+                                dtype=gaitk.DTYPE_TF32 if args.dtype == "tf32" else gaitk.DTYPE_F32)
     # synthetic batches: NBUF distinct batches per rank (each 10 KB/window -> B=32768 is 327 MB >> 126 MB L2)
     NBUF = 2
     host = []
@@ -269,8 +270,8 @@ def run_gpu(args):
         roof = {"bound": "hbm", "kernel": f"stream_kernel<{dom}> (fused fwd+loss+bwd)", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "ms_per_launch": per_stream[dom], "algorithmic_bytes_per_launch": alg,
-                "note": "fp32 FFMA path is issue-bound, not HBM-bound (DESIGN.md section 4); the launch also contains a "
-                        "~2 us reduce kernel and the single-CTA update kernel",
+                "note": "issue/latency-bound, not HBM-bound (DESIGN.md 3.1); the timed launch also contains the small reduce "
+                        "kernel and the single-CTA update kernel",
                 "per_stream_ms": per_stream,
                 "step_hbm_gbs": B * BYTES_PER_WINDOW / (ms_max / args.steps * 1e-3) / 1e9}
 
@@ -285,7 +286,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(B), "parallelism": f"dp{world}", "global_batch": world * B,
                        "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
                        "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks"},
@@ -308,6 +309,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="tf32", choices=["f32", "tf32"], help="contraction arithmetic of the stream kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaitk" else args.warmup
     if args.impl == "reference":

@@ -106,6 +106,10 @@ int     gaitk_num_streams(const gaitk_plan* plan);
 int     gaitk_stream_in_dim(const gaitk_plan* plan, int stream);   /* channels of stream input */
 int     gaitk_stream_in_len(const gaitk_plan* plan, int stream);   /* rows of stream input     */
 
+/* Launch geometry of one stream kernel (introspection for DESIGN.md / profiling). */
+int gaitk_stream_geometry(const gaitk_plan* plan, int stream, int dtype, int* ctas_per_sm, int* windows_per_tile,
+                          size_t* smem_bytes);
+
 /* Bytes of scratch (per-CTA partial gradients etc.) the step needs for a batch of B. */
 size_t gaitk_workspace_bytes(const gaitk_plan* plan, int B);
 
@@ -209,6 +213,12 @@ int gaitk_fog_prepare_pose(const double* poses, const int64_t* clip_start, const
                            int n_clips, int J, int T_out, float* out, void* stream);
 int gaitk_fog_prepare_sensor(const double* sens, const int64_t* clip_start, const int64_t* clip_len,
                              int n_clips, int D, int T_out, float* out, void* stream);
+
+/* Hardware self-test of the tcgen05 (5th-gen tensor core) layer: runs nops tf32 MMAs (each op = 8 uint32:
+ * a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo (bytes), accumulate, idesc) over shared-memory images of A and B
+ * and returns the 128 x ncols fp32 accumulator.  Test infrastructure for the descriptor conventions. */
+int gaitk_umma_selftest(const float* A, int nA, const float* B, int nB, const uint32_t* ops, int nops, int ncols,
+                        float* D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,10 +22,11 @@ SOLVER_SLSQP, SOLVER_EXACT = 0, 1
 EXPORTS = [
     "gaitk_version", "gaitk_last_error", "gaitk_plan_create", "gaitk_plan_destroy", "gaitk_param_count",
     "gaitk_param_info", "gaitk_param_total", "gaitk_shared_total", "gaitk_num_streams", "gaitk_stream_in_dim",
-    "gaitk_stream_in_len", "gaitk_workspace_bytes", "gaitk_forward", "gaitk_loss", "gaitk_backward",
+    "gaitk_stream_in_len", "gaitk_stream_geometry", "gaitk_workspace_bytes", "gaitk_forward", "gaitk_loss", "gaitk_backward",
     "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_cagrad", "gaitk_cagrad_solve_host",
     "gaitk_sgd", "gaitk_window_indices", "gaitk_stats_accumulate", "gaitk_stats_finalize",
     "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
+    "gaitk_umma_selftest",
 ]
 
 
@@ -71,6 +72,8 @@ def lib():
     L.gaitk_num_streams.argtypes = [vp]; L.gaitk_num_streams.restype = i32
     L.gaitk_stream_in_dim.argtypes = [vp, i32]; L.gaitk_stream_in_dim.restype = i32
     L.gaitk_stream_in_len.argtypes = [vp, i32]; L.gaitk_stream_in_len.restype = i32
+    L.gaitk_stream_geometry.argtypes = [vp, i32, i32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]
+    L.gaitk_stream_geometry.restype = i32
     L.gaitk_workspace_bytes.argtypes = [vp, i32]; L.gaitk_workspace_bytes.restype = sz
     L.gaitk_forward.argtypes = [vp, vp, pp, pp, i32, u32, pp, i32, vp]; L.gaitk_forward.restype = i32
     L.gaitk_loss.argtypes = [vp, vp, i32, i32, C.POINTER(LossDesc), vp, vp, vp, vp, vp]; L.gaitk_loss.restype = i32
@@ -93,6 +96,7 @@ def lib():
     L.gaitk_window_gather.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]; L.gaitk_window_gather.restype = i32
     L.gaitk_fog_prepare_pose.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]; L.gaitk_fog_prepare_pose.restype = i32
     L.gaitk_fog_prepare_sensor.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]; L.gaitk_fog_prepare_sensor.restype = i32
+    L.gaitk_umma_selftest.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp]; L.gaitk_umma_selftest.restype = i32
     _lib = L
     return L
 

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,7 +13,9 @@
 
 #include "../../include/gaitk.h"
 #include "stream_kernel.cuh"
+#include "stream_kernel_tc.cuh"
 #include "update_kernels.cuh"
+#include "umma_selftest.cuh"
 
 using namespace gaitk;
 
@@ -30,12 +33,14 @@ struct ParamInfo {
     std::string name; long long off; int numel; int group; int dims[4]; int shared_off;
 };
 typedef void (*StreamKernelFn)(const StreamArgs, const SmemPlan);
+typedef void (*StreamKernelTcFn)(const StreamArgs, const TcPlan);
 
 struct StreamPlan {
     int enc, CIN, T_in, T, W, rows_in, rows, halo, RBi, RB, pool_sensor;
     int H, C, S, NFL, KT1, skip_identity;
     StreamKernelFn fn;
     SmemPlan sp; GradOff go; int NGP; size_t smem_bytes; int ctas_per_sm;
+    StreamKernelTcFn fn_tc; TcPlan tp; size_t smem_tc; int ctas_tc;      // tensor-core variant (nullptr when unavailable)
     int p_w1, p_b1, p_w2, p_b2, p_wsk, p_bsk, p_lng, p_lnb, p_hng, p_hnb, p_hw, p_hb;   // param indices (-1 = none)
     int nseg; Seg seg[MAX_SEG];
 };
@@ -80,6 +85,18 @@ static StreamKernelFn find_kernel(const KernelKey& k) {
     return nullptr;
 }
 
+template <class Cfg> static StreamKernelTcFn kfn_tc() { return &stream_kernel_tc<Cfg>; }
+static StreamKernelTcFn find_kernel_tc(const KernelKey& k) {
+#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_) \
+        return kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
+    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
+    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
+    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
+#undef GK_CASE
+    return nullptr;
+}
+
 static int round_rb(int rows, int halo) {          // rows per chunk, == 1 (mod 8): conflict-free chunk planes
     int rb = rows + 2 * halo;
     while (rb % 8 != 1) ++rb;
@@ -98,7 +115,8 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     sp.NFL = NF / 32;
     const int Tmax = std::max(T, T_in);
     sp.W = (pool_sensor || Tmax > NT / 2) ? 1 : std::min(WMAX, NT / Tmax);
-    sp.rows = T * sp.W; sp.rows_in = T_in * sp.W; sp.halo = 2 * sp.W;
+    while (sp.W & (sp.W - 1)) --sp.W;                   // power of two (row <-> (t, w) by shifts)
+    sp.rows = T * sp.W; sp.rows_in = T_in * sp.W; sp.halo = (KT1 / 2 > 1 ? KT1 / 2 : 1) * sp.W;
     sp.RB = round_rb(sp.rows, sp.halo); sp.RBi = round_rb(sp.rows_in, sp.halo);
     KernelKey key = {enc, CIN, KT1, H, sp.C, sp.S, sp.NFL};
     sp.fn = find_kernel(key);
@@ -137,6 +155,47 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)sp.fn, NT, sp.smem_bytes));
     if (occ < 1) return fail(GAITK_E_SHAPE, "stream %d kernel does not fit on an SM", s);
     sp.ctas_per_sm = occ;
+    // ---- tensor-core variant (tcgen05 + mma.sync, tf32): full 128-row tiles only
+    sp.fn_tc = (sp.rows == NT && T_in == T) ? find_kernel_tc(key) : nullptr;
+    if (sp.fn_tc) {
+        auto ev = [](int x) { return (x + 1) / 2 * 2; };
+        const int KX = ev(CI4), KH = ev(H4), KC = ev(C4), KS = ev(S4);
+        auto r16 = [](int x) { return (x + 15) / 16 * 16; };
+        const int N1 = enc == ENC_INSOLE ? r16(H) : r16(sp.C), NC = r16(sp.C), NS = r16(sp.S), NH = r16(H);
+        TcPlan& t = sp.tp; memset(&t, 0, sizeof(t));
+        int q = 0;
+        auto tk = [&](int n) { int rr = q; q += (n + 3) / 4 * 4; return rr; };
+        t.X = tk(KX * sp.RB * 4);
+        if (enc == ENC_INSOLE) { t.HA = tk(KH * sp.RB * 4); t.D1 = tk(H4 * sp.RB * 4); }
+        t.XH = tk(KC * sp.RB * 4); t.D = tk(C4 * sp.RB * 4); t.F = tk(KC * sp.RB * 4); t.RSTD = tk(sp.RB); t.Z = tk(KS * sp.RB * 4);
+        t.W1B = tk(KT1 * KX * N1 * 4); t.B1 = tk(O1);
+        if (enc == ENC_INSOLE) { t.W2B = tk(3 * KH * NC * 4); t.B2 = tk(CP); t.W2D = tk(3 * KC * NH * 4); }
+        t.LNG = tk(CP); t.LNB = tk(CP);
+        t.WBB = tk(3 * KC * NS * 4); t.BB = tk(sp.S); t.WBD = tk(3 * KS * NC * 4);
+        t.HW = tk(d.num_classes * NF); t.HB = tk(KMAX); t.HNG = tk(NF); t.HNB = tk(NF); t.INW = tk(KMAX);
+        t.DP = tk(sp.W * NF); t.P = tk(sp.W * NF); t.BINS = tk(2 * d.backbone_dim + 2 * T + 8);
+        t.STG = tk(sp.W * T * CIN);                      // TMA bulk-prefetch staging (raw window bytes)
+        t.STAGE = 0;                                     // flush staging aliases the (dead by then) activations
+        if (q < 16 * std::max(NF, 256)) q = 16 * std::max(NF, 256);
+        t.total = q;
+        sp.smem_tc = (size_t)q * sizeof(float);
+        if (sp.smem_tc > 200 * 1024) sp.fn_tc = nullptr;
+    }
+    if (sp.fn_tc) {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)sp.fn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_tc));
+        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate TMEM although
+        // registers and shared memory admit more (ncu: occupancy_limit_registers / _shared_mem).  The kernel is
+        // persistent with a grid-stride tile loop, so any grid is correct: size it from registers / shared
+        // memory / TMEM columns and let the hardware co-schedule what it can.
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)sp.fn_tc));
+        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NT;
+        const size_t smem_per_cta = sp.smem_tc + fa.sharedSizeBytes + 1024;
+        int by_regs = 65536 / std::max(regs_per_cta, 1), by_smem = (int)((size_t)227 * 1024 / smem_per_cta);
+        int occ2 = std::max(1, std::min(std::min(by_regs, by_smem), 16));      // 32 TMEM columns per CTA -> <= 16
+        if (const char* e = getenv("GAITK_TC_CTAS")) occ2 = std::max(1, atoi(e));
+        sp.ctas_tc = occ2;
+    }
     return 0;
 }
 
@@ -252,6 +311,16 @@ extern "C" int64_t gaitk_shared_total(const gaitk_plan* p) { return p ? p->P : 0
 extern "C" int gaitk_num_streams(const gaitk_plan* p) { return p ? p->n_streams : 0; }
 extern "C" int gaitk_stream_in_dim(const gaitk_plan* p, int s) { return (p && s >= 0 && s < p->n_streams) ? p->st[s].CIN : 0; }
 extern "C" int gaitk_stream_in_len(const gaitk_plan* p, int s) { return (p && s >= 0 && s < p->n_streams) ? p->st[s].T_in : 0; }
+extern "C" int gaitk_stream_geometry(const gaitk_plan* p, int s, int dtype, int* ctas_per_sm, int* windows_per_tile, size_t* smem_bytes) {
+    if (!p || s < 0 || s >= p->n_streams) return fail(GAITK_E_BADARG, "bad stream");
+    const StreamPlan& sp = p->st[s];
+    const bool tc = dtype == GAITK_DTYPE_TF32;
+    if (tc && !sp.fn_tc) return fail(GAITK_E_DTYPE, "no tensor-core kernel for this stream");
+    if (ctas_per_sm) *ctas_per_sm = tc ? sp.ctas_tc : sp.ctas_per_sm;
+    if (windows_per_tile) *windows_per_tile = sp.W;
+    if (smem_bytes) *smem_bytes = tc ? sp.smem_tc : sp.smem_bytes;
+    return 0;
+}
 extern "C" int64_t gaitk_gbuf_floats(const gaitk_plan* p) { return p ? (int64_t)MAXT * p->P + p->NP + 8 : 0; }
 
 extern "C" int gaitk_param_info(const gaitk_plan* p, int index, char* name, size_t cap, int64_t* offset, int64_t* numel,
@@ -266,12 +335,20 @@ extern "C" int gaitk_param_info(const gaitk_plan* p, int index, char* name, size
     return 0;
 }
 
-static int stream_grid(const gaitk_plan* pl, const StreamPlan& sp, int B) {
+static int stream_grid(const gaitk_plan* pl, const StreamPlan& sp, int B, int dtype = GAITK_DTYPE_F32) {
     const int ntiles = (B + sp.W - 1) / sp.W;
-    return std::max(1, std::min(ntiles, pl->sm_count * sp.ctas_per_sm));
+    const int per_sm = dtype == GAITK_DTYPE_TF32 ? sp.ctas_tc : sp.ctas_per_sm;
+    return std::max(1, std::min(ntiles, pl->sm_count * per_sm));
+}
+static int check_dtype(const gaitk_plan* pl, int dtype) {
+    if (dtype == GAITK_DTYPE_F32) return 0;
+    if (dtype != GAITK_DTYPE_TF32) return fail(GAITK_E_DTYPE, "unknown dtype %d", dtype);
+    for (int s = 0; s < pl->n_streams; ++s)
+        if (!pl->st[s].fn_tc) return fail(GAITK_E_DTYPE, "tensor-core (tf32) kernels exist for WearGait C=12/S=16 with 128-row tiles; stream %d has none", s);
+    return 0;
 }
 static size_t stream_ws_floats(const gaitk_plan* pl, const StreamPlan& sp, int B) {
-    return (size_t)stream_grid(pl, sp, B) * sp.NGP;
+    return (size_t)std::max(stream_grid(pl, sp, B), sp.fn_tc ? stream_grid(pl, sp, B, GAITK_DTYPE_TF32) : 0) * sp.NGP;
 }
 extern "C" size_t gaitk_workspace_bytes(const gaitk_plan* pl, int B) {
     if (!pl) return 0;
@@ -299,9 +376,10 @@ static void fill_args(const gaitk_plan* pl, int s, const float* params, const fl
     a.go = sp.go; a.NGP = sp.NGP;
 }
 
-static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int grid, cudaStream_t st) {
+static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int grid, cudaStream_t st, int dtype = GAITK_DTYPE_F32) {
     const StreamPlan& sp = pl->st[s];
-    sp.fn<<<grid, NT, sp.smem_bytes, st>>>(a, sp.sp);
+    if (dtype == GAITK_DTYPE_TF32) sp.fn_tc<<<grid, NT, sp.smem_tc, st>>>(a, sp.tp);
+    else sp.fn<<<grid, NT, sp.smem_bytes, st>>>(a, sp.sp);
     LAUNCH_CHECK();
     return 0;
 }
@@ -309,13 +387,13 @@ static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int g
 extern "C" int gaitk_forward(gaitk_plan* pl, const float* params, const float* const* x, const int64_t* const* win_start,
                              int B, uint32_t enabled_mask, float* const* logits, int dtype, void* stream) {
     if (!pl || !params || !x || !logits) return fail(GAITK_E_BADARG, "null argument");
-    if (dtype != GAITK_DTYPE_F32) return fail(GAITK_E_DTYPE, "dtype %d not available in this build", dtype);
+    { int rc_ = check_dtype(pl, dtype); if (rc_) return rc_; }
     if (B <= 0) return 0;
     for (int s = 0; s < pl->n_streams; ++s) {
         if (!logits[s]) continue;
         StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_FWD, !(enabled_mask & (1u << s)), a);
         a.logits = logits[s];
-        int rc = launch_stream(pl, s, a, stream_grid(pl, pl->st[s], B), (cudaStream_t)stream);
+        int rc = launch_stream(pl, s, a, stream_grid(pl, pl->st[s], B, dtype), (cudaStream_t)stream, dtype);
         if (rc) return rc;
     }
     return 0;
@@ -345,7 +423,7 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
                                 float consistency_lambda, float* const* logits, float* gbuf, void* workspace,
                                 size_t workspace_bytes, int dtype, void* stream) {
     if (!pl || !params || !x || !y || !loss || !denom || !gbuf || !workspace) return fail(GAITK_E_BADARG, "null argument");
-    if (dtype != GAITK_DTYPE_F32) return fail(GAITK_E_DTYPE, "dtype %d not available in this build", dtype);
+    { int rc_ = check_dtype(pl, dtype); if (rc_) return rc_; }
     if (consistency_lambda != 0.f)
         return fail(GAITK_E_BADARG, "consistency term couples the streams: use gaitk_forward + gaitk_backward per task");
     if (workspace_bytes < gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
@@ -360,8 +438,8 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         a.logit_off = logit_off ? logit_off[s] : nullptr;
         a.logits = logits ? logits[s] : nullptr;
         a.partial = (float*)workspace;
-        const int grid = stream_grid(pl, pl->st[s], B);
-        int rc = launch_stream(pl, s, a, grid, st);
+        const int grid = stream_grid(pl, pl->st[s], B, dtype);
+        int rc = launch_stream(pl, s, a, grid, st, dtype);
         if (rc) return rc;
         if ((rc = launch_reduce(pl, s, (const float*)workspace, grid, gbuf, s, private_mult, s, st))) return rc;
     }
@@ -374,7 +452,7 @@ extern "C" int gaitk_backward(gaitk_plan* pl, const float* params, const float* 
                               int B, uint32_t enabled_mask, const float* const* dlogits, float* grads, void* workspace,
                               size_t workspace_bytes, int dtype, void* stream) {
     if (!pl || !params || !x || !dlogits || !grads || !workspace) return fail(GAITK_E_BADARG, "null argument");
-    if (dtype != GAITK_DTYPE_F32) return fail(GAITK_E_DTYPE, "dtype %d not available in this build", dtype);
+    { int rc_ = check_dtype(pl, dtype); if (rc_) return rc_; }
     // scratch: [gbuf | partials]
     const size_t gb = (size_t)gaitk_gbuf_floats(pl) * sizeof(float);
     if (workspace_bytes < gb + gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
@@ -386,8 +464,8 @@ extern "C" int gaitk_backward(gaitk_plan* pl, const float* params, const float* 
         if (!dlogits[s]) continue;
         StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_BWD_EXT, !(enabled_mask & (1u << s)), a);
         a.dlogits_ext = dlogits[s]; a.partial = partial;
-        const int grid = stream_grid(pl, pl->st[s], B);
-        int rc = launch_stream(pl, s, a, grid, st);
+        const int grid = stream_grid(pl, pl->st[s], B, dtype);
+        int rc = launch_stream(pl, s, a, grid, st, dtype);
         if (rc) return rc;
         // all shared contributions land in task column 0 with unit coefficient
         if ((rc = launch_reduce(pl, s, partial, grid, gbuf, 0, 1.0f, -1, st))) return rc;
@@ -727,6 +805,18 @@ extern "C" int gaitk_fog_prepare_sensor(const double* sens, const int64_t* clip_
     if (!sens || !clip_start || !clip_len || !out || D <= 0 || T_out <= 0) return fail(GAITK_E_BADARG, "bad argument");
     if (n_clips <= 0) return 0;
     fog_sensor_kernel<<<n_clips, 128, 0, (cudaStream_t)stream>>>(sens, (const long long*)clip_start, (const long long*)clip_len, D, T_out, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ tcgen05 self-test
+extern "C" int gaitk_umma_selftest(const float* A, int nA, const float* B, int nB, const uint32_t* ops, int nops, int ncols,
+                                   float* D, void* stream) {
+    if (!A || !B || !ops || !D || nops < 1 || (ncols != 32 && ncols != 64 && ncols != 128 && ncols != 256)) return fail(GAITK_E_BADARG, "bad argument");
+    const size_t smem = ((size_t)((nA + 255) / 256) * 256 + nB + 64) * sizeof(float);
+    if (smem > 200 * 1024) return fail(GAITK_E_SHAPE, "operands too large");
+    CUDA_TRY(cudaFuncSetAttribute((const void*)umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, nA, B, nB, (const UmmaOp*)ops, nops, ncols, D);
     LAUNCH_CHECK();
     return 0;
 }

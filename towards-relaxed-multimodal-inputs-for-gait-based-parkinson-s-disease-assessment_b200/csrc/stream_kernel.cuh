@@ -1,78 +1,10 @@
 // stream_kernel.cuh -- one gait stream (encoder -> shared backbone -> head -> loss) forward AND
-// backward in a single persistent kernel, fp32 FFMA arithmetic ("GAITK_DTYPE_F32" path).
-//
-// Reference semantics (paths relative to the reference root):
-//   encoders   data/WearGait/weargait_encoders.py:40-101, train/feature_encoder.py:27-77
-//   backbone   weargait_encoders.py:103-113 / feature_encoder.py:80-109  (+ .flatten(1))
-//   head       weargait_encoders.py:19-37 / feature_encoder.py:7-24,112-146
-//   losses     train/learning/optimizers/classification_losses.py:54-109
-//   backward   what autograd does for losses[i].backward() multitask_weighting.py:680-688
-//
-// Work decomposition: a tile = W windows interleaved row-wise (row r <-> time t = r / W, window
-// w = r % W), so a time shift of one step is a shift of W rows and the zero "same" padding of the
-// convolutions is simply the zero halo at both ends of the tile -- valid for every window at once.
-// Thread i owns rows i, i+128, ...  Every activation lives in shared memory as [chunk][row][4]
-// (chunk = channel / 4): a row's 4-channel group is one 16-byte word, consecutive rows are
-// consecutive words (conflict-free LDS.128 / STS.128, and exactly the no-swizzle K-major /
-// MN-major core-matrix order tcgen05 descriptors address with SBO = 128 B).
-// Inputs are read from HBM exactly once per step; nothing but logits and per-CTA partial gradient
-// sums is written back.
+// backward in a single persistent kernel, fp32 FFMA arithmetic ("GAITK_DTYPE_F32" path, parity 1e-5).
+// Layout, tiling and phase structure: see stream_common.cuh and DESIGN.md section 3.1.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "stream_common.cuh"
 
 namespace gaitk {
-
-constexpr int NT = 128;        // threads per CTA == rows per slot
-constexpr int KMAX = 4;        // GAITK_MAX_CLASSES
-constexpr int WMAX = 4;        // windows per tile (one warp each in the head phase)
-
-enum EncKind { ENC_CONV_GELU_LN = 0, ENC_INSOLE = 1, ENC_LINEAR_LN_RELU = 2, ENC_CONV_POOL = 3 };
-enum Mode { MODE_FWD = 0, MODE_FUSED = 1, MODE_BWD_EXT = 2 };
-
-// stream-local gradient layout (offsets in floats into a partial-gradient row; -1 = absent)
-struct GradOff {
-    int w1, b1, w2, b2, wsk, bsk, lng, lnb, wbb, bbb, hng, hnb, hw, hb;
-    int total;      // NG
-};
-
-struct StreamArgs {
-    // input
-    const float* x;                // (B, T_in, CIN) dense, or frame store (N, CIN) with win_start
-    const long long* win_start;    // optional [B] first frame of each window
-    int B, T_in, T, W, bdim, K, NF;
-    int rows_in, rows, halo, RBi, RB;
-    int mode, zero_input, pool_sensor;
-    // parameters (global memory, PyTorch layouts)
-    const float *w1, *b1, *w2, *b2, *wsk, *bsk, *lng, *lnb, *wbb, *bbb, *hng, *hnb, *hw, *hb;
-    int head_norm, head_cos, skip_identity;
-    // loss
-    const long long* y;
-    float scale; float margin[KMAX]; float cls_w[KMAX]; int nan_degenerate;
-    const float* logit_off;        // optional (B,K)
-    const float* denom;            // device scalar: sum_b w[y_b] over the GLOBAL batch
-    const float* dlogits_ext;      // MODE_BWD_EXT (B,K)
-    // outputs
-    float* logits;                 // optional (B,K)
-    float* partial;                // [gridDim.x][NGP]
-    float* dx;                     // optional input gradient (dense layout) -- MODE_BWD_EXT only
-    GradOff go; int NGP;
-};
-
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float f4get(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
-
-// exact-erf GELU (nn.GELU() default) and its derivative
-__device__ __forceinline__ void gelu_fwd(float a, float& g, float& dg) {
-    const float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752440f));
-    g = a * cdf;
-    dg = cdf + a * 0.39894228040143267794f * __expf(-0.5f * a * a);
-}
 
 // out[o] = bias[o] + sum_{tap, ci} in[row + (tap - KT/2) * W][ci] * wf[tap][ci][o]
 // `in` is a chunked buffer with RBx rows per chunk; wf/bias live in shared memory.
@@ -104,50 +36,6 @@ __device__ __forceinline__ void conv_row(const float* __restrict__ in, int RBx, 
             }
         }
     }
-}
-
-template <int N>
-__device__ __forceinline__ void store_row(float* buf, int RBx, int halo, int r, const float (&v)[N]) {
-    static_assert(N % 4 == 0, "");
-    float4* p = reinterpret_cast<float4*>(buf) + (halo + r);
-#pragma unroll
-    for (int c4 = 0; c4 < N / 4; ++c4) p[c4 * RBx] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-}
-template <int N>
-__device__ __forceinline__ void load_row(const float* buf, int RBx, int halo, int r, float (&v)[N]) {
-    static_assert(N % 4 == 0, "");
-    const float4* p = reinterpret_cast<const float4*>(buf) + (halo + r);
-#pragma unroll
-    for (int c4 = 0; c4 < N / 4; ++c4) {
-        const float4 t = p[c4 * RBx];
-        v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
-    }
-}
-
-// LayerNorm over the CR real channels of v (biased variance, eps 1e-5): xh, rstd
-template <int CP, int CR>
-__device__ __forceinline__ void ln_fwd(const float (&v)[CP], float (&xh)[CP], float& rstd) {
-    float mu = 0.f;
-#pragma unroll
-    for (int c = 0; c < CR; ++c) mu += v[c];
-    mu *= (1.0f / CR);
-    float var = 0.f;
-#pragma unroll
-    for (int c = 0; c < CR; ++c) { const float d = v[c] - mu; var = fmaf(d, d, var); }
-    var *= (1.0f / CR);
-    rstd = rsqrtf(var + 1e-5f);
-#pragma unroll
-    for (int c = 0; c < CP; ++c) xh[c] = c < CR ? (v[c] - mu) * rstd : 0.f;
-}
-// dv from dxh (= dy * gamma)
-template <int CP, int CR>
-__device__ __forceinline__ void ln_bwd(const float (&dxh)[CP], const float (&xh)[CP], float rstd, float (&dv)[CP]) {
-    float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < CR; ++c) { m1 += dxh[c]; m2 = fmaf(dxh[c], xh[c], m2); }
-    m1 *= (1.0f / CR); m2 *= (1.0f / CR);
-#pragma unroll
-    for (int c = 0; c < CP; ++c) dv[c] = c < CR ? rstd * (dxh[c] - m1 - xh[c] * m2) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -216,52 +104,6 @@ struct Wgrad {
         }
         __syncthreads();
     }
-};
-
-// per-row-thread accumulators (bias / LayerNorm affine grads): deterministic block sum of N values
-template <int N>
-__device__ __forceinline__ void flush_rowacc(const float (&v)[N], int nreal, float* stage, float* dst, float* dst2, int tid) {
-    __syncthreads();
-    const int lane = tid & 31, wrp = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const float s = warp_sum(v[i]);
-        if (lane == 0) stage[i * 4 + wrp] = s;
-    }
-    __syncthreads();
-    if (tid < nreal) {
-        const float s = (stage[tid * 4] + stage[tid * 4 + 1]) + (stage[tid * 4 + 2] + stage[tid * 4 + 3]);
-        dst[tid] = s;
-        if (dst2) dst2[tid] = s;
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------
-// compile-time description of one stream
-template <int ENC_, int CIN_, int KT1_, int H_, int C_, int S_, int NFL_>
-struct StreamCfg {
-    static constexpr int ENC = ENC_;
-    static constexpr int CIN = CIN_;                 // real input channels
-    static constexpr int CI4 = (CIN_ + 3) / 4;
-    static constexpr int KT1 = KT1_;                 // taps of the first conv (1 for Linear)
-    static constexpr int H = H_;                     // insole hidden channels (0 otherwise)
-    static constexpr int H4 = (H_ + 3) / 4;
-    static constexpr int C = C_;                     // encoder output channels (real)
-    static constexpr int C4 = (C_ + 3) / 4;
-    static constexpr int CP = C4 * 4;
-    static constexpr int S = S_;                     // backbone channels (multiple of 4)
-    static constexpr int S4 = S_ / 4;
-    static constexpr int NFL = NFL_;                 // head features per lane (NF = 32 * NFL)
-    static constexpr int O1 = (ENC_ == ENC_INSOLE) ? H4 * 4 : CP;   // padded outputs of the first conv
-};
-
-// shared-memory plan (offsets in floats); filled on the host, passed by value
-struct SmemPlan {
-    int X, HA, D1, XH, D, F, RSTD, Z, A;            // activation buffers
-    int W1F, B1, W2F, B2, W2D, LNG, LNB, WBF, BB, WBD, HW, HB, HNG, HNB, INW;   // weights
-    int P, DP, LOGIT, BINS, STAGE;                   // head / pooling scratch
-    int total;
 };
 
 template <class Cfg>
@@ -363,8 +205,9 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     Wgrad<3, (ENC == ENC_INSOLE ? H4 : 1), (ENC == ENC_INSOLE ? C4 : 1)> g_w2;
     Wgrad<3, C4, S4> g_wb;
     float g_b1[O1], g_b2[ENC == ENC_INSOLE ? CP : 4], g_lng[CP], g_lnb[CP], g_bb[S];
-    float g_hw[KMAX][NFL], g_hng[NFL], g_hnb[NFL], g_hb[KMAX];
-    float acc_loss = 0.f, acc_correct = 0.f;
+    HeadState<NFL, S> head; head.zero();
+    HeadCtx hc; hc.Zs = Zs; hc.RB = RB; hc.halo = halo; hc.W = W; hc.S = S; hc.bin_s = bins; hc.bin_e = bins + bdim;
+    hc.hws = hws; hc.hbs = hbs; hc.hngs = hngs; hc.hnbs = hnbs; hc.inws = inws; hc.DPs = DPs; hc.Ps = nullptr;
     if (train) {
         g_w1.zero(); g_w2.zero(); g_wb.zero();
 #pragma unroll
@@ -375,14 +218,6 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         for (int i = 0; i < CP; ++i) { g_lng[i] = 0.f; g_lnb[i] = 0.f; }
 #pragma unroll
         for (int i = 0; i < S; ++i) g_bb[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            g_hb[k] = 0.f;
-#pragma unroll
-            for (int i = 0; i < NFL; ++i) g_hw[k][i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < NFL; ++i) { g_hng[i] = 0.f; g_hnb[i] = 0.f; }
     }
     const float inv_denom = (A.mode == MODE_FUSED) ? 1.0f / A.denom[0] : 0.f;
 
@@ -393,7 +228,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         {
             const int per_win = T_in * CIN;
             for (int e = tid; e < W * per_win; e += NT) {
-                const int w = e / per_win, rem = e - w * per_win;
+                const int w = (e >= per_win) + (e >= 2 * per_win) + (e >= 3 * per_win), rem = e - w * per_win;   // W <= 4
                 const int t = rem / CIN, c = rem - t * CIN;
                 const int wi = win0 + w;
                 float v = 0.f;
@@ -475,155 +310,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         }
         __syncthreads();
         // ================= adaptive pool + head + loss: warp w <-> window w of the tile
-        if (wrp < W) {
-            const int wi = win0 + wrp;
-            float f[NFL], xn[NFL], xh[NFL];
-            float rstd_h = 1.f;
-#pragma unroll
-            for (int i = 0; i < NFL; ++i) {
-                const int j = lane + 32 * i, b = j / S, s = j - b * S;
-                const int t0 = bin_s[b], t1 = bin_e[b];
-                float acc = 0.f;
-                for (int t = t0; t < t1; ++t) acc += Zs[((s >> 2) * RB + halo + t * W + wrp) * 4 + (s & 3)];
-                f[i] = acc / (float)(t1 - t0);
-            }
-            if (A.head_norm) {
-                float m = 0.f;
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) m += f[i];
-                m = warp_sum(m) / (float)NF;
-                float v = 0.f;
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) { const float d = f[i] - m; v = fmaf(d, d, v); }
-                v = warp_sum(v) / (float)NF;
-                rstd_h = rsqrtf(v + 1e-5f);
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) { xh[i] = (f[i] - m) * rstd_h; xn[i] = fmaf(xh[i], hngs[lane + 32 * i], hnbs[lane + 32 * i]); }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) { xh[i] = 0.f; xn[i] = f[i]; }
-            }
-            float nx = 0.f, inx = 1.f;
-            if (A.head_cos) {
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) nx = fmaf(xn[i], xn[i], nx);
-                nx = sqrtf(warp_sum(nx));
-                inx = 1.0f / fmaxf(nx, 1e-8f);
-            }
-            float logit[KMAX], dot[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                logit[k] = 0.f; dot[k] = 0.f;
-                if (k < K) {
-                    float d = 0.f;
-#pragma unroll
-                    for (int i = 0; i < NFL; ++i) d = fmaf(xn[i], hws[k * NF + lane + 32 * i], d);
-                    d = warp_sum(d);
-                    dot[k] = d;
-                    if (A.head_cos) logit[k] = fminf(fmaxf(d * inx * inws[k], -1.0f + 1e-8f), 1.0f - 1e-8f);
-                    else logit[k] = d + hbs[k];
-                }
-            }
-            if (wi < A.B && A.logits && lane < K)
-                A.logits[(size_t)wi * K + lane] = lane == 0 ? logit[0] : lane == 1 ? logit[1] : lane == 2 ? logit[2] : logit[3];
-            if (train) {
-                float dl[KMAX];
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) dl[k] = 0.f;
-                if (wi < A.B) {
-                    if (A.mode == MODE_FUSED) {
-                        const int y = (int)A.y[wi];
-                        float zz[KMAX]; float mx = -INFINITY; int am = 0; float best = -INFINITY;
-#pragma unroll
-                        for (int k = 0; k < KMAX; ++k) if (k < K) {
-                            float z = logit[k];
-                            if (A.logit_off) z -= A.logit_off[(size_t)wi * K + k];
-                            if (k == y) z -= A.margin[k];
-                            z *= A.scale;
-                            if (A.nan_degenerate) z = __int_as_float(0x7fc00000);
-                            zz[k] = z; mx = fmaxf(mx, z);
-                            if (logit[k] > best) { best = logit[k]; am = k; }
-                        }
-                        float se = 0.f;
-#pragma unroll
-                        for (int k = 0; k < KMAX; ++k) if (k < K) se += expf(zz[k] - mx);
-                        const float lse = mx + logf(se);
-                        float zy = 0.f, wy = 0.f;
-#pragma unroll
-                        for (int k = 0; k < KMAX; ++k) if (k < K && k == y) { zy = zz[k]; wy = A.cls_w[k]; }
-                        acc_loss += wy * (lse - zy) * inv_denom;
-                        acc_correct += (am == y) ? 1.f : 0.f;
-#pragma unroll
-                        for (int k = 0; k < KMAX; ++k) if (k < K)
-                            dl[k] = A.scale * wy * inv_denom * (expf(zz[k] - lse) - (k == y ? 1.f : 0.f));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < KMAX; ++k) if (k < K) dl[k] = A.dlogits_ext[(size_t)wi * K + k];
-                    }
-                }
-                // head backward
-                float dxn[NFL];
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) dxn[i] = 0.f;
-                if (A.head_cos) {
-                    float dinx = 0.f;
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) if (k < K) {
-                        const float cv = dot[k] * inx * inws[k];
-                        const float g = (cv >= -1.0f + 1e-8f && cv <= 1.0f - 1e-8f) ? dl[k] : 0.f;
-                        const float ddot = g * inx * inws[k];
-                        dinx = fmaf(g, dot[k] * inws[k], dinx);
-                        const float dinw = g * dot[k] * inx;                 // d/d(inw_k)
-                        const float iw = inws[k];
-                        const bool wfree = iw < 1e8f;                        // ||w|| > eps
-#pragma unroll
-                        for (int i = 0; i < NFL; ++i) {
-                            const float wkj = hws[k * NF + lane + 32 * i];
-                            dxn[i] = fmaf(ddot, wkj, dxn[i]);
-                            float gw = ddot * xn[i];
-                            if (wfree) gw = fmaf(dinw, -wkj * iw * iw * iw, gw);
-                            g_hw[k][i] += gw;
-                        }
-                    }
-                    if (nx > 1e-8f) {
-                        const float cfac = -dinx * inx * inx * inx;
-#pragma unroll
-                        for (int i = 0; i < NFL; ++i) dxn[i] = fmaf(cfac, xn[i], dxn[i]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) if (k < K) {
-                        g_hb[k] += dl[k];
-#pragma unroll
-                        for (int i = 0; i < NFL; ++i) {
-                            dxn[i] = fmaf(dl[k], hws[k * NF + lane + 32 * i], dxn[i]);
-                            g_hw[k][i] = fmaf(dl[k], xn[i], g_hw[k][i]);
-                        }
-                    }
-                }
-                float df[NFL];
-                if (A.head_norm) {
-                    float m1 = 0.f, m2 = 0.f; float dxh[NFL];
-#pragma unroll
-                    for (int i = 0; i < NFL; ++i) {
-                        g_hng[i] = fmaf(dxn[i], xh[i], g_hng[i]); g_hnb[i] += dxn[i];
-                        dxh[i] = dxn[i] * hngs[lane + 32 * i];
-                        m1 += dxh[i]; m2 = fmaf(dxh[i], xh[i], m2);
-                    }
-                    m1 = warp_sum(m1) / (float)NF; m2 = warp_sum(m2) / (float)NF;
-#pragma unroll
-                    for (int i = 0; i < NFL; ++i) df[i] = rstd_h * (dxh[i] - m1 - xh[i] * m2);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NFL; ++i) df[i] = dxn[i];
-                }
-#pragma unroll
-                for (int i = 0; i < NFL; ++i) {
-                    const int j = lane + 32 * i, b = j / S;
-                    DPs[wrp * NF + j] = df[i] / (float)(bin_e[b] - bin_s[b]);
-                }
-            }
-        }
+        if (wrp < W) head.run(A, hc, wrp, lane, win0, train, inv_denom);
         if (!train) { __syncthreads(); continue; }
         __syncthreads();
         // ================= backbone backward: dz (through pool + ReLU), in place over Z
@@ -751,43 +438,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     }
     g_wb.flush(stage, out + go.wbb, nullptr, C, S, tid);
     flush_rowacc<S>(g_bb, S, stage, out + go.bbb, nullptr, tid);
-    // head accumulators: per warp (window slot), per lane (feature); sum the warps in order
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) if (k < K)
-#pragma unroll
-        for (int i = 0; i < NFL; ++i) stage[(wrp * KMAX + k) * NF + lane + 32 * i] = g_hw[k][i];
-    __syncthreads();
-    for (int e = tid; e < K * NF; e += NT) {
-        const int k = e / NF, j = e - k * NF;
-        float s = 0.f;
-        for (int w = 0; w < NT / 32; ++w) s += stage[(w * KMAX + k) * NF + j];
-        out[go.hw + e] = s;
-    }
-    __syncthreads();
-    if (A.head_norm) {
-#pragma unroll
-        for (int i = 0; i < NFL; ++i) { stage[wrp * 2 * NF + lane + 32 * i] = g_hng[i]; stage[wrp * 2 * NF + NF + lane + 32 * i] = g_hnb[i]; }
-        __syncthreads();
-        for (int e = tid; e < 2 * NF; e += NT) {
-            float s = 0.f;
-            for (int w = 0; w < NT / 32; ++w) s += stage[w * 2 * NF + e];
-            if (e < NF) out[go.hng + e] = s; else out[go.hnb + e - NF] = s;
-        }
-        __syncthreads();
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) stage[wrp * 8 + k] = g_hb[k];
-        stage[wrp * 8 + 4] = acc_loss; stage[wrp * 8 + 5] = acc_correct;
-    }
-    __syncthreads();
-    if (tid < 6) {
-        float s = 0.f;
-        for (int w = 0; w < NT / 32; ++w) s += stage[w * 8 + tid];
-        if (tid < 4) { if (tid < K && go.hb >= 0) out[go.hb + tid] = s; }
-        else out[go.total + (tid - 4)] = s;      // [NG] = loss, [NG+1] = correct
-    }
+    head.flush(A, stage, out, tid);
 }
 
 }  // namespace gaitk

@@ -1,0 +1,51 @@
+// umma_selftest.cuh -- hardware self-test of the tcgen05 layer: runs an arbitrary list of tf32 MMAs over
+// caller-supplied shared-memory images of A and B and returns the 128 x N fp32 accumulator.  Used by
+// tests/test_gpu_umma.py to pin the descriptor conventions (K-major tap-shifted operands for the
+// convolutions, MN-major operands for the weight gradients) against a CPU product.
+#pragma once
+#include "umma.cuh"
+
+namespace gaitk {
+
+struct UmmaOp { uint32_t a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo, accumulate, idesc; };
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const float* A, int nA, const float* B, int nB, const UmmaOp* ops,
+                                                            int nops, int ncols, float* D /*128 x ncols*/) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    float* As = sm; float* Bs = sm + ((nA + 255) / 256) * 256;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < nA; i += 128) As[i] = umma::to_tf32(A[i]);
+    for (int i = tid; i < nB; i += 128) Bs[i] = umma::to_tf32(B[i]);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+    if (tid < 32) umma::tmem_alloc(&tmem_slot, (uint32_t)ncols);
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    if (tid == 0) {
+        const uint32_t a0 = umma::smem_u32(As), b0 = umma::smem_u32(Bs);
+        for (int i = 0; i < nops; ++i) {
+            const UmmaOp o = ops[i];
+            umma::mma_tf32(tbase, umma::make_desc(a0 + o.a_off, o.a_lbo, o.a_sbo), umma::make_desc(b0 + o.b_off, o.b_lbo, o.b_sbo),
+                           o.idesc, o.accumulate);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    const uint32_t lane_base = (uint32_t)(tid & ~31) << 16;
+    for (int c = 0; c < ncols; c += 8) {
+        float v[8];
+        umma::ld_x8(tbase + lane_base + c, v);
+        umma::ld_wait();
+        for (int j = 0; j < 8; ++j) D[(size_t)tid * ncols + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tbase, (uint32_t)ncols);
+}
+
+}  // namespace gaitk

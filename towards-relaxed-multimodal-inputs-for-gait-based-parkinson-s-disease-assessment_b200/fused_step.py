@@ -26,12 +26,14 @@ from .plan import FlatParamModule
 class FusedTrainStep:
     def __init__(self, model: FlatParamModule, criterions: Sequence, *, cagrad_c: float, max_norm: float = 1.0,
                  lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, private_mult: float = 2.0,
-                 process_group=None, consistency_lambda: float = 0.0, solver: int = _lib.SOLVER_SLSQP):
+                 process_group=None, consistency_lambda: float = 0.0, solver: int = _lib.SOLVER_SLSQP,
+                 dtype: int = None):
         self.model = model; self.criterions = list(criterions)
         self.cagrad_c = float(cagrad_c); self.max_norm = float(max_norm)
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
         self.private_mult = float(private_mult); self.pg = process_group
         self.consistency_lambda = float(consistency_lambda); self.solver = int(solver)
+        self.dtype = int(getattr(model, 'compute_dtype', _lib.DTYPE_F32) if dtype is None else dtype)
         self._mom = None; self._gbuf = None; self._denom = None; self._diag = None
         self._pinned = {}; self._dev_in = {}
 
@@ -105,7 +107,7 @@ class FusedTrainStep:
                                      ptr_array([y.data_ptr() for y in ys]), B, descs, None, denom.data_ptr(), enabled_mask,
                                      task_mask, self.private_mult, self.consistency_lambda,
                                      None if logits_out is None else ptr_array([0 if l is None else l.data_ptr() for l in logits_out]),
-                                     gbuf.data_ptr(), ws.data_ptr(), ws.numel(), _lib.DTYPE_F32, st), "gaitk_step_grads")
+                                     gbuf.data_ptr(), ws.data_ptr(), ws.numel(), self.dtype, st), "gaitk_step_grads")
         if self._distributed():
             torch.distributed.all_reduce(gbuf, group=self.pg if self.pg not in (None, False) else None)
         check(lib().gaitk_step_update(plan.handle, flat.data_ptr() if update else None, mom.data_ptr() if update else None,

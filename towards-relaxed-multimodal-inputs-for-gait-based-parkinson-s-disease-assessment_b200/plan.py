@@ -63,6 +63,12 @@ class Plan:
     def handle(self):
         return self._h
 
+    def geometry(self, stream: int, dtype: int = _lib.DTYPE_F32):
+        """(CTAs per SM, windows per tile, dynamic shared memory bytes) of one stream kernel."""
+        c, w, sm = C.c_int(), C.c_int(), C.c_size_t()
+        check(lib().gaitk_stream_geometry(self._h, stream, int(dtype), C.byref(c), C.byref(w), C.byref(sm)))
+        return c.value, w.value, sm.value
+
     def workspace_bytes(self, B: int) -> int:
         return int(lib().gaitk_workspace_bytes(self._h, int(B)))
 
@@ -91,7 +97,8 @@ class Plan:
             B = b
         return B
 
-    def forward(self, flat_params: torch.Tensor, xs, enabled_mask: int = 0b111, win_start=None, want=None):
+    def forward(self, flat_params: torch.Tensor, xs, enabled_mask: int = 0b111, win_start=None, want=None,
+                dtype: int = _lib.DTYPE_F32):
         B = self._check_inputs(xs, win_start)
         logits = [torch.empty(B, self.K, dtype=torch.float32, device=self.device)
                   if (xs[s] is not None and (want is None or want[s])) else None for s in range(self.n_streams)]
@@ -99,17 +106,18 @@ class Plan:
                                   ptr_array([0 if x is None else x.data_ptr() for x in xs]),
                                   None if win_start is None else ptr_array([0 if w is None else w.data_ptr() for w in win_start]),
                                   B, enabled_mask, ptr_array([0 if l is None else l.data_ptr() for l in logits]),
-                                  _lib.DTYPE_F32, stream_handle()), "gaitk_forward")
+                                  int(dtype), stream_handle()), "gaitk_forward")
         return logits
 
-    def backward(self, flat_params, xs, dlogits, grads_flat: torch.Tensor, enabled_mask: int = 0b111, win_start=None):
+    def backward(self, flat_params, xs, dlogits, grads_flat: torch.Tensor, enabled_mask: int = 0b111, win_start=None,
+                 dtype: int = _lib.DTYPE_F32):
         B = self._check_inputs(xs, win_start)
         ws = self.workspace(B, self.gbuf_floats + 64)
         check(lib().gaitk_backward(self._h, flat_params.data_ptr(),
                                    ptr_array([0 if x is None else x.data_ptr() for x in xs]),
                                    None if win_start is None else ptr_array([0 if w is None else w.data_ptr() for w in win_start]),
                                    B, enabled_mask, ptr_array([0 if d is None else d.data_ptr() for d in dlogits]),
-                                   grads_flat.data_ptr(), ws.data_ptr(), ws.numel(), _lib.DTYPE_F32, stream_handle()),
+                                   grads_flat.data_ptr(), ws.data_ptr(), ws.numel(), int(dtype), stream_handle()),
               "gaitk_backward")
 
 
@@ -120,6 +128,7 @@ class FlatParamModule(torch.nn.Module):
 
     _plan: Optional[Plan] = None
     _flat: Optional[torch.Tensor] = None
+    compute_dtype: int = _lib.DTYPE_F32      # _lib.DTYPE_TF32 selects the tcgen05 / mma.sync tensor-core kernels
 
     def _plan_kwargs(self) -> dict:  # pragma: no cover - abstract
         raise NotImplementedError
@@ -178,7 +187,9 @@ class _StreamsFn(torch.autograd.Function):
         xs = list(args[:n_streams])
         plan = module.plan()
         flat = module.flat_params()
-        logits = plan.forward(flat, xs, enabled_mask)
+        dtype = int(getattr(module, 'compute_dtype', _lib.DTYPE_F32))
+        logits = plan.forward(flat, xs, enabled_mask, dtype=dtype)
+        ctx.dtype = dtype
         ctx.module = module; ctx.enabled_mask = enabled_mask; ctx.n_streams = n_streams
         ctx.xs = xs
         ctx.set_materialize_grads(False)
@@ -192,7 +203,7 @@ class _StreamsFn(torch.autograd.Function):
         dls = [None if (d is None or ctx.xs[s] is None) else d.contiguous().float() for s, d in enumerate(dls)]
         grads = torch.zeros(plan.NP, dtype=torch.float32, device=plan.device)
         if any(d is not None for d in dls):
-            plan.backward(flat, ctx.xs, dls, grads, ctx.enabled_mask)
+            plan.backward(flat, ctx.xs, dls, grads, ctx.enabled_mask, dtype=ctx.dtype)
         touched = set()
         for s, d in enumerate(dls):
             if d is not None:
