@@ -77,54 +77,76 @@ GAITK_HD inline bool cg_solve_small(double K[4][4], double* r, int m) {
 }
 
 // min 1/2 s^T B s + g^T s   s.t.  sum s = c0,  lo <= s <= hi     (B positive definite, n <= 3)
+// One bound-activity pattern `comb` (base-3 digits: 0 free, 1 at lower, 2 at upper): solve the equality-
+// constrained sub-problem and check the KKT conditions.  Returns true with (s, val) when it is THE solution.
+GAITK_HD inline bool cg_qp_combo(const double B[3][3], const double* g, const double* lo, const double* hi, double c0, int n,
+                                 int comb, double* s, double* val_out) {
+    int st[3]; { int t = comb; for (int i = n - 1; i >= 0; --i) { st[i] = t % 3; t /= 3; } }
+    int F[3], nf = 0; double fixed_sum = 0;
+    for (int i = 0; i < 3; ++i) s[i] = 0.0;
+    for (int i = 0; i < n; ++i) { if (st[i] == 0) F[nf++] = i; else { s[i] = st[i] == 1 ? lo[i] : hi[i]; fixed_sum += s[i]; } }
+    const double rhs_sum = c0 - fixed_sum;
+    double lam = 0; bool has_lam = false;
+    if (nf == 0) {
+        if (fabs(rhs_sum) > 1e-12) return false;
+    } else {
+        double K[4][4]; double r[4];
+        for (int a = 0; a < nf; ++a) {
+            for (int b = 0; b < nf; ++b) K[a][b] = B[F[a]][F[b]];
+            K[a][nf] = 1.0; K[nf][a] = 1.0;
+            double acc = -g[F[a]];
+            for (int j = 0; j < n; ++j) if (st[j] != 0) acc -= B[F[a]][j] * s[j];
+            r[a] = acc;
+        }
+        K[nf][nf] = 0.0; r[nf] = rhs_sum;
+        if (!cg_solve_small(K, r, nf + 1)) return false;
+        for (int a = 0; a < nf; ++a) s[F[a]] = r[a];
+        lam = r[nf]; has_lam = true;
+    }
+    for (int a = 0; a < nf; ++a) { const int i = F[a]; if (s[i] < lo[i] - 1e-13 || s[i] > hi[i] + 1e-13) return false; }
+    double grad[3];
+    for (int i = 0; i < n; ++i) { grad[i] = g[i]; for (int j = 0; j < n; ++j) grad[i] += B[i][j] * s[j]; }
+    if (!has_lam) {
+        double lo_l = -INFINITY, hi_l = INFINITY;
+        for (int i = 0; i < n; ++i) { if (st[i] == 1) lo_l = fmax(lo_l, -grad[i]); else hi_l = fmin(hi_l, -grad[i]); }
+        if (lo_l > hi_l + 1e-12) return false;
+    } else {
+        for (int i = 0; i < n; ++i) {
+            if (st[i] == 0) continue;
+            const double m = grad[i] + lam, t = 1e-12 * fmax(1.0, fabs(grad[i]));
+            if (st[i] == 1 && m < -t) return false;
+            if (st[i] == 2 && m > t) return false;
+        }
+    }
+    double val = 0;
+    for (int i = 0; i < n; ++i) { val += g[i] * s[i]; for (int j = 0; j < n; ++j) val += 0.5 * s[i] * B[i][j] * s[j]; }
+    *val_out = val;
+    return true;
+}
+
 GAITK_HD inline void cg_qp(const double B[3][3], const double* g, const double* lo, const double* hi, double c0, int n, double* s_out) {
     int ncomb = 1; for (int i = 0; i < n; ++i) ncomb *= 3;
+#if defined(__CUDA_ARCH__)
+    // device: the <= 27 patterns are evaluated by the lanes of the (fully active) calling warp
+    const int lane = threadIdx.x & 31;
+    double s[3] = {0, 0, 0}, val = INFINITY;
+    const bool ok = lane < ncomb && cg_qp_combo(B, g, lo, hi, c0, n, lane, s, &val);
+    if (!ok) val = INFINITY;
+    double best = val; int who = lane;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (ov < best || (ov == best && ow < who)) { best = ov; who = ow; }
+    }
+    for (int i = 0; i < 3; ++i) { const double v = __shfl_sync(0xffffffffu, s[i], who); s_out[i] = (best < INFINITY && i < n) ? v : 0.0; }
+#else
     double best_val = 0; bool have = false;
-    for (int i = 0; i < n; ++i) s_out[i] = 0.0;
+    for (int i = 0; i < 3; ++i) s_out[i] = 0.0;
     for (int comb = 0; comb < ncomb; ++comb) {
-        int st[3]; { int t = comb; for (int i = n - 1; i >= 0; --i) { st[i] = t % 3; t /= 3; } }   // 0 free, 1 lower, 2 upper
-        double s[3] = {0, 0, 0}; int F[3], nf = 0; double fixed_sum = 0;
-        for (int i = 0; i < n; ++i) { if (st[i] == 0) F[nf++] = i; else { s[i] = st[i] == 1 ? lo[i] : hi[i]; fixed_sum += s[i]; } }
-        const double rhs_sum = c0 - fixed_sum;
-        double lam = 0; bool has_lam = false;
-        if (nf == 0) {
-            if (fabs(rhs_sum) > 1e-12) continue;
-        } else {
-            double K[4][4]; double r[4];
-            for (int a = 0; a < nf; ++a) {
-                for (int b = 0; b < nf; ++b) K[a][b] = B[F[a]][F[b]];
-                K[a][nf] = 1.0; K[nf][a] = 1.0;
-                double acc = -g[F[a]];
-                for (int j = 0; j < n; ++j) if (st[j] != 0) acc -= B[F[a]][j] * s[j];
-                r[a] = acc;
-            }
-            K[nf][nf] = 0.0; r[nf] = rhs_sum;
-            if (!cg_solve_small(K, r, nf + 1)) continue;
-            for (int a = 0; a < nf; ++a) s[F[a]] = r[a];
-            lam = r[nf]; has_lam = true;
-        }
-        bool ok = true;
-        for (int a = 0; a < nf; ++a) { const int i = F[a]; if (s[i] < lo[i] - 1e-13 || s[i] > hi[i] + 1e-13) ok = false; }
-        if (!ok) continue;
-        double grad[3];
-        for (int i = 0; i < n; ++i) { grad[i] = g[i]; for (int j = 0; j < n; ++j) grad[i] += B[i][j] * s[j]; }
-        if (!has_lam) {
-            double lo_l = -INFINITY, hi_l = INFINITY;
-            for (int i = 0; i < n; ++i) { if (st[i] == 1) lo_l = fmax(lo_l, -grad[i]); else hi_l = fmin(hi_l, -grad[i]); }
-            if (lo_l > hi_l + 1e-12) continue;
-        } else {
-            for (int i = 0; i < n; ++i) {
-                if (st[i] == 0) continue;
-                const double m = grad[i] + lam, t = 1e-12 * fmax(1.0, fabs(grad[i]));
-                if (st[i] == 1 && m < -t) ok = false;
-                if (st[i] == 2 && m > t) ok = false;
-            }
-            if (!ok) continue;
-        }
-        double val = 0;
-        for (int i = 0; i < n; ++i) { val += g[i] * s[i]; for (int j = 0; j < n; ++j) val += 0.5 * s[i] * B[i][j] * s[j]; }
+        double s[3], val;
+        if (!cg_qp_combo(B, g, lo, hi, c0, n, comb, s, &val)) continue;
         if (!have || val < best_val - 1e-15) { have = true; best_val = val; for (int i = 0; i < n; ++i) s_out[i] = s[i]; }
     }
+#endif
 }
 
 // SLSQP iteration from x = 1/n.  Returns the exit mode (0 converged, 8 positive directional derivative,

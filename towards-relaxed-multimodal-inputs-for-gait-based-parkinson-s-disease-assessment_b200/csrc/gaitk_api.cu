@@ -412,7 +412,7 @@ static int launch_reduce(const gaitk_plan* pl, int s, const float* partial, int 
     for (int i = 0; i < sp.nseg; ++i) R.seg[i] = sp.seg[i];
     R.gbuf = gbuf; R.P = pl->P; R.NP = pl->NP; R.task = task; R.private_mult = mult; R.stat_slot = stat_slot;
     const int n = R.NG + 2;
-    reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(R);
+    reduce_partials_kernel<<<(n + 127) / 128, dim3(128, 8), 0, st>>>(R);
     LAUNCH_CHECK();
     return 0;
 }
@@ -514,7 +514,7 @@ extern "C" int gaitk_step_update(gaitk_plan* pl, float* params, float* momentum,
     U.params = params; U.momentum = momentum; U.gbuf = gbuf; U.grads_out = grads_out; U.diag = diag;
     U.task_mask = task_mask; U.n_tasks_max = pl->n_streams; U.alpha = cagrad_c; U.max_norm = max_norm;
     U.lr = lr; U.mom = mom; U.wd = weight_decay; U.do_sgd = do_sgd ? 1 : 0; U.solver = solver;
-    cagrad_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(U);
+    cagrad_update_kernel<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(U);
     LAUNCH_CHECK();
     return 0;
 }
@@ -528,7 +528,7 @@ extern "C" int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float m
     U.ps[0].off = 0; U.ps[0].numel = P; U.ps[0].shared_off = 0; U.ps[0].has_grad = 1;
     U.grads_out = shared_grad; U.diag = diag; U.task_mask = (1u << n_tasks) - 1u; U.n_tasks_max = n_tasks;
     U.alpha = c; U.max_norm = max_norm; U.do_sgd = 0; U.solver = solver;
-    cagrad_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(U);
+    cagrad_update_kernel<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(U);
     LAUNCH_CHECK();
     return 0;
 }
@@ -621,28 +621,46 @@ extern "C" int gaitk_loss(const float* logits, const int64_t* y, int B, int K, c
     return 0;
 }
 
-struct DenomArgs { const long long* y[GAITK_MAX_STREAMS]; int count[GAITK_MAX_STREAMS]; float cls_w[GAITK_MAX_STREAMS][KMAX]; int n; };
-__global__ void __launch_bounds__(256) denom_kernel(DenomArgs D, float* denom) {
-    __shared__ double sh[256];
+struct DenomArgs { const long long* y[GAITK_MAX_STREAMS]; int count[GAITK_MAX_STREAMS]; float cls_w[GAITK_MAX_STREAMS][KMAX]; int same_as[GAITK_MAX_STREAMS]; int n; };
+// one CTA per distinct label vector: class histogram (exact integers) -> sum_c count_c * w_c in fp64
+__global__ void __launch_bounds__(1024) denom_kernel(DenomArgs D, float* denom) {
+    __shared__ int hist[32][KMAX];
     const int s = blockIdx.x;
-    double acc = 0;
+    if (D.same_as[s] != s) return;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const long long* y = D.y[s];
     for (int b = threadIdx.x; b < D.count[s]; b += blockDim.x) {
-        const int yy = (int)D.y[s][b];
-        acc += (double)(yy == 0 ? D.cls_w[s][0] : yy == 1 ? D.cls_w[s][1] : yy == 2 ? D.cls_w[s][2] : D.cls_w[s][3]);
+        const int yy = (int)y[b];
+        c0 += yy == 0; c1 += yy == 1; c2 += yy == 2; c3 += yy == 3;
     }
-    sh[threadIdx.x] = acc; __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) denom[s] = (float)sh[0];
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (lane == 0) { hist[wrp][0] = c0; hist[wrp][1] = c1; hist[wrp][2] = c2; hist[wrp][3] = c3; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long h[KMAX] = {0, 0, 0, 0};
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) for (int k = 0; k < KMAX; ++k) h[k] += hist[w][k];
+        for (int t = 0; t < D.n; ++t) {
+            if (D.same_as[t] != s) continue;
+            double acc = 0;
+            for (int k = 0; k < KMAX; ++k) acc += (double)h[k] * (double)D.cls_w[t][k];
+            denom[t] = (float)acc;
+        }
+    }
 }
 extern "C" int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_streams, const gaitk_loss_desc* loss,
                                        float* denom, void* stream) {
     if (!y || !counts || !loss || !denom || n_streams < 1 || n_streams > GAITK_MAX_STREAMS) return fail(GAITK_E_BADARG, "bad argument");
     DenomArgs D; memset(&D, 0, sizeof(D)); D.n = n_streams;
     for (int s = 0; s < n_streams; ++s) {
-        D.y[s] = (const long long*)y[s]; D.count[s] = counts[s];
+        D.y[s] = (const long long*)y[s]; D.count[s] = counts[s]; D.same_as[s] = s;
+        for (int t = 0; t < s; ++t) if (y[t] == y[s] && counts[t] == counts[s]) { D.same_as[s] = D.same_as[t]; break; }
         for (int k = 0; k < KMAX; ++k) D.cls_w[s][k] = loss[s].cls_weight[k];
     }
-    denom_kernel<<<n_streams, 256, 0, (cudaStream_t)stream>>>(D, denom);
+    denom_kernel<<<n_streams, 1024, 0, (cudaStream_t)stream>>>(D, denom);
     LAUNCH_CHECK();
     return 0;
 }

@@ -26,19 +26,24 @@ struct ReduceArgs {
     int task; float private_mult; int stat_slot;         // stat_slot < 0: do not record loss/correct
 };
 
-// sum the per-CTA partial rows in fixed order, then add into gbuf (passes run in launch order)
-__global__ void reduce_partials_kernel(const ReduceArgs R) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= R.NG + 2) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const float* p = R.partial + e;
-    int g = 0;
-    for (; g + 3 < R.grid; g += 4) {
-        s0 += p[(size_t)g * R.NGP]; s1 += p[(size_t)(g + 1) * R.NGP];
-        s2 += p[(size_t)(g + 2) * R.NGP]; s3 += p[(size_t)(g + 3) * R.NGP];
+// sum the per-CTA partial rows in fixed order (8 row slices per output, combined in slice order), then add
+// into gbuf (passes run in launch order).  blockDim = (128, 8).
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const ReduceArgs R) {
+    __shared__ float sh[8][128];
+    const int e = blockIdx.x * 128 + threadIdx.x, sl = threadIdx.y;
+    float s0 = 0.f, s1 = 0.f;
+    if (e < R.NG + 2) {
+        const float* p = R.partial + e;
+        int g = sl;
+        for (; g + 8 < R.grid; g += 16) { s0 += p[(size_t)g * R.NGP]; s1 += p[(size_t)(g + 8) * R.NGP]; }
+        if (g < R.grid) s0 += p[(size_t)g * R.NGP];
     }
-    for (; g < R.grid; ++g) s0 += p[(size_t)g * R.NGP];
-    const float s = (s0 + s1) + (s2 + s3);
+    sh[sl][threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (sl != 0 || e >= R.NG + 2) return;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
     float* G = R.gbuf; float* PG = R.gbuf + (size_t)MAXT * R.P; float* ST = PG + R.NP;
     if (e >= R.NG) {
         if (R.stat_slot >= 0) ST[(e - R.NG) * 4 + R.stat_slot] += s;
@@ -64,25 +69,17 @@ struct UpdateArgs {
     int do_sgd, solver;
 };
 
-// block-wide sum of doubles (blockDim.x multiple of 32, <= 1024)
-__device__ inline double block_sum_d(double v, double* sh) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    if (lane == 0) sh[wrp] = v;
-    __syncthreads();
-    double s = 0;
-    for (int i = 0; i < nw; ++i) s += sh[i];
-    return s;
-}
-
-// single CTA: Gram -> solve -> combine -> clip -> (optional) SGD over the flat parameter buffer
-__global__ void __launch_bounds__(1024) cagrad_update_kernel(const UpdateArgs U) {
-    __shared__ double shd[32];
+// single CTA: Gram -> solve -> combine -> clip -> (optional) SGD over the flat parameter buffer.
+// Every thread first loads "its" parameter / momentum / gradient elements (<= EPT each), so that global
+// latency overlaps the latency-bound simplex solve that warp 0 runs in between.
+constexpr int UPD_THREADS = 1024;
+constexpr int UPD_EPT = 8;                                  // elements per thread: NP <= 8192 per pass
+__global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const UpdateArgs U) {
+    __shared__ double shd[6][32];
     __shared__ double coef[MAXT];
     __shared__ int tl[MAXT];
     __shared__ int nt_s;
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wrp = tid >> 5;
     const float* G = U.gbuf; const float* PG = U.gbuf + (size_t)MAXT * U.P;
     if (tid == 0) {
         int n = 0;
@@ -91,18 +88,32 @@ __global__ void __launch_bounds__(1024) cagrad_update_kernel(const UpdateArgs U)
     }
     __syncthreads();
     const int n = nt_s;
+    const int t0 = tl[0], t1 = n > 1 ? tl[1] : tl[0], t2 = n > 2 ? tl[2] : tl[0];
+    // ---- Gram matrix: one pass, one combined block reduction (fp64)
     double gg[6] = {0, 0, 0, 0, 0, 0};     // 00 01 02 11 12 22
     for (int p = tid; p < U.P; p += nth) {
-        double v[MAXT];
-        for (int i = 0; i < MAXT; ++i) v[i] = i < n ? (double)G[(size_t)tl[i] * U.P + p] : 0.0;
-        gg[0] += v[0] * v[0]; gg[1] += v[0] * v[1]; gg[2] += v[0] * v[2];
-        gg[3] += v[1] * v[1]; gg[4] += v[1] * v[2]; gg[5] += v[2] * v[2];
+        const double v0 = (double)G[(size_t)t0 * U.P + p];
+        const double v1 = n > 1 ? (double)G[(size_t)t1 * U.P + p] : 0.0;
+        const double v2 = n > 2 ? (double)G[(size_t)t2 * U.P + p] : 0.0;
+        gg[0] += v0 * v0; gg[1] += v0 * v1; gg[2] += v0 * v2; gg[3] += v1 * v1; gg[4] += v1 * v2; gg[5] += v2 * v2;
     }
-    for (int i = 0; i < 6; ++i) gg[i] = block_sum_d(gg[i], shd);
-    if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        for (int o = 16; o > 0; o >>= 1) gg[i] += __shfl_xor_sync(0xffffffffu, gg[i], o);
+        if (lane == 0) shd[i][wrp] = gg[i];
+    }
+    // ---- this thread's elements of the flat parameter buffer (loads in flight during the solve)
+    const long long total = U.NP > 0 ? U.NP : (U.nparams ? U.ps[0].numel : 0);      // gaitk_cagrad: one pseudo-parameter
+    const int passes = (int)((total + (long long)nth * UPD_EPT - 1) / ((long long)nth * UPD_EPT));
+    __syncthreads();
+    if (tid < 32) {
+        // warp 0 runs the solve (all lanes redundantly; the QP enumeration is lane-parallel)
+        double g6[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { double s = 0; for (int w = 0; w < (nth >> 5); ++w) s += shd[i][w]; g6[i] = s; }
         // the reference forms GG in fp32 (torch mm) and hands the fp32 values to SciPy
-        const float a[3][3] = {{(float)gg[0], (float)gg[1], (float)gg[2]}, {(float)gg[1], (float)gg[3], (float)gg[4]},
-                               {(float)gg[2], (float)gg[4], (float)gg[5]}};
+        const float a[3][3] = {{(float)g6[0], (float)g6[1], (float)g6[2]}, {(float)g6[1], (float)g6[3], (float)g6[4]},
+                               {(float)g6[2], (float)g6[4], (float)g6[5]}};
         Quad3 q;
         for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) q.A[i][j] = (double)a[i][j];
         double w[3] = {0, 0, 0}; double c = 0; int iters = 0;
@@ -121,8 +132,8 @@ __global__ void __launch_bounds__(1024) cagrad_update_kernel(const UpdateArgs U)
         const double norm = sqrt(norm2 > 0 ? norm2 : 0);
         double clip = 1.0;
         if (U.max_norm > 0) { clip = (double)U.max_norm / (norm + 1e-6); if (clip > 1.0) clip = 1.0; }
-        for (int i = 0; i < MAXT; ++i) coef[i] = i < n ? k[i] * clip : 0.0;
-        if (U.diag) {
+        if (tid == 0) for (int i = 0; i < MAXT; ++i) coef[i] = i < n ? k[i] * clip : 0.0;
+        if (U.diag && tid == 0) {
             for (int i = 0; i < 3; ++i) U.diag[i] = 0.f;
             for (int i = 0; i < n; ++i) U.diag[tl[i]] = (float)w[i];
             for (int i = 0; i < 9; ++i) U.diag[3 + i] = 0.f;
@@ -130,28 +141,46 @@ __global__ void __launch_bounds__(1024) cagrad_update_kernel(const UpdateArgs U)
             U.diag[12] = (float)norm; U.diag[13] = (float)cg_obj(q, w, n); U.diag[14] = (float)iters; U.diag[15] = (float)clip;
         }
     }
-    __syncthreads();
-    const float k0 = (float)coef[0], k1 = (float)coef[1], k2 = (float)coef[2];
-    const int t0 = tl[0], t1 = n > 1 ? tl[1] : tl[0], t2 = n > 2 ? tl[2] : tl[0];
-    for (int ip = 0; ip < U.nparams; ++ip) {
-        const ParamSeg s = U.ps[ip];
-        for (int e = tid; e < s.numel; e += nth) {
-            float g;
+    for (int pass = 0; pass < passes; ++pass) {
+        // gather phase (before the barrier that publishes the coefficients): element -> segment, loads
+        float gsh0[UPD_EPT], gsh1[UPD_EPT], gsh2[UPD_EPT], pv[UPD_EPT], mv[UPD_EPT];
+        int kind[UPD_EPT];                                  // 0 none, 1 shared, 2 private ; bit 2: has_grad
+#pragma unroll
+        for (int j = 0; j < UPD_EPT; ++j) {
+            const long long e = (long long)pass * nth * UPD_EPT + (long long)j * nth + tid;
+            kind[j] = 0; gsh0[j] = gsh1[j] = gsh2[j] = 0.f; pv[j] = mv[j] = 0.f;
+            if (e >= total) continue;
+            int ip = 0;
+            for (int i = 1; i < U.nparams; ++i) if (e >= U.ps[i].off) ip = i;       // segments are sorted by offset
+            const ParamSeg s = U.ps[ip];
+            const int o = (int)(e - s.off);
             if (s.shared_off >= 0) {
-                const size_t p = (size_t)s.shared_off + e;
-                g = k0 * G[(size_t)t0 * U.P + p];
-                if (n > 1) g = fmaf(k1, G[(size_t)t1 * U.P + p], g);
-                if (n > 2) g = fmaf(k2, G[(size_t)t2 * U.P + p], g);
+                const size_t p = (size_t)s.shared_off + o;
+                gsh0[j] = G[(size_t)t0 * U.P + p];
+                if (n > 1) gsh1[j] = G[(size_t)t1 * U.P + p];
+                if (n > 2) gsh2[j] = G[(size_t)t2 * U.P + p];
+                kind[j] = 1;
             } else {
-                g = PG[s.off + e];
+                gsh0[j] = PG[e]; kind[j] = 2;
             }
-            if (U.grads_out) U.grads_out[s.off + e] = s.has_grad ? g : 0.f;
-            if (U.do_sgd && s.has_grad) {
-                const float p = U.params[s.off + e];
-                g = fmaf(U.wd, p, g);
-                const float b = fmaf(U.mom, U.momentum[s.off + e], g);
-                U.momentum[s.off + e] = b;
-                U.params[s.off + e] = p - U.lr * b;
+            if (s.has_grad) kind[j] |= 4;
+            if (U.do_sgd && s.has_grad) { pv[j] = U.params[e]; mv[j] = U.momentum[e]; }
+        }
+        if (pass == 0) __syncthreads();                    // coefficients from the solve
+        const float k0 = (float)coef[0], k1 = (float)coef[1], k2 = (float)coef[2];
+#pragma unroll
+        for (int j = 0; j < UPD_EPT; ++j) {
+            const long long e = (long long)pass * nth * UPD_EPT + (long long)j * nth + tid;
+            if (e >= total || kind[j] == 0) continue;
+            float g = gsh0[j];
+            if ((kind[j] & 3) == 1) { g = k0 * gsh0[j]; if (n > 1) g = fmaf(k1, gsh1[j], g); if (n > 2) g = fmaf(k2, gsh2[j], g); }
+            const bool hg = (kind[j] & 4) != 0;
+            if (U.grads_out) U.grads_out[e] = hg ? g : 0.f;
+            if (U.do_sgd && hg) {
+                g = fmaf(U.wd, pv[j], g);
+                const float b = fmaf(U.mom, mv[j], g);
+                U.momentum[e] = b;
+                U.params[e] = pv[j] - U.lr * b;
             }
         }
     }
