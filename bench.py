@@ -186,7 +186,8 @@ def run_gpu(args):
         g = torch.cat(ys); return [g, g, g]
 
     def synth_labels_only(Bn, seed):
-        return synth(Bn, seed)[1]
+        import gait_oracle as O
+        return O.synth_weargait_labels(Bn, seed=seed)
     yglob = [global_labels(i) for i in range(NBUF)]
     l2_flush = None
     if B * BYTES_PER_WINDOW < 2 * 126e6:               # small batches: flush L2 between steps instead
@@ -249,6 +250,7 @@ def run_gpu(args):
         peak, peak_src = peaks()
         names = ("walkway", "insole", "imu")
         scratch = torch.empty(model.plan().NP, dtype=torch.float32, device=dev)
+        step.pg = False                                   # rank-local timing: no collective in this section
         for s in range(3):
             tasks = [k == s for k in range(3)]
             xs, y = devb[0]

@@ -626,6 +626,15 @@ def synth_weargait_batch(B: int, T: int = 64, seed: int = 0, p_pd: float = 0.6):
     return [xw, xi, xm], y
 
 
+def synth_weargait_labels(B: int, seed: int = 0, p_pd: float = 0.6):
+    """The label vector synth_weargait_batch(B, seed=seed) returns, without generating the sensor data."""
+    rng = np.random.default_rng(seed)
+    y = (rng.random(B) < p_pd).astype(np.int64)
+    if B > 1:
+        y[0], y[1] = 0, 1
+    return y
+
+
 def synth_fog_batch(B: int, seed: int = 0, pose_len=101, sens_len=426, joints=7, sens_ch=6):
     rng = np.random.default_rng(seed)
     y = rng.choice(3, size=B, p=[0.5, 0.3, 0.2]).astype(np.int64)
