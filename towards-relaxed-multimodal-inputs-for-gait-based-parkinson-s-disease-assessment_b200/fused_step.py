@@ -36,6 +36,7 @@ class FusedTrainStep:
         self.dtype = int(getattr(model, 'compute_dtype', _lib.DTYPE_F32) if dtype is None else dtype)
         self._mom = None; self._gbuf = None; self._denom = None; self._diag = None
         self._pinned = {}; self._dev_in = {}
+        self._copy_stream = None; self._staged = {}; self._slot_free = {}
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, plan):
@@ -116,20 +117,66 @@ class FusedTrainStep:
                                       diag.data_ptr(), self.solver, st), "gaitk_step_update")
         return self.stats()
 
-    # ------------------------------------------------------------------ end-to-end (host batch) entry
+    # ------------------------------------------------------------------ end-to-end (host batch) entries
     def step_host(self, xs_host: Sequence[torch.Tensor], ys_host: Sequence[torch.Tensor], **kw):
         """The call a trainer makes with a DataLoader batch: pinned host tensors in, H2D copies on the
         current stream, fused step, and a device->host read of (loss, correct)."""
-        dev = self.model.plan().device if self.model._plan is not None else torch.device("cuda", torch.cuda.current_device())
-        xs = [self._to_dev(("x", i), x, dev) for i, x in enumerate(xs_host)]
+        self.stage_host(xs_host, ys_host, slot=0)
+        return self.step_staged(slot=0, **kw)
+
+    def stage_host(self, xs_host: Sequence[torch.Tensor], ys_host: Sequence[torch.Tensor], slot: int = 0):
+        """Start the H2D copy of a (pinned) host batch into device slot `slot` on the copy stream and return
+        immediately.  With two slots the copy of batch i+1 runs under the compute of batch i:
+
+            step.stage_host(b0, y0, 0)
+            for i in range(n):
+                if i + 1 < n: step.stage_host(b[i+1], y[i+1], (i + 1) % 2)
+                out = step.step_staged(i % 2)
+        """
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+        ev_free = self._slot_free.get(slot)
+        with torch.cuda.stream(self._copy_stream):
+            if ev_free is not None:
+                self._copy_stream.wait_event(ev_free)          # the step that last read this slot has finished
+            xs = [self._to_dev((slot, "x", i), x, dev) for i, x in enumerate(xs_host)]
+            same = all(y is ys_host[0] for y in ys_host)
+            if same:
+                y0 = self._to_dev((slot, "y", 0), ys_host[0], dev); ys = [y0] * len(ys_host)
+            else:
+                ys = [self._to_dev((slot, "y", i), y, dev) for i, y in enumerate(ys_host)]
+            ev = torch.cuda.Event(); ev.record(self._copy_stream)
+        self._staged[slot] = (xs, ys, ev)
+
+    def step_staged(self, slot: int = 0, **kw):
+        xs, ys, ev = self._staged[slot]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        loss, correct = self.step(xs, ys, **kw)
+        done = torch.cuda.Event(); done.record(cur); self._slot_free[slot] = done
+        return torch.cat([loss, correct]).to("cpu", non_blocking=False)
+
+    # ------------------------------------------------------------------ device-resident dataset entry
+    def step_indices(self, stores: Sequence[torch.Tensor], win_start_host: Sequence[torch.Tensor],
+                     ys_host: Sequence[torch.Tensor], **kw):
+        """B200-first data path: the normalised frame stores (N_frames, D) live in HBM for the whole fold
+        (uploaded once, like prepare_split runs once per fold); per step the host sends only the window
+        start indices (int64[B], pinned) and the labels; the stream kernels gather the windows themselves."""
+        dev = stores[0].device
+        same_w = all(w is win_start_host[0] for w in win_start_host)
+        if same_w:
+            w0 = self._to_dev(("w", 0), win_start_host[0], dev); ws = [w0] * len(win_start_host)
+        else:
+            ws = [self._to_dev(("w", i), w, dev) for i, w in enumerate(win_start_host)]
         same = all(y is ys_host[0] for y in ys_host)
         if same:
-            y0 = self._to_dev(("y", 0), ys_host[0], dev); ys = [y0] * len(ys_host)
+            y0 = self._to_dev(("yi", 0), ys_host[0], dev); ys = [y0] * len(ys_host)
         else:
-            ys = [self._to_dev(("y", i), y, dev) for i, y in enumerate(ys_host)]
-        loss, correct = self.step(xs, ys, **kw)
-        out = torch.cat([loss, correct]).to("cpu", non_blocking=False)
-        return out
+            ys = [self._to_dev(("yi", i), y, dev) for i, y in enumerate(ys_host)]
+        loss, correct = self.step(list(stores), ys, win_start=ws, **kw)
+        return torch.cat([loss, correct]).to("cpu", non_blocking=False)
 
     def _to_dev(self, key, t, dev):
         buf = self._dev_in.get(key)
