@@ -474,3 +474,56 @@ def test_tf32_path_large_batch_vs_fp32_path(gk):
     assert np.abs(b[1] - a[1]).max() <= 0.002 * B           # argmax flips only on near-ties
     assert relerr(b[2], a[2]) < 1e-3, relerr(b[2], a[2])          # shared-gradient matrix G
     assert relerr(b[3], a[3]) < 4e-3, relerr(b[3], a[3])          # all final gradients (private ones dominate)
+
+
+def test_end_to_end_training_matches_oracle(gk):
+    """30 training steps + evaluation under the 7 modality masks: fused CUDA path vs the CPU oracle on the same
+    data / seeds.  north_star: end-to-end metrics within 0.5 points."""
+    import gait_oracle as O
+    torch.manual_seed(11)
+    m = gk.WearGaitThreeModal().cuda()
+    state = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    p = O.canonical_params(state, True); bufs = {}
+    B, steps = 64, 30
+    counts = [[130, 190]] * 3
+    crit = [gk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in counts]
+    st = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, lr=1e-2, process_group=False)
+    tl_gpu, tl_cpu = [], []
+    for it in range(steps):
+        xs, y = O.synth_weargait_batch(B, seed=1000 + it % 5)
+        loss, _ = st.step([dev(x) for x in xs], [dev(y)] * 3)
+        ex = O.weargait_train_step(p, bufs, [torch.from_numpy(x) for x in xs], [torch.from_numpy(y)] * 3, synchronized=True,
+                                   wm="gcl", counts=counts, alpha=0.5, lr=1e-2)
+        tl_gpu.append(loss.cpu().numpy()); tl_cpu.append(np.array(ex["losses"]))
+    close(np.array(tl_gpu), np.array(tl_cpu), 2e-3, "loss trajectory")
+    # held-out evaluation under every mask (weargait_train.eval_with_mask, sync ensemble)
+    xs, y = O.synth_weargait_batch(512, seed=77)
+    xd = [dev(x) for x in xs]; yd = dev(y); xt = [torch.from_numpy(x) for x in xs]; yt = torch.from_numpy(y)
+    m.eval()
+    for name, mask in O.MASK_COMBOS.items():
+        with torch.no_grad():
+            lg = m(*xd, enabled=mask)
+        probs = [torch.softmax(l, 1) for l, u in zip(lg, mask) if u]
+        acc_gpu = 100.0 * float(((sum(probs) / len(probs)).argmax(1) == yd).sum()) / yd.numel()
+        c, n = O.eval_mask_sync(p, xt, yt, mask)
+        assert abs(acc_gpu - 100.0 * c / n) <= 0.5, (name, acc_gpu, 100.0 * c / n)
+
+
+def test_end_to_end_training_tf32_close_to_fp32(gk):
+    """Same protocol, tensor-core path vs fp32 path: accuracies within 0.5 points after 30 steps."""
+    import gait_oracle as O
+    accs = {}
+    for dt in (gk.DTYPE_F32, gk.DTYPE_TF32):
+        torch.manual_seed(11)
+        m = gk.WearGaitThreeModal().cuda(); m.compute_dtype = dt
+        crit = [gk.GCLLoss(cls_num_list=[130, 190], m=0.2, s=25, noise_mul=0.0) for _ in range(3)]
+        st = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, lr=1e-2, process_group=False, dtype=dt)
+        for it in range(30):
+            xs, y = O.synth_weargait_batch(256, seed=1000 + it % 5)
+            st.step([dev(x) for x in xs], [dev(y)] * 3)
+        xs, y = O.synth_weargait_batch(2048, seed=77)
+        with torch.no_grad():
+            lg = m(*[dev(x) for x in xs])
+        p = sum(torch.softmax(l, 1) for l in lg) / 3
+        accs[dt] = 100.0 * float((p.argmax(1) == dev(y)).sum()) / len(y)
+    assert abs(accs[gk.DTYPE_F32] - accs[gk.DTYPE_TF32]) <= 0.5, accs
