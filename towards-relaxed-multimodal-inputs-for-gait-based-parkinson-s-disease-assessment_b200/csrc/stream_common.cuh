@@ -166,6 +166,7 @@ struct HeadCtx {
     const float* Zs; int RB, halo, W, S; const int* bin_s; const int* bin_e;
     const float *hws, *hbs, *hngs, *hnbs, *inws; float* DPs;
     const float* Ps;      // optional pre-pooled features [W][NF] (already divided by the bin size)
+    const int* ys;        // optional labels of the tile's windows, prefetched to shared memory
 };
 
 template <int NFL, int SC>
@@ -243,7 +244,7 @@ struct HeadState {
                 for (int k = 0; k < KMAX; ++k) dl[k] = 0.f;
                 if (wi < A.B) {
                     if (A.mode == MODE_FUSED) {
-                        const int y = (int)A.y[wi];
+                        const int y = c.ys ? c.ys[w_] : (int)A.y[wi];
                         float zz[KMAX]; float mx = -INFINITY; int am = 0; float best = -INFINITY;
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) if (k < K) {

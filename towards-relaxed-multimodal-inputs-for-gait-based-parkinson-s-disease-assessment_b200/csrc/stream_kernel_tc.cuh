@@ -135,6 +135,29 @@ __device__ __forceinline__ void issue_conv(uint32_t tmem_d, uint32_t a_base, int
     }
 }
 
+// The descriptors of a convolution do not depend on the tile: build them once per kernel into shared memory
+// (KT * KCH/2 pairs) so that issuing an MMA is two LDS.64 plus the instruction.
+template <int KT, int KCH, int N>
+__device__ __forceinline__ void build_conv_descs(uint64_t* tab, uint32_t a_base, int RBx, int halo, int W, uint32_t b_base) {
+    for (int i = 0; i < KT * (KCH / 2); ++i) {
+        const int tap = i / (KCH / 2), kp = i - tap * (KCH / 2);
+        const uint32_t a = a_base + (uint32_t)(((2 * kp) * RBx + halo + (tap - KT / 2) * W) * 16);
+        const uint32_t b = b_base + (uint32_t)(((tap * KCH + 2 * kp) * N) * 16);
+        tab[2 * i] = umma::make_desc(a, (uint32_t)RBx * 16u, 128u);
+        tab[2 * i + 1] = umma::make_desc(b, (uint32_t)N * 16u, 128u);
+    }
+}
+template <int KT, int KCH, int N>
+__device__ __forceinline__ void issue_conv_tab(uint32_t tmem_d, const uint64_t* tab) {
+    constexpr uint32_t idesc = umma::make_idesc_tf32(128, N, false, false);
+    constexpr int NM = KT * (KCH / 2);
+    uint64_t d[2 * NM];
+#pragma unroll
+    for (int i = 0; i < 2 * NM; ++i) d[i] = tab[i];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) umma::mma_tf32(tmem_d, d[2 * i], d[2 * i + 1], idesc, i != 0 ? 1u : 0u);
+}
+
 template <int N>
 __device__ __forceinline__ void store_row_tf32(float* buf, int RBx, int halo, int r, const float (&v)[N]) {
     float4* p = reinterpret_cast<float4*>(buf) + (halo + r);
@@ -150,11 +173,24 @@ __device__ __forceinline__ void tmem_row(uint32_t taddr, float (&v)[N]) {
     umma::ld_wait();
 }
 
+#ifdef GAITK_PHASE_TIMING
+#define PH(i) do { if (lane == 0) { const long long t_ = clock64(); ph_acc[wrp][i] += t_ - ph_last; ph_last = t_; } } while (0)
+#else
+#define PH(i) do { } while (0)
+#endif
+
 template <class Cfg>
 __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(const StreamArgs A, const TcPlan SP) {
     extern __shared__ __align__(1024) float sm[];
     __shared__ uint64_t bar, ldbar;
     __shared__ uint32_t tmem_slot;
+    __shared__ int ys_tile[2][WMAX];                      // labels of the current / next tile
+    __shared__ uint64_t dtab[5][2 * 12];                  // MMA descriptor pairs: conv1, conv2, bb, bb dgrad, conv2 dgrad
+#ifdef GAITK_PHASE_TIMING
+    __shared__ long long ph_acc[4][16];
+    long long ph_last = 0;
+    if (threadIdx.x < 64) ph_acc[threadIdx.x / 16][threadIdx.x % 16] = 0;
+#endif
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     constexpr int ENC = Cfg::ENC, CIN = Cfg::CIN, CI4 = Cfg::CI4, KT1 = Cfg::KT1, H = Cfg::H, H4 = Cfg::H4;
     constexpr int C = Cfg::C, C4 = Cfg::C4, CP = Cfg::CP, S = Cfg::S, S4 = Cfg::S4, NFL = Cfg::NFL;
@@ -238,6 +274,18 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
                    sZ = umma::smem_u32(Zs), sW1 = umma::smem_u32(w1b), sW2 = umma::smem_u32(w2b), sW2D = umma::smem_u32(w2d),
                    sWB = umma::smem_u32(wbb), sWBD = umma::smem_u32(wbd);
 
+    static_assert(KT1 * (KX / 2) <= 12 && 3 * (KH / 2) <= 12 && 3 * (KC / 2) <= 12 && 3 * (KS / 2) <= 12, "descriptor table size");
+    if (tid == 0) {
+        build_conv_descs<KT1, KX, N1>(dtab[0], sX, RB, halo, W, sW1);
+        if constexpr (ENC == ENC_INSOLE) {
+            build_conv_descs<3, KH, NC>(dtab[1], sHA, RB, halo, W, sW2);
+            build_conv_descs<3, KC, NH>(dtab[4], sXH, RB, halo, W, sW2D);
+        }
+        build_conv_descs<3, KC, NS>(dtab[2], sF, RB, halo, W, sWB);
+        build_conv_descs<3, KS, NC>(dtab[3], sZ, RB, halo, W, sWBD);
+    }
+    __syncthreads();
+
     // ---- persistent accumulators
     WgradMma<KT1, CI4 * 4, (O1 + 7) / 8 * 8> g_w1;
     WgradMma<3, (ENC == ENC_INSOLE ? H4 * 4 : 4), (ENC == ENC_INSOLE ? NC : 8)> g_w2;
@@ -251,6 +299,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     const bool pool_shfl = binsz > 0 && (binsz & (binsz - 1)) == 0 && binsz * W <= 32;
     float* Ps = sm + SP.P;
     hc.Ps = pool_shfl ? Ps : nullptr;
+    hc.ys = nullptr;
     const int logW = 31 - __clz(W);                      // W is a power of two (planner)
     g_w1.zero(); g_w2.zero(); g_wb.zero();
 #pragma unroll
@@ -270,6 +319,8 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         __syncthreads();                                                    \
         if (tid == 0) { umma::fence_after_sync(); ISSUE; umma::commit(&bar); } \
     } while (0)
+#define GAITK_MMA_ISSUE_SYNCED(ISSUE)                                       \
+    do { if (tid == 0) { umma::fence_after_sync(); ISSUE; umma::commit(&bar); } } while (0)
 #define GAITK_MMA_WAIT()                                                    \
     do { umma::mbar_wait(&bar, phase); phase ^= 1u; umma::fence_after_sync(); } while (0)
 
@@ -279,8 +330,12 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     uint32_t ldphase = 0;
     // warp 0 prefetches the W windows of a tile into the staging buffer: one cp.async.bulk per window
     // (16-byte aligned source), or a plain copy for a window whose frame-store offset is not aligned.
+    int ylab_next = 0;
+    constexpr int PF_WARP = 3;                           // has slack in the backbone weight-gradient phase (owns no tile there)
     auto prefetch = [&](int tile) {
-        if (wrp != 0 || A.zero_input) return;
+        if (wrp != PF_WARP) return;
+        if (A.mode == MODE_FUSED && lane < W) { const int wi = tile * W + lane; ylab_next = wi < A.B ? (int)A.y[wi] : 0; }   // consumed later
+        if (A.zero_input) return;
         uint32_t bytes = 0;
         for (int w = 0; w < W; ++w) {
             const int wi = tile * W + w;
@@ -302,12 +357,17 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             }
         }
     };
-    if (blockIdx.x < ntiles) prefetch(blockIdx.x);
+    int yslot = 0;
+    if (blockIdx.x < ntiles) { prefetch(blockIdx.x); if (wrp == PF_WARP && lane < W) ys_tile[0][lane] = ylab_next; }
+#ifdef GAITK_PHASE_TIMING
+    __syncthreads(); ph_last = clock64();
+#endif
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int win0 = tile * W;
         // ================= staged window bytes -> Xs [chunk][row][4] (tf32)
         if (!A.zero_input) {
             umma::mbar_wait(&ldbar, ldphase); ldphase ^= 1u;
+            PH(0);
             if constexpr (CIN % 4 == 0) {
                 const int pw4 = per_win / 4;
                 for (int e = tid; e < W * pw4; e += NT) {
@@ -328,12 +388,16 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             }
         }
         umma::fence_smem_to_async(); umma::fence_before_sync();
+        PH(1);
         __syncthreads();                                   // Xs complete, staging buffer free again
-        if (tile + (int)gridDim.x < ntiles) prefetch(tile + (int)gridDim.x);
+        PH(2);
+        hc.ys = (A.mode == MODE_FUSED) ? ys_tile[yslot] : nullptr;
+        const bool has_next = tile + (int)gridDim.x < ntiles;
         // ================= encoder forward
         if constexpr (ENC == ENC_INSOLE) {
-            GAITK_MMA_PHASE((issue_conv<KT1, KX, N1>(tmem, sX, RB, halo, W, sW1)));
+            GAITK_MMA_ISSUE_SYNCED((issue_conv_tab<KT1, KX, N1>(tmem, dtab[0])));
             GAITK_MMA_WAIT();
+            PH(3);
             {
                 float a1[N1], ha[O1], d1[O1];
                 tmem_row<N1>(trow, a1);
@@ -342,11 +406,13 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
                 store_row_tf32<O1>(HAs, RB, halo, r, ha);
                 if (train) store_row<O1>(D1s, RB, halo, r, d1);
             }
-            GAITK_MMA_PHASE((issue_conv<3, KH, NC>(tmem, sHA, RB, halo, W, sW2)));
+            PH(4);
+            GAITK_MMA_PHASE((issue_conv_tab<3, KH, NC>(tmem, dtab[1])));
         } else {
-            GAITK_MMA_PHASE((issue_conv<KT1, KX, N1>(tmem, sX, RB, halo, W, sW1)));
+            GAITK_MMA_ISSUE_SYNCED((issue_conv_tab<KT1, KX, N1>(tmem, dtab[0])));
         }
         GAITK_MMA_WAIT();
+        PH(5);
         {
             float a[NC], g[CP], d[CP], xh[CP], f[CP]; float rstd;
             tmem_row<NC>(trow, a);
@@ -359,9 +425,11 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             store_row_tf32<CP>(Fs, RB, halo, r, f);
             if (train) { store_row<CP>(Ds, RB, halo, r, d); store_row<CP>(XHs, RB, halo, r, xh); RSTDs[r] = rstd; }
         }
+        PH(6);
         // ================= shared backbone forward
-        GAITK_MMA_PHASE((issue_conv<3, KC, NS>(tmem, sF, RB, halo, W, sWB)));
+        GAITK_MMA_PHASE((issue_conv_tab<3, KC, NS>(tmem, dtab[2])));
         GAITK_MMA_WAIT();
+        PH(7);
         {
             float z[NS];
             tmem_row<NS>(trow, z);
@@ -384,12 +452,16 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
                 }
             }
         }
+        PH(8);
         umma::fence_before_sync();
         __syncthreads();
+        PH(9);
         // ================= pool + head + loss (warp per window)
         if (wrp < W) head.run(A, hc, wrp, lane, win0, train, inv_denom);
-        if (!train) { __syncthreads(); continue; }
+        if (!train) { if (has_next) prefetch(tile + (int)gridDim.x); __syncthreads(); continue; }
+        PH(10);
         __syncthreads();
+        PH(11);
         // ================= dz through pool + ReLU, in place over Z (tf32: it is an MMA operand now)
         {
             const int t = r >> logW, w = r & (W - 1);
@@ -415,10 +487,14 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             for (int s = 0; s < S; ++s) { dz[s] = z[s] > 0.f ? dz[s] : 0.f; g_bb[s] += dz[s]; }
             store_row_tf32<S>(Zs, RB, halo, r, dz);
         }
+        PH(12);
         // backbone dgrad on the tensor core while all warps do the backbone weight gradient
-        GAITK_MMA_PHASE((issue_conv<3, KS, NC>(tmem, sZ, RB, halo, W, sWBD)));
+        GAITK_MMA_PHASE((issue_conv_tab<3, KS, NC>(tmem, dtab[3])));
+        if (has_next) prefetch(tile + (int)gridDim.x);          // TMA bulk copies + label loads for the next tile (warp 3)
         g_wb.accumulate(Fs, RB, Zs, RB, halo, W, rows, wrp, lane);
+        PH(13);
         GAITK_MMA_WAIT();
+        PH(14);
         {
             float df[NC], xh[CP], dxh[CP], dg[CP], da[CP], d[CP];
             tmem_row<NC>(trow, df);
@@ -445,7 +521,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         }
         if constexpr (ENC == ENC_INSOLE) {
             // conv2 dgrad on the tensor core, conv2 weight gradient on the warps
-            GAITK_MMA_PHASE((issue_conv<3, KC, NH>(tmem, sXH, RB, halo, W, sW2D)));
+            GAITK_MMA_PHASE((issue_conv_tab<3, KC, NH>(tmem, dtab[4])));
             g_w2.accumulate(HAs, RB, XHs, RB, halo, W, rows, wrp, lane);
             GAITK_MMA_WAIT();
             {
@@ -464,9 +540,22 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             __syncthreads();
             g_w1.accumulate(Xs, RB, XHs, RB, halo, W, rows, wrp, lane);
         }
+        if (has_next && wrp == PF_WARP && lane < W) ys_tile[yslot ^ 1][lane] = ylab_next;
+        yslot ^= 1;
+        PH(15);
         __syncthreads();
     }
+#ifdef GAITK_PHASE_TIMING
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        const int w = threadIdx.x;
+        printf("ENC%d CIN%d warp%d:", ENC, CIN, w);
+        for (int i = 0; i < 16; ++i) printf(" %lld", ph_acc[w][i] / max(1, (ntiles + (int)gridDim.x - 1) / (int)gridDim.x));
+        printf("\n");
+    }
+#endif
 #undef GAITK_MMA_PHASE
+#undef GAITK_MMA_ISSUE_SYNCED
 #undef GAITK_MMA_WAIT
 
     // ================= teardown + flush
