@@ -539,15 +539,26 @@ def weargait_private_keys(p: Params, synchronized: bool) -> List[List[str]]:
 
 
 def weargait_train_step(p: Params, bufs, xs, ys, *, synchronized=True, wm="gcl", counts=None,
-                        alpha=0.5, max_norm=1.0, lr=1e-3, momentum=0.9, wd=1e-4, **loss_kw):
-    """One train_one_epoch iteration :305-311: forward, 3 losses,
-    step_cagrad_three, SGD.  Mutates p/bufs; returns diagnostics."""
+                        alpha=0.5, max_norm=1.0, lr=1e-3, momentum=0.9, wd=1e-4, tasks=None, **loss_kw):
+    """One train_one_epoch iteration :305-311: forward, 3 losses, step_cagrad_three, SGD.  Mutates p/bufs;
+    returns diagnostics.
+
+    ``tasks`` (3 bools) is the relaxed-input training case of SURVEY 8(d) cfg 3(ii): a disabled stream is
+    zero-filled exactly as _maybe_zero (weargait_train.py:355-358) and its loss is passed as None, which
+    step_cagrad_three filters out (:200-203); CAGrad then runs with n_tasks = number of live losses (the
+    harness holds one CAGrad(n_tasks=k) per k, since get_weighted_loss indexes range(self.n_tasks))."""
+    if tasks is None:
+        tasks = (True, True, True)
+    xs = apply_mask(xs, tasks)
     logits, losses = weargait_losses(p, xs, ys, synchronized=synchronized, wm=wm, counts=counts, **loss_kw)
-    grads, extra = step_gradients(p, losses, weargait_shared_keys(p, synchronized),
-                                  weargait_private_keys(p, synchronized), alpha, max_norm,
-                                  private_twice=True)
+    live = [i for i, t in enumerate(tasks) if t]
+    priv = weargait_private_keys(p, synchronized)
+    dead_keys = set(k for i in range(3) if i not in live for k in priv[i])
+    sub = {k: v for k, v in p.items() if k not in dead_keys}          # leaves no live loss reaches keep grad None
+    grads, extra = step_gradients(sub, [losses[i] for i in live], weargait_shared_keys(p, synchronized),
+                                  [priv[i] for i in live], alpha, max_norm, private_twice=True)
     sgd_update(p, grads, bufs, lr, momentum, wd)
-    extra.update(logits=[l.detach() for l in logits], losses=[float(l.detach()) for l in losses], grads=grads)
+    extra.update(logits=[l.detach() for l in logits], losses=[float(l.detach()) for l in losses], grads=grads, live=live)
     return extra
 
 

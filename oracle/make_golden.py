@@ -72,7 +72,7 @@ def _save(name, **arrs):
 
 # ------------------------------------------------------------------ WearGait
 def weargait_case(name, *, synchronized, wm, use_norm=False, use_cosine=False, B=8, steps=3,
-                  alpha=0.5, seed=43, model_kw=None, drw=False, T=64):
+                  alpha=0.5, seed=43, model_kw=None, drw=False, T=64, masks=None):
     WT.set_seed(seed)
     model = WE.WearGaitThreeModal(synchronized=synchronized, use_norm=use_norm, use_cosine=use_cosine,
                                   **(model_kw or {}))
@@ -100,7 +100,7 @@ def weargait_case(name, *, synchronized, wm, use_norm=False, use_cosine=False, B
     if drw:
         for c, k in zip(crit, ("walkway", "insole", "imu")):
             c.weight = WT.inv_freq_weights(cnt[k])
-    cag = CAGrad(n_tasks=3, device=torch.device("cpu"), c=alpha)
+    cags = {k: CAGrad(n_tasks=k, device=torch.device("cpu"), c=alpha) for k in (1, 2, 3)}   # one per live-task count
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
     rec = {}
     for st in range(steps):
@@ -109,12 +109,17 @@ def weargait_case(name, *, synchronized, wm, use_norm=False, use_cosine=False, B
         xt = [torch.from_numpy(x) for x in xs]
         yt = [torch.from_numpy(y) for y in ys]
         model.train()
+        mask = (True, True, True) if masks is None else masks[st]
+        xt = [WT._maybe_zero(x, u) for x, u in zip(xt, mask)]           # weargait_train.py:355-358
         lw, li, lm = model(*xt)
-        L = [crit[0](lw, yt[0]), crit[1](li, yt[1]), crit[2](lm, yt[2])]
+        Lall = [crit[0](lw, yt[0]), crit[1](li, yt[1]), crit[2](lm, yt[2])]
+        L = [l if u else None for l, u in zip(Lall, mask)]
+        live = [l for l in L if l is not None]
+        cag = cags[len(live)]
         # what CAGrad sees: per-task shared-gradient matrix (recomputed, non-destructively)
         shared = list(model.get_shared_parameters())
         G = torch.stack([torch.cat([g_.reshape(-1) for g_ in torch.autograd.grad(l, shared, retain_graph=True)])
-                         for l in L], 1)
+                         for l in live], 1)
         # step_cagrad_three discards CAGrad's return value; capture it with the same call
         # signature it uses (weargait_train.py:214), forwarding unchanged.
         got = {}
@@ -128,7 +133,7 @@ def weargait_case(name, *, synchronized, wm, use_norm=False, use_cosine=False, B
         WT.step_cagrad_three(model, L[0], L[1], L[2], opt, cag)
         cag.backward = orig_backward
         rec[f"s{st}"] = dict(logits=np.stack([_np(lw), _np(li), _np(lm)]),
-                             losses=np.array([float(l) for l in L]), G=_np(G),
+                             losses=np.array([float(l.detach()) for l in Lall]), G=_np(G),
                              GTG=np.asarray(got["extra"]["GTG"]), w=np.asarray(got["extra"]["weights"]))
         for k, v in _grads(model).items():
             if v is not None:
@@ -145,7 +150,7 @@ def weargait_case(name, *, synchronized, wm, use_norm=False, use_cosine=False, B
         for j in range(3):
             flat[f"y{i}_{j}"] = labels[i][j]
     meta = dict(synchronized=synchronized, wm=wm, use_norm=use_norm, use_cosine=use_cosine, B=B, steps=steps,
-                alpha=alpha, counts=counts, drw=drw, T=T, model_kw=model_kw or {})
+                alpha=alpha, counts=counts, drw=drw, T=T, model_kw=model_kw or {}, masks=masks)
     _save(name, meta=json.dumps(meta), state0=state0, **flat)
 
 
@@ -374,6 +379,10 @@ def main():
         "wg_scaled": lambda: weargait_case("wg_scaled", synchronized=True, wm="gcl", B=3, steps=2, T=256,
                                            model_kw=dict(enc_out_ch=24, shared_out_ch=32)),
         "wg_masks": lambda: weargait_mask_case("wg_masks"),
+        "wg_sync_gcl_dropped": lambda: weargait_case("wg_sync_gcl_dropped", synchronized=True, wm="gcl", steps=4,
+                                                     masks=[(True, False, True), (False, True, False), (True, True, True), (False, True, True)]),
+        "wg_async_gcl_dropped": lambda: weargait_case("wg_async_gcl_dropped", synchronized=False, wm="gcl", steps=3,
+                                                      masks=[(False, True, True), (True, False, False), (True, True, False)]),
         "fog_async_gcl": lambda: fog_case("fog_async_gcl", dataset="fog", synchronized=False, wm="gcl"),
         "fog_sync_gcl": lambda: fog_case("fog_sync_gcl", dataset="fog", synchronized=True, wm="gcl"),
         "fog_async_ldam": lambda: fog_case("fog_async_ldam", dataset="fog", synchronized=False, wm="ldam", steps=2),

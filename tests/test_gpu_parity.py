@@ -527,3 +527,55 @@ def test_end_to_end_training_tf32_close_to_fp32(gk):
         p = sum(torch.softmax(l, 1) for l in lg) / 3
         accs[dt] = 100.0 * float((p.argmax(1) == dev(y)).sum()) / len(y)
     assert abs(accs[gk.DTYPE_F32] - accs[gk.DTYPE_TF32]) <= 0.5, accs
+
+
+@pytest.mark.parametrize("sync", [True, False])
+def test_relaxed_input_training_with_dropped_streams(gk, sync):
+    """SURVEY 8(d) cfg 3(ii): a per-batch modality mask during training -- masked streams zero-filled
+    (_maybe_zero, weargait_train.py:355-358) and their losses dropped from the CAGrad task list
+    (step_cagrad_three :200-203), n_tasks in {1,2,3}.  Fused path vs oracle over a sequence of masks."""
+    import gait_oracle as O
+    torch.manual_seed(21)
+    m = gk.WearGaitThreeModal(synchronized=sync).cuda()
+    state = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    p = O.canonical_params(state, sync); bufs = {}
+    counts = [[30, 70], [45, 55], [20, 80]]
+    crit = [gk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in counts]
+    st = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, process_group=False)
+    masks = [(True, True, True), (True, False, True), (False, True, False), (False, True, True), (True, True, False), (True, False, False)]
+    for it, mask in enumerate(masks):
+        xs, y = O.synth_weargait_batch(48, seed=300 + it)
+        r = np.random.default_rng(it)
+        ys = [y, y, y] if sync else [y, r.permutation(y), r.permutation(y)]
+        loss, correct = st.step([dev(x) for x in xs], [dev(v) for v in ys], enabled=mask, tasks=mask)
+        ex = O.weargait_train_step(p, bufs, [torch.from_numpy(x) for x in xs], [torch.from_numpy(v) for v in ys],
+                                   synchronized=sync, wm="gcl", counts=counts, alpha=0.5, tasks=mask)
+        got = loss.cpu().numpy()
+        for i in range(3):
+            if mask[i]:
+                assert abs(got[i] - ex["losses"][i]) <= 5e-5 * max(1.0, abs(ex["losses"][i])), (it, i, got, ex["losses"])
+        for k, v in m.state_dict().items():
+            if k in p:
+                close(v.cpu().numpy(), p[k].detach().numpy(), 2e-5, f"step {it} mask {mask} {k}")
+
+
+@pytest.mark.parametrize("name", ["wg_sync_gcl_dropped", "wg_async_gcl_dropped"])
+def test_dropped_stream_training_matches_reference_goldens(gk, name):
+    """The same relaxed-input case against what the REFERENCE produced (step_cagrad_three with None losses,
+    CAGrad(n_tasks=k)): parameters after every step, live losses, simplex weights."""
+    g = load_golden(name); meta = g["meta"]
+    m = wg_model(gk, g)
+    step = gk.FusedTrainStep(m, wg_criteria(gk, meta), cagrad_c=meta["alpha"], private_mult=2.0, process_group=False)
+    for st in range(meta["steps"]):
+        i = st % 2; mask = tuple(bool(u) for u in meta["masks"][st])
+        xs = [dev(g[f"x{i}_{j}"]) for j in range(3)]; ys = [dev(g[f"y{i}_{j}"]) for j in range(3)]
+        loss, _ = step.step(xs, ys, enabled=mask, tasks=mask)
+        ref = sub(g, f"s{st}")
+        live = [j for j in range(3) if mask[j]]
+        close(loss.cpu().numpy()[live], ref["losses"][live], 2e-5, "live losses")
+        d = step.diag().cpu().numpy()
+        assert np.abs(d[:3][live] - ref["w"]).max() < 2e-4, (d[:3], ref["w"])
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} mask {mask} param {k[6:]}")

@@ -8,7 +8,7 @@ import gait_oracle as O
 from conftest import load_golden, sub
 
 WG_CASES = ["wg_sync_gcl", "wg_sync_gcl_drw", "wg_async_ce", "wg_async_gcl", "wg_sync_classwt_nc",
-            "wg_sync_norm", "wg_scaled"]
+            "wg_sync_norm", "wg_scaled", "wg_sync_gcl_dropped", "wg_async_gcl_dropped"]
 FOG_CASES = ["fog_async_gcl", "fog_sync_gcl", "fog_async_ldam", "fog_sync_ce_nc", "fbg_async_classwt"]
 
 
@@ -37,8 +37,9 @@ def test_weargait_step_matches_reference(name):
         i = st % 2
         xs = [torch.from_numpy(g[f"x{i}_{j}"]) for j in range(3)]
         ys = [torch.from_numpy(g[f"y{i}_{j}"]) for j in range(3)]
+        mask = tuple(meta["masks"][st]) if meta.get("masks") else None
         ex = O.weargait_train_step(p, bufs, xs, ys, synchronized=sync, wm=meta["wm"], counts=meta["counts"],
-                                   alpha=meta["alpha"], weights=weights)
+                                   alpha=meta["alpha"], weights=weights, tasks=mask)
         ref = sub(g, f"s{st}")
         _close(torch.stack(ex["logits"]).numpy(), ref["logits"])
         _close(ex["losses"], ref["losses"])
@@ -51,8 +52,12 @@ def test_weargait_step_matches_reference(name):
                 if sync and (name_.startswith("head_i.") or name_.startswith("head_m.") or name_.startswith("_shared")):
                     continue
                 _close(ex["grads"][name_].numpy(), v, rtol=2e-4, atol=2e-6)
-        # parameters no loss reaches stay gradient-free (enc_i.ln1)
-        assert ex["grads"]["enc_i.ln1.weight"] is None and "grad:enc_i.ln1.weight" not in ref
+        # parameters no loss reaches stay gradient-free (enc_i.ln1; encoders of dropped streams)
+        assert ex["grads"].get("enc_i.ln1.weight") is None and "grad:enc_i.ln1.weight" not in ref
+        if mask is not None:
+            for i, pre in enumerate(("enc_w.", "enc_i.", "enc_m.")):
+                if not mask[i]:
+                    assert not any(k.startswith("grad:" + pre) for k in ref)
         for k, v in ref.items():
             if k.startswith("param:"):
                 name_ = k[6:]
