@@ -135,7 +135,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch), "cpu_sample_batch": B, "timing": "time.perf_counter around each step"},
+        "config": {"workload": workload_name(args.batch, getattr(args, "workload", "weargait")), "cpu_sample_batch": B, "timing": "time.perf_counter around each step"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{len(times)} steps of B={B} windows (bounded sample of the per-GPU batch), torch {torch.__version__} CPU"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -144,9 +144,54 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(B):
-    return (f"WearGait 3-stream multimodal train step (configs[1]): B={B} windows/GPU of (64,2)+(64,13)+(64,24) fp32, "
-            "sync labels, GCL m=0.2 s=25, CAGrad c=0.5, SGD mom 0.9 wd 1e-4")
+def workload_name(B, kind="weargait"):
+    if kind == "fog":
+        return (f"FoG 2-stream train step (configs[3]): B={B} sequences/GPU of skeleton (101,21) + sensor (426,6) fp32, async heads, "
+                "GCL m=0.2 s=25, CAGrad c=0.1, SGD mom 0.9 wd 1e-4")
+    tag = {"weargait": "configs[1]: sync labels, shared head",
+           "weargait_async": "configs[2] async: independent per-stream labels, three private heads",
+           "weargait_relaxed": "configs[2] relaxed input: per-step modality mask cycling the 7 MASK_COMBOS, masked streams zero-filled "
+                               "and dropped from the CAGrad task list"}[kind]
+    return (f"WearGait 3-stream multimodal train step ({tag}): B={B} windows/GPU of (64,2)+(64,13)+(64,24) fp32, "
+            "GCL m=0.2 s=25, CAGrad c=0.5, SGD mom 0.9 wd 1e-4")
+
+
+MASK_CYCLE = [(True, False, False), (False, True, False), (False, False, True), (True, True, False), (True, False, True),
+              (False, True, True), (True, True, True)]
+
+
+def build_workload(args, gaitk, dev, rank):
+    """-> dict(model, crit, step_kw(i), host batches, stream names, dims, units)"""
+    import gait_oracle as O
+    kind = args.workload; B = args.batch
+    if kind == "fog":
+        model = gaitk.MultiModalMultiTaskModel(21, 6, 6, 6, 426, 16, 8, 128, 3, synchronized_loading=False).to(dev)
+        counts = [[500, 300, 200], [450, 330, 220]]
+        crit = [gaitk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in counts]
+        host = []
+        for i in range(2):
+            sk, se, y = O.synth_fog_batch(B, seed=1000 * rank + i)
+            y2 = np.random.default_rng(7 + i).permutation(y)
+            host.append(([torch.from_numpy(sk).pin_memory(), torch.from_numpy(se).pin_memory()],
+                         [torch.from_numpy(y).pin_memory(), torch.from_numpy(y2).pin_memory()]))
+        return dict(model=model, crit=crit, host=host, names=("skeleton", "sensor"), dims=((101, 21), (426, 6)),
+                    cagrad_c=0.1, private_mult=1.0, dtype="f32", kw=lambda i: {})
+    sync = kind != "weargait_async"
+    model = gaitk.WearGaitThreeModal(synchronized=sync).to(dev)
+    crit = [gaitk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in COUNTS]
+    host = []
+    for i in range(2):
+        xs, y = synth(B, 1000 * rank + i)
+        yt = torch.from_numpy(y).pin_memory()
+        if sync:
+            ys = [yt, yt, yt]
+        else:
+            r = np.random.default_rng(50 + i)
+            ys = [yt, torch.from_numpy(r.permutation(y)).pin_memory(), torch.from_numpy(r.permutation(y)).pin_memory()]
+        host.append(([torch.from_numpy(x).pin_memory() for x in xs], ys))
+    kw = (lambda i: dict(enabled=MASK_CYCLE[i % 7], tasks=MASK_CYCLE[i % 7])) if kind == "weargait_relaxed" else (lambda i: {})
+    return dict(model=model, crit=crit, host=host, names=("walkway", "insole", "imu"), dims=((T, 2), (T, 13), (T, 24)),
+                cagrad_c=0.5, private_mult=2.0, dtype=args.dtype, kw=kw)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -164,33 +209,29 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(0)                               # identical replicas on every rank
-    model = gaitk.WearGaitThreeModal().to(dev)
-    crit = [gaitk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in COUNTS]
+    wl = build_workload(args, gaitk, dev, rank)
+    model, crit, host, names, dims = wl["model"], wl["crit"], wl["host"], wl["names"], wl["dims"]
     for c in crit:
         c.consume_rng = False
-    step = gaitk.FusedTrainStep(model, crit, cagrad_c=0.5, max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
-                                private_mult=2.0, process_group=None if world > 1 else False,
-                                dtype=gaitk.DTYPE_TF32 if args.dtype == "tf32" else gaitk.DTYPE_F32)
-    # synthetic batches: NBUF distinct batches per rank (each 10 KB/window -> B=32768 is 327 MB >> 126 MB L2)
-    NBUF = 2
-    host = []
-    for i in range(NBUF):
-        xs, y = synth(B, 1000 * rank + i)
-        host.append(([torch.from_numpy(x).pin_memory() for x in xs], torch.from_numpy(y).pin_memory()))
-    devb = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in host]
+    ns = len(names)
+    bytes_per_unit = sum(t * d for t, d in dims) * 4 + 8
+    dtype_id = gaitk.DTYPE_TF32 if wl["dtype"] == "tf32" else gaitk.DTYPE_F32
+    step = gaitk.FusedTrainStep(model, crit, cagrad_c=wl["cagrad_c"], max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
+                                private_mult=wl["private_mult"], process_group=None if world > 1 else False, dtype=dtype_id)
+    NBUF = len(host)
+    devb = [([x.to(dev) for x in xs], [y.to(dev) for y in ys]) for xs, ys in host]
     # global label vectors (all ranks' labels; cheap) fix the weighted-mean denominators
     def global_labels(i):
         if world == 1:
             return None
-        ys = [torch.from_numpy(synth_labels_only(B, 1000 * r + i)).to(dev) for r in range(world)]
-        g = torch.cat(ys); return [g, g, g]
-
-    def synth_labels_only(Bn, seed):
+        if args.workload != "weargait":
+            raise SystemExit("multi-GPU bench is wired for the default workload")
         import gait_oracle as O
-        return O.synth_weargait_labels(Bn, seed=seed)
+        g = torch.cat([torch.from_numpy(O.synth_weargait_labels(B, seed=1000 * r + i)).to(dev) for r in range(world)])
+        return [g, g, g]
     yglob = [global_labels(i) for i in range(NBUF)]
     l2_flush = None
-    if B * BYTES_PER_WINDOW < 2 * 126e6:               # small batches: flush L2 between steps instead
+    if B * bytes_per_unit < 2 * 126e6:                 # small batches: flush L2 between steps instead
         l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -199,10 +240,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def one_step(i):
-        xs, y = devb[i % NBUF]
+        xs, ys = devb[i % NBUF]
         if l2_flush is not None:
             l2_flush.fill_(i & 0xff)
-        step.step(xs, [y, y, y], ys_global=yglob[i % NBUF])
+        step.step(xs, ys, ys_global=yglob[i % NBUF], **wl["kw"](i))
 
     # ---- device-resident timing
     for i in range(args.warmup):
@@ -229,11 +270,11 @@ def run_gpu(args):
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H of (loss, correct), every step.  The H2D copy of
     # batch i+1 is issued on a copy stream before step i is launched (two device slots), so it overlaps compute.
     def e2e_loop(n):
-        xs, y = host[0]; step.stage_host(xs, [y, y, y], slot=0)
+        xs, ys = host[0]; step.stage_host(xs, ys, slot=0)
         for i in range(n):
             if i + 1 < n:
-                xs, y = host[(i + 1) % NBUF]; step.stage_host(xs, [y, y, y], slot=(i + 1) % 2)
-            out = step.step_staged(slot=i % 2, ys_global=yglob[i % NBUF])
+                xs, ys = host[(i + 1) % NBUF]; step.stage_host(xs, ys, slot=(i + 1) % 2)
+            out = step.step_staged(slot=i % 2, ys_global=yglob[i % NBUF], **wl["kw"](i))
         return out
     e2e_loop(min(args.warmup, 3))
     barrier()
@@ -246,27 +287,23 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t2.item()) * 1e-3)
-    h2d = B * T * sum(DIMS) * 4 + B * 8
-    d2h = 6 * 4
+    h2d = B * (bytes_per_unit - 8) + sum(int(y.numel()) * 8 for y in dict.fromkeys(host[0][1]))
+    d2h = 2 * ns * 4
 
     # ---- end-to-end with the dataset resident in HBM (the B200-first data path): the frame stores are uploaded once
     # per fold; every step the host sends only the window-start indices and labels (pinned), the kernels gather.
-    stores = [torch.cat([devb[i][0][s].reshape(-1, DIMS[s]) for i in range(NBUF)]) for s in range(3)]
-    ycat = torch.cat([host[i][1] for i in range(NBUF)])
-    gen = torch.Generator().manual_seed(1234 + rank)
-    idx_host, y_host = [], []
-    for i in range(4):
-        perm = torch.randperm(NBUF * B, generator=gen)[:B]
-        idx_host.append((perm * T).to(torch.int64).pin_memory()); y_host.append(ycat[perm].contiguous().pin_memory())
-    def yg_for(i):
-        if world == 1:
-            return None
-        return None                                    # labels of other ranks are not replicated in this synthetic setup
-    model.set_window(T)
-    for i in range(3):
-        step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3) if world == 1 else None
     res_value = None
-    if world == 1:
+    if world == 1 and args.workload == "weargait":
+        stores = [torch.cat([devb[i][0][s].reshape(-1, DIMS[s]) for i in range(NBUF)]) for s in range(3)]
+        ycat = torch.cat([host[i][1][0] for i in range(NBUF)])
+        gen = torch.Generator().manual_seed(1234 + rank)
+        idx_host, y_host = [], []
+        for i in range(4):
+            perm = torch.randperm(NBUF * B, generator=gen)[:B]
+            idx_host.append((perm * T).to(torch.int64).pin_memory()); y_host.append(ycat[perm].contiguous().pin_memory())
+        model.set_window(T)
+        for i in range(3):
+            step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3)
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
@@ -279,34 +316,34 @@ def run_gpu(args):
     roof = None; per_stream = {}
     if rank == 0:
         peak, peak_src = peaks()
-        names = ("walkway", "insole", "imu")
         scratch = torch.empty(model.plan().NP, dtype=torch.float32, device=dev)
         step.pg = False                                   # rank-local timing: no collective in this section
-        for s in range(3):
-            tasks = [k == s for k in range(3)]
-            xs, y = devb[0]
+        for s_ in range(ns):
+            tasks = [k == s_ for k in range(ns)]
+            xs, ys = devb[0]
             for _ in range(2):
-                step.step(xs, [y, y, y], tasks=tasks, update=False, grads_out=scratch)
+                step.step(xs, ys, tasks=tasks, update=False, grads_out=scratch)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
             a.record()
             for r in range(reps):
-                xs, y = devb[r % NBUF]
-                step.step(xs, [y, y, y], tasks=tasks, update=False, grads_out=scratch)
+                xs, ys = devb[r % NBUF]
+                step.step(xs, ys, tasks=tasks, update=False, grads_out=scratch)
             b.record(); torch.cuda.synchronize()
-            per_stream[names[s]] = a.elapsed_time(b) / reps
+            per_stream[names[s_]] = a.elapsed_time(b) / reps
         dom = max(per_stream, key=per_stream.get)
-        s = names.index(dom)
-        alg = B * (T * DIMS[s] * 4 + 8)
+        s_ = names.index(dom)
+        alg = B * (dims[s_][0] * dims[s_][1] * 4 + 8)
         ach = alg / (per_stream[dom] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": f"stream_kernel<{dom}> (fused fwd+loss+bwd)", "achieved": ach, "peak": peak,
+        kname = "stream_kernel_tc" if wl["dtype"] == "tf32" else "stream_kernel"
+        roof = {"bound": "hbm", "kernel": f"{kname}<{dom}> (fused fwd+loss+bwd)", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "ms_per_launch": per_stream[dom], "algorithmic_bytes_per_launch": alg,
                 "note": "issue/latency-bound, not HBM-bound (DESIGN.md 3.1); the timed launch also contains the small reduce "
-                        "kernel and the single-CTA update kernel",
+                        "kernel and the single-CTA update kernel; ncu: DRAM read == algorithmic bytes (profiles/)",
                 "per_stream_ms": per_stream,
-                "step_hbm_gbs": B * BYTES_PER_WINDOW / (ms_max / args.steps * 1e-3) / 1e9}
+                "step_hbm_gbs": B * bytes_per_unit / (ms_max / args.steps * 1e-3) / 1e9}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -319,8 +356,8 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(B), "parallelism": f"dp{world}", "global_batch": world * B,
+            "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": workload_name(B, args.workload), "parallelism": f"dp{world}", "global_batch": world * B,
                        "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
                        "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -348,6 +385,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog"],
+                    help="default = BASELINE.json configs[1]; the others are extra report lines")
     ap.add_argument("--dtype", default="tf32", choices=["f32", "tf32"], help="contraction arithmetic of the stream kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaitk" else args.warmup
