@@ -296,6 +296,27 @@ def fog_forward(p: Params, x_skel, x_sens, sensor_length: int, bdim: int = 8,
     return task_head(p, rs, "task_head_skel."), task_head(p, rt, "task_head_sensor.")
 
 
+def fog_single_forward(p: Params, x, kind: str, sensor_length: int = 426, bdim: int = 8, out_len: int = 101):
+    """SkelModalityModel / SensorModalityModel.forward feature_encoder.py:301-305,340-344
+    (state_dict names encoder.*, backbone.*, task_head.*)."""
+    if kind == "skeleton":
+        h = x @ p["encoder.fc1.weight"].t() + p["encoder.fc1.bias"]
+        f = torch.relu(layer_norm(h, p["encoder.ln1.weight"], p["encoder.ln1.bias"]))
+    else:
+        f = conv_time(x, p["encoder.conv1d.weight"], p["encoder.conv1d.bias"])
+        if f.shape[1] == sensor_length:
+            f = adaptive_avg_pool_time(f, out_len)
+    r = backbone(p, f, bdim, "backbone.conv1d.weight", "backbone.conv1d.bias")
+    return task_head(p, r, "task_head.")
+
+
+def weargait_single_forward(p: Params, x, mod: str, bdim: int = 8):
+    """_single_logits_and_labels weargait_train.py:252-271: one branch of the 3-stream model."""
+    enc = {"walkway": enc_walkway, "insole": enc_insole, "imu": enc_imu}[mod]
+    head = {"walkway": "head_w.", "insole": "head_i.", "imu": "head_m."}[mod]
+    return task_head(p, backbone(p, enc(p, x), bdim), head)
+
+
 # --------------------------------------------------------------------------
 # A10  losses                          classification_losses.py:54-109 etc.
 # --------------------------------------------------------------------------

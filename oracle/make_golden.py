@@ -233,6 +233,48 @@ def fog_case(name, *, dataset, synchronized, wm, use_nc=False, B=8, steps=3, alp
     _save(name, meta=json.dumps(meta), state0=state0, **flat)
 
 
+# ------------------------------------------------------------------ single-modality paths
+def single_modality_case(name, seed=5, B=6):
+    FT.set_random_seed(seed)
+    flat = {}
+    prm = FT.FBG_FOG_PARAMS["fog"]
+    sk, se, y = synth_fog_batch(B, seed=77)
+    yt = torch.from_numpy(y)
+    args = SimpleNamespace(modality="skeleton", use_norm_and_cos=False, synchronized_loading=False)
+    for mod, x in (("skeleton", sk), ("sensor", se)):
+        args.modality = mod
+        model = FT.choose_model(args, prm, torch.device("cpu"))        # SkelModalityModel / SensorModalityModel (use_norm=True)
+        for k, v in _state(model).items():
+            flat[f"{mod}/state0/{k}"] = v
+        logits = model(torch.from_numpy(x))
+        loss = torch.nn.CrossEntropyLoss()(logits, yt)
+        model.zero_grad(); loss.backward()
+        flat[f"{mod}/logits"] = _np(logits); flat[f"{mod}/loss"] = np.array(float(loss.detach()))
+        for k, v in _grads(model).items():
+            flat[f"{mod}/grad/{k}"] = v
+    flat["sk"] = sk; flat["se"] = se; flat["y"] = y
+    # WearGait --single_mod branch: enc_? -> shared backbone -> head_? (weargait_train.py:252-271)
+    WT.set_seed(seed)
+    model = WE.WearGaitThreeModal(synchronized=True)
+    xs, yw = synth_weargait_batch(B, seed=78)
+    batch = {"xs": [torch.from_numpy(x) for x in xs], "y": torch.from_numpy(yw)}
+    for k, v in _state(model).items():
+        flat[f"wg/state0/{k}"] = v
+    for mod in ("walkway", "insole", "imu"):
+        logits, yy = WT._single_logits_and_labels(model, batch, False, mod)
+        loss = torch.nn.CrossEntropyLoss()(logits, yy)
+        model.zero_grad(); loss.backward()
+        flat[f"wg/{mod}/logits"] = _np(logits); flat[f"wg/{mod}/loss"] = np.array(float(loss.detach()))
+        for k, v in _grads(model).items():
+            if v is not None:
+                flat[f"wg/{mod}/grad/{k}"] = v
+    for j in range(3):
+        flat[f"wg/x{j}"] = xs[j]
+    flat["wg/y"] = yw
+    np.savez_compressed(OUT / f"{name}.npz", **flat)
+    print(f"  wrote {name}.npz ({(OUT / (name + '.npz')).stat().st_size / 1024:.0f} KiB, {len(flat)} arrays)")
+
+
 # ------------------------------------------------------------------ CAGrad solver corpus
 def cagrad_corpus(name):
     rng = np.random.default_rng(11)
@@ -388,6 +430,7 @@ def main():
         "fog_async_ldam": lambda: fog_case("fog_async_ldam", dataset="fog", synchronized=False, wm="ldam", steps=2),
         "fog_sync_ce_nc": lambda: fog_case("fog_sync_ce_nc", dataset="fog", synchronized=True, wm="ce", use_nc=True, steps=2),
         "fbg_async_classwt": lambda: fog_case("fbg_async_classwt", dataset="fbg", synchronized=False, wm="class_wt", steps=2),
+        "single_modality": lambda: single_modality_case("single_modality"),
         "cagrad_corpus": lambda: cagrad_corpus("cagrad_corpus"),
         "data_path": lambda: data_case("data_path"),
     }

@@ -579,3 +579,43 @@ def test_dropped_stream_training_matches_reference_goldens(gk, name):
         for k, v in ref.items():
             if k.startswith("param:"):
                 close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} mask {mask} param {k[6:]}")
+
+
+def test_single_modality_paths_match_reference(gk):
+    """SkelModalityModel / SensorModalityModel (feature_encoder.py:268-344) and the --single_mod branch of the
+    WearGait model driven exactly as weargait_train._single_logits_and_labels does (sub-module calls)."""
+    g = load_golden("single_modality")
+    prm = dict(skeleton_input_dim=21, skeleton_output_dim=6, sensor_in_channels=6, sensor_out_channels=6, sensor_length=426,
+               shared_out_channels=16, backbone_dim=8, taskhead_input_dim=128, num_classes=3)
+    y = dev(g["y"])
+    for mod, xk in (("skeleton", "sk"), ("sensor", "se")):
+        if mod == "skeleton":
+            m = gk.SkelModalityModel(21, 6, 6, 16, 8, 128, 3)
+        else:
+            m = gk.SensorModalityModel(6, 6, 426, 16, 8, 128, 3)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(sub(g, mod), "state0").items()}, strict=True)
+        m = m.cuda()
+        lg = m(dev(g[xk]))
+        close(lg.detach().cpu().numpy(), g[f"{mod}/logits"], 2e-5, f"{mod} logits")
+        loss = gk.CrossEntropyLoss()(lg, y); loss.backward()
+        close(float(loss), g[f"{mod}/loss"], 2e-5, "loss")
+        named = dict(m.named_parameters())
+        for k, v in sub(sub(g, mod), "grad").items():
+            close(named[k].grad.cpu().numpy(), v, 5e-5, f"{mod} grad {k}")
+    yw = dev(g["wg/y"])
+    for j, mod in enumerate(("walkway", "insole", "imu")):
+        m = gk.WearGaitThreeModal(synchronized=True)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(sub(g, "wg"), "state0").items()}, strict=True)
+        m = m.cuda()
+        x = dev(g[f"wg/x{j}"])
+        enc = {"walkway": m.enc_w, "insole": m.enc_i, "imu": m.enc_m}[mod]
+        head = {"walkway": m.head_w, "insole": m.head_i, "imu": m.head_m}[mod]
+        lg = head(m.backbone(enc(x)).flatten(1))                       # weargait_train.py:262-270
+        close(lg.detach().cpu().numpy(), g[f"wg/{mod}/logits"], 2e-5, f"wg {mod} logits")
+        loss = gk.CrossEntropyLoss()(lg, yw); loss.backward()
+        named = dict(m.named_parameters())
+        for k, v in sub(sub(sub(g, "wg"), mod), "grad").items():
+            if k in named:
+                close(named[k].grad.cpu().numpy(), v, 5e-5, f"wg {mod} grad {k}")
+        others = [p for n_, p in named.items() if n_.startswith("enc_") and not n_.startswith({"walkway": "enc_w", "insole": "enc_i", "imu": "enc_m"}[mod])]
+        assert all(p.grad is None for p in others)

@@ -158,3 +158,25 @@ def test_data_path_matches_reference():
             Wt[i, a:b] = np.float32(1.0) / np.float32(b - a)
         np.testing.assert_allclose(Wt, g[f"pool_{L}_{Oo}"], rtol=1e-6, atol=0)
         assert ((Wt > 0) == (g[f"pool_{L}_{Oo}"] > 0)).all()
+
+
+def test_single_modality_paths_match_reference():
+    g = load_golden("single_modality")
+    y = torch.from_numpy(g["y"])
+    for mod, xk in (("skeleton", "sk"), ("sensor", "se")):
+        p = {k: torch.tensor(v).requires_grad_(True) for k, v in sub(sub(g, mod), "state0").items()}
+        lg = O.fog_single_forward(p, torch.from_numpy(g[xk]), mod)
+        _close(lg.detach().numpy(), g[f"{mod}/logits"])
+        loss = O.weighted_ce(lg, y); loss.backward()
+        _close(float(loss), g[f"{mod}/loss"])
+        for k, v in sub(sub(g, mod), "grad").items():
+            _close(p[k].grad.numpy(), v, rtol=2e-4, atol=2e-6)
+    yw = torch.from_numpy(g["wg/y"])
+    for j, mod in enumerate(("walkway", "insole", "imu")):
+        p = O.canonical_params(sub(sub(g, "wg"), "state0"), True)
+        lg = O.weargait_single_forward(O._HeadAlias(p), torch.from_numpy(g[f"wg/x{j}"]), mod)
+        _close(lg.detach().numpy(), g[f"wg/{mod}/logits"])
+        loss = O.weighted_ce(lg, yw); loss.backward()
+        for k, v in sub(sub(sub(g, "wg"), mod), "grad").items():
+            if k in p:
+                _close(p[k].grad.numpy(), v, rtol=2e-4, atol=2e-6)

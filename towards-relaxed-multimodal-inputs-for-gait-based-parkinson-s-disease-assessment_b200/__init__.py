@@ -4,11 +4,11 @@ from . import _lib
 from ._lib import GaitkError, lib, DTYPE_F32, DTYPE_TF32, SOLVER_SLSQP, SOLVER_EXACT
 from .plan import Plan, FlatParamModule
 from .weargait_encoders import WearGaitThreeModal
-from .feature_encoder import MultiModalMultiTaskModel
+from .feature_encoder import MultiModalMultiTaskModel, SensorModalityModel, SkelModalityModel
 from .classification_losses import GCLLoss, LDAMLoss, CrossEntropyLoss, make_loss_desc, criterion_spec
 from .multitask_weighting import CAGrad
 from .fused_step import FusedTrainStep
 from . import dist
 
-__all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "MultiModalMultiTaskModel",
+__all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "MultiModalMultiTaskModel", "SensorModalityModel", "SkelModalityModel",
            "GCLLoss", "LDAMLoss", "CrossEntropyLoss", "make_loss_desc", "criterion_spec", "CAGrad", "FusedTrainStep"]

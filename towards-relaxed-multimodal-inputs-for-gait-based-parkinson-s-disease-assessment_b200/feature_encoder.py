@@ -133,3 +133,79 @@ class MultiModalMultiTaskModel(FlatParamModule):
         if self.synchronized_loading:
             shared += list(self.task_head_shared.parameters())
         return shared
+
+
+class _SingleStreamModel(FlatParamModule):
+    """One stream of the 2-stream FoG/FBG plan (the other stream's parameters are zero dummies, never launched)."""
+    _stream = 0
+
+    def _plan_kwargs(self):
+        c = self._cfg
+        return dict(family=_lib.FAMILY_FOG, T=c["T"], enc_out_ch=c["enc_out_ch"], shared_out_ch=c["shared_out_ch"],
+                    backbone_dim=c["backbone_dim"], num_classes=c["num_classes"], use_norm=c["use_norm"], use_cosine=False,
+                    synchronized=False, skel_in_dim=c["skel_in_dim"], sensor_in_ch=c["sensor_in_ch"],
+                    sensor_len=c["sensor_len"], sensor_out_len=c["T"])
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        object.__setattr__(self, "_flat", None)
+        return out
+
+    def forward(self, x):
+        xs = [None, None]; xs[self._stream] = x
+        return run_streams(self, xs, 0b11)[self._stream]
+
+
+class SensorModalityModel(_SingleStreamModel):
+    """feature_encoder.py:268-305: SensorEncoder -> SharedBackbone -> TaskHead (use_norm=True by default)."""
+    _stream = 1
+
+    def __init__(self, sensor_in_channels: int, sensor_out_channels: int, sensor_length: int, shared_out_channels: int,
+                 backbone_dim: int, taskhead_input_dim: int, num_classes: int, use_norm: bool = True):
+        super().__init__()
+        self.encoder = SensorEncoder(in_channels=sensor_in_channels, out_channels=sensor_out_channels, sensor_length=sensor_length)
+        self.backbone = SharedBackbone(in_channels=sensor_out_channels, shared_out_channels=shared_out_channels, backbone_dim=backbone_dim)
+        self.task_head = TaskHead(input_dim=taskhead_input_dim, num_classes=num_classes, use_norm=use_norm, use_cosine=False)
+        self._cfg = dict(T=self.encoder.output_length, enc_out_ch=sensor_out_channels, shared_out_ch=shared_out_channels,
+                         backbone_dim=backbone_dim, num_classes=num_classes, use_norm=bool(use_norm),
+                         skel_in_dim=21 if sensor_in_channels == 6 else 51, sensor_in_ch=sensor_in_channels, sensor_len=sensor_length)
+
+    def _plan_name_map(self):
+        mp = {"sensor_encoder.conv1d.weight": "encoder.conv1d.weight", "sensor_encoder.conv1d.bias": "encoder.conv1d.bias",
+              "backbone.conv1d.weight": "backbone.conv1d.weight", "backbone.conv1d.bias": "backbone.conv1d.bias"}
+        for k in ("norm.weight", "norm.bias", "fc.weight", "fc.bias"):
+            mp["task_head_sensor." + k] = "task_head." + k
+        return mp
+
+    def forward(self, x):
+        if x.shape[1] != self._cfg["sensor_len"]:
+            raise _lib.GaitkError(f"sensor clips must have sensor_length={self._cfg['sensor_len']} frames")
+        return super().forward(x)
+
+
+class SkelModalityModel(_SingleStreamModel):
+    """feature_encoder.py:308-344: SkeletonMLP -> SharedBackbone -> TaskHead (use_norm=True by default)."""
+    _stream = 0
+
+    def __init__(self, skeleton_input_dim: int, skeleton_output_dim: int, sensor_out_channels: int, shared_out_channels: int,
+                 backbone_dim: int, taskhead_input_dim: int, num_classes: int, use_norm: bool = True):
+        super().__init__()
+        self.encoder = SkeletonMLP(input_dim=skeleton_input_dim, output_dim=skeleton_output_dim)
+        self.backbone = SharedBackbone(in_channels=sensor_out_channels, shared_out_channels=shared_out_channels, backbone_dim=backbone_dim)
+        self.task_head = TaskHead(input_dim=taskhead_input_dim, num_classes=num_classes, use_norm=use_norm, use_cosine=False)
+        fog = skeleton_input_dim == 21
+        self._cfg = dict(T=101, enc_out_ch=skeleton_output_dim, shared_out_ch=shared_out_channels, backbone_dim=backbone_dim,
+                         num_classes=num_classes, use_norm=bool(use_norm), skel_in_dim=skeleton_input_dim,
+                         sensor_in_ch=6 if fog else 3, sensor_len=426 if fog else 65)
+
+    def _plan_name_map(self):
+        mp = {"skeleton_encoder.fc1.weight": "encoder.fc1.weight", "skeleton_encoder.fc1.bias": "encoder.fc1.bias",
+              "skeleton_encoder.ln1.weight": "encoder.ln1.weight", "skeleton_encoder.ln1.bias": "encoder.ln1.bias",
+              "backbone.conv1d.weight": "backbone.conv1d.weight", "backbone.conv1d.bias": "backbone.conv1d.bias"}
+        for k in ("norm.weight", "norm.bias", "fc.weight", "fc.bias"):
+            mp["task_head_skel." + k] = "task_head." + k
+        return mp
+
+    def forward(self, x):
+        self._cfg["T"] = int(x.shape[1])
+        return super().forward(x)

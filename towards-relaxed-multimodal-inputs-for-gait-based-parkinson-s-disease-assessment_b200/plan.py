@@ -133,9 +133,21 @@ class FlatParamModule(torch.nn.Module):
     def _plan_kwargs(self) -> dict:  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _canonical_parameters(self) -> List[torch.nn.Parameter]:
+    def _plan_name_map(self) -> Optional[dict]:
+        """plan parameter name -> this module's parameter name; a plan parameter that is missing here (a stream the
+        module does not have) is backed by a zero dummy.  None = names are identical."""
+        return None
+
+    def _named_for_plan(self):
         named = dict(self.named_parameters())
-        return named
+        mp = self._plan_name_map()
+        if mp is None:
+            return named
+        out = {}
+        for pi in self.plan().params:
+            src = mp.get(pi.name)
+            out[pi.name] = named[src] if src is not None else None
+        return out
 
     def plan(self) -> Plan:
         dev = next(self.parameters()).device
@@ -150,13 +162,15 @@ class FlatParamModule(torch.nn.Module):
         """The flat buffer, (re)built whenever some parameter no longer aliases it (after .to(),
         load_state_dict(assign=True), manual .data swaps ...)."""
         plan = self.plan()
-        named = dict(self.named_parameters())
+        named = self._named_for_plan()
         flat = self._flat
         ok = flat is not None
         if ok:
             base = flat.data_ptr()
             for pi in plan.params:
                 p = named[pi.name]
+                if p is None:
+                    continue
                 if p.data_ptr() != base + 4 * pi.offset or p.dtype != torch.float32 or not p.is_contiguous():
                     ok = False; break
         if not ok:
@@ -164,6 +178,8 @@ class FlatParamModule(torch.nn.Module):
             with torch.no_grad():
                 for pi in plan.params:
                     p = named[pi.name]
+                    if p is None:
+                        continue
                     if tuple(p.shape) != pi.shape:
                         raise _lib.GaitkError(f"parameter {pi.name} has shape {tuple(p.shape)}, plan expects {pi.shape}")
                     v = flat[pi.offset:pi.offset + pi.numel].view(pi.shape)
@@ -172,8 +188,8 @@ class FlatParamModule(torch.nn.Module):
             object.__setattr__(self, "_flat", flat)
         return flat
 
-    def plan_parameters(self) -> List[torch.nn.Parameter]:
-        named = dict(self.named_parameters())
+    def plan_parameters(self) -> List[Optional[torch.nn.Parameter]]:
+        named = self._named_for_plan()
         return [named[pi.name] for pi in self.plan().params]
 
 
@@ -192,6 +208,7 @@ class _StreamsFn(torch.autograd.Function):
         ctx.dtype = dtype
         ctx.module = module; ctx.enabled_mask = enabled_mask; ctx.n_streams = n_streams
         ctx.xs = xs
+        ctx.present = [a is not None for a in args[n_streams:]]
         ctx.set_materialize_grads(False)
         outs = tuple(l if l is not None else torch.zeros(0, device=plan.device) for l in logits)
         ctx.mark_non_differentiable(*[o for o, l in zip(outs, logits) if l is None])
@@ -209,10 +226,10 @@ class _StreamsFn(torch.autograd.Function):
             if d is not None:
                 touched.add(0); touched.add(1 + s)
         out = [None, None, None] + [None] * ctx.n_streams          # no input gradients (raw sensor data)
-        for pi in plan.params:
+        for pi, present in zip(plan.params, ctx.present):
             # parameters no live stream reaches get None, exactly like autograd (enc_i.ln1 never gets a grad)
             reach = pi.group == 0 or pi.group in touched
-            out.append(grads[pi.offset:pi.offset + pi.numel].view(pi.shape) if (reach and pi.group >= 0) else None)
+            out.append(grads[pi.offset:pi.offset + pi.numel].view(pi.shape) if (reach and pi.group >= 0 and present) else None)
         return tuple(out)
 
 
