@@ -217,7 +217,8 @@ def run_gpu(args):
     bytes_per_unit = sum(t * d for t, d in dims) * 4 + 8
     dtype_id = gaitk.DTYPE_TF32 if wl["dtype"] == "tf32" else gaitk.DTYPE_F32
     step = gaitk.FusedTrainStep(model, crit, cagrad_c=wl["cagrad_c"], max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
-                                private_mult=wl["private_mult"], process_group=None if world > 1 else False, dtype=dtype_id)
+                                private_mult=wl["private_mult"], process_group=None if world > 1 else False, dtype=dtype_id,
+                                use_graph=bool(args.graph) and world == 1)
     NBUF = len(host)
     devb = [([x.to(dev) for x in xs], [y.to(dev) for y in ys]) for xs, ys in host]
     # global label vectors (all ranks' labels; cheap) fix the weighted-mean denominators
@@ -359,7 +360,8 @@ def run_gpu(args):
             "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": workload_name(B, args.workload), "parallelism": f"dp{world}", "global_batch": world * B,
                        "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
-                       "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks"},
+                       "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks",
+                       "cuda_graph": bool(args.graph) and world == 1},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host batch of (B,64,2)+(B,64,13)+(B,64,24) fp32 + labels copied every step (copy of batch i+1 "
                             "overlaps step i), result (loss[3], correct[3]) read back every step"},
@@ -385,6 +387,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as one CUDA graph (single-GPU)")
     ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog"],
                     help="default = BASELINE.json configs[1]; the others are extra report lines")
     ap.add_argument("--dtype", default="tf32", choices=["f32", "tf32"], help="contraction arithmetic of the stream kernels")

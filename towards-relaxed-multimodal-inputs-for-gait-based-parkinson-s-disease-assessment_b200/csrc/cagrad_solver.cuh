@@ -53,8 +53,9 @@ GAITK_HD inline void cg_clip01(const double* x, double* y, int n) {
     for (int i = 0; i < n; ++i) y[i] = x[i] < 0 ? 0.0 : (x[i] > 1 ? 1.0 : x[i]);
 }
 
-// Gaussian elimination with partial pivoting, m <= 4.  Returns false when singular.
+// Gaussian elimination with partial pivoting, m <= 4 (one reciprocal per pivot).  Returns false when singular.
 GAITK_HD inline bool cg_solve_small(double K[4][4], double* r, int m) {
+    double inv[4];
     for (int col = 0; col < m; ++col) {
         int piv = col; double best = fabs(K[col][col]);
         for (int i = col + 1; i < m; ++i) if (fabs(K[i][col]) > best) { best = fabs(K[i][col]); piv = i; }
@@ -63,15 +64,16 @@ GAITK_HD inline bool cg_solve_small(double K[4][4], double* r, int m) {
             for (int j = 0; j < m; ++j) { const double t = K[col][j]; K[col][j] = K[piv][j]; K[piv][j] = t; }
             const double t = r[col]; r[col] = r[piv]; r[piv] = t;
         }
+        inv[col] = 1.0 / K[col][col];
         for (int i = col + 1; i < m; ++i) {
-            const double f = K[i][col] / K[col][col];
+            const double f = K[i][col] * inv[col];
             if (f != 0.0) { for (int j = col; j < m; ++j) K[i][j] -= f * K[col][j]; r[i] -= f * r[col]; }
         }
     }
     for (int i = m - 1; i >= 0; --i) {
         double s = r[i];
         for (int j = i + 1; j < m; ++j) s -= K[i][j] * r[j];
-        r[i] = s / K[i][i];
+        r[i] = s * inv[i];
     }
     return true;
 }

@@ -27,7 +27,7 @@ class FusedTrainStep:
     def __init__(self, model: FlatParamModule, criterions: Sequence, *, cagrad_c: float, max_norm: float = 1.0,
                  lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, private_mult: float = 2.0,
                  process_group=None, consistency_lambda: float = 0.0, solver: int = _lib.SOLVER_SLSQP,
-                 dtype: int = None):
+                 dtype: int = None, use_graph: bool = False):
         self.model = model; self.criterions = list(criterions)
         self.cagrad_c = float(cagrad_c); self.max_norm = float(max_norm)
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
@@ -37,6 +37,7 @@ class FusedTrainStep:
         self._mom = None; self._gbuf = None; self._denom = None; self._diag = None
         self._pinned = {}; self._dev_in = {}
         self._copy_stream = None; self._staged = {}; self._slot_free = {}
+        self.use_graph = bool(use_graph); self._graphs = {}
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, plan):
@@ -72,7 +73,7 @@ class FusedTrainStep:
         return self._diag
 
     # ------------------------------------------------------------------ step
-    def step(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], *, enabled: Sequence[bool] = None,
+    def _step_impl(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], *, enabled: Sequence[bool] = None,
              tasks: Sequence[bool] = None, ys_global: Optional[Sequence[torch.Tensor]] = None,
              win_start: Optional[Sequence[torch.Tensor]] = None, logits_out: Optional[Sequence] = None,
              update: bool = True, grads_out: Optional[torch.Tensor] = None):
@@ -115,6 +116,35 @@ class FusedTrainStep:
                                       gbuf.data_ptr(), task_mask, self.cagrad_c, self.max_norm, self.lr, self.momentum,
                                       self.weight_decay, None if grads_out is None else grads_out.data_ptr(),
                                       diag.data_ptr(), self.solver, st), "gaitk_step_update")
+        return self.stats()
+
+    def step(self, xs, ys, **kw):
+        """One fused training step.  With use_graph=True the launch sequence (denominators, stream kernels, reduces,
+        update) is captured once per distinct set of buffer addresses / options and replayed as ONE CUDA graph."""
+        if not self.use_graph or self._distributed() or kw.get("grads_out") is not None or kw.get("logits_out") is not None:
+            return self._step_impl(xs, ys, **kw)
+        ws = kw.get("win_start")
+        if hasattr(self.model, "set_window") and (ws is None or ws[0] is None):
+            self.model.set_window(xs[0].shape[1])
+        def ptrs(seq):
+            return None if seq is None else tuple(0 if t is None else t.data_ptr() for t in seq)
+        key = (ptrs(xs), ptrs(ys), ptrs(kw.get("ys_global")), ptrs(kw.get("win_start")), tuple(kw.get("enabled") or ()),
+               tuple(kw.get("tasks") or ()), kw.get("update", True), xs[0].shape[0] if kw.get("win_start") is None else kw["win_start"][0].numel(),
+               tuple(id(c.weight) if getattr(c, "weight", None) is not None else 0 for c in self.criterions),
+               self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c)
+        g = self._graphs.get(key)
+        if g is None:
+            self._step_impl(xs, ys, **kw)                      # this call's step, eagerly (also allocates buffers / workspace)
+            torch.cuda.synchronize()
+            # capture records the launch sequence without executing it; later calls replay it
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_impl(xs, ys, **kw)
+            if len(self._graphs) > 64:
+                self._graphs.clear()
+            self._graphs[key] = g
+            return self.stats()
+        g.replay()
         return self.stats()
 
     # ------------------------------------------------------------------ end-to-end (host batch) entries
