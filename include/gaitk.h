@@ -50,6 +50,9 @@ extern "C" {
 /* simplex solver inside CAGrad */
 #define GAITK_SOLVER_SLSQP 0      /* restatement of SciPy SLSQP's iteration (reference parity; default) */
 #define GAITK_SOLVER_EXACT 1      /* true optimum (closed-form line minima + bisection)                 */
+#define GAITK_SOLVER_MEAN  2      /* no CAGrad: shared grad = mean of the task rows, i.e. torch.stack(losses).mean()
+                                     .backward() of step_cagrad_three's plain path (weargait_train.py:244-248); pass
+                                     private_mult = 1/n_tasks and max_norm = 0 (that path does not clip)        */
 
 typedef struct gaitk_model_desc {
     int32_t family;               /* GAITK_FAMILY_*                                                   */
@@ -66,7 +69,8 @@ typedef struct gaitk_model_desc {
     int32_t sensor_in_ch;         /* sensor_in_channels (6 / 3)                                       */
     int32_t sensor_len;           /* sensor_length (426 / 65): pooled to sensor_out_len iff T_in == it*/
     int32_t sensor_out_len;       /* SensorEncoder output_length (101)                                */
-    int32_t reserved[3];
+    int32_t reserved[3];          /* reserved[0] = proj_ch: SharedLatent3's per-stream Linear(C -> proj_ch) before the
+                                     backbone (weargait_encoders.py:299-303); 0 = none                                */
 } gaitk_model_desc;
 
 /* One CE-family criterion: CE / weighted CE (weargait_train.py:121-130), GCL

@@ -633,6 +633,35 @@ def fog_train_step(p: Params, bufs, x_skel, x_sens, ys, yt, *, sensor_length, sy
 # evaluation under masks                         weargait_train.py:391-433
 # --------------------------------------------------------------------------
 
+def baseline_forward(p: Params, xs, kind: str, synchronized: bool, bdim: int = 8):
+    """Fusion baselines weargait_encoders.py:247-322 (``kind`` = "late_fusion" | "shared_latent").
+    late_fusion sync: shared head on the MEAN latent (:271-277); async: per-stream heads on per-stream latents.
+    shared_latent: encoder -> Linear(enc_out_ch->proj_ch) per stream -> shared backbone -> head(s) (:310-322)."""
+    view = _HeadAlias(p) if synchronized else p
+    feats = [enc_walkway(p, xs[0]), enc_insole(p, xs[1]), enc_imu(p, xs[2])]
+    if kind == "shared_latent":
+        feats = [f @ p[f"proj_{m}.weight"].t() + p[f"proj_{m}.bias"] for f, m in zip(feats, "wim")]
+    elif kind != "late_fusion":
+        raise ValueError(kind)
+    reps = [backbone(p, f, bdim) for f in feats]
+    if kind == "late_fusion" and synchronized:
+        lg = task_head(view, (reps[0] + reps[1] + reps[2]) / 3.0, "head_w.")
+        return lg, lg, lg
+    return tuple(task_head(view, r, h) for r, h in zip(reps, WG_HEADS))
+
+
+def baseline_train_step(p: Params, bufs, xs, ys, *, kind, synchronized, lr=1e-3, momentum=0.9, wd=1e-4, bdim=8):
+    """step_cagrad_three with cagrad=None (weargait_train.py:244-248): mean of the three CE losses, one backward,
+    no clipping, SGD."""
+    logits = baseline_forward(p, xs, kind, synchronized, bdim)
+    losses = [weighted_ce(lg, y) for lg, y in zip(logits, ys)]
+    keys = list(p)
+    gs = torch.autograd.grad(torch.stack(losses).mean(), [p[k] for k in keys], allow_unused=True)
+    grads = {k: g for k, g in zip(keys, gs)}
+    sgd_update(p, grads, bufs, lr, momentum, wd)
+    return dict(logits=[l.detach() for l in logits], losses=[float(l.detach()) for l in losses], grads=grads)
+
+
 def eval_mask_sync(p: Params, xs, y, mask, bdim=8) -> Tuple[int, int]:
     """(#correct of the softmax-mean ensemble over enabled streams, B)."""
     with torch.no_grad():

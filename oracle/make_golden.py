@@ -233,6 +233,48 @@ def fog_case(name, *, dataset, synchronized, wm, use_nc=False, B=8, steps=3, alp
     _save(name, meta=json.dumps(meta), state0=state0, **flat)
 
 
+# ------------------------------------------------------------------ fusion baselines (--baseline)
+def baseline_case(name, baseline, synchronized, B=8, steps=2, seed=43):
+    WT.set_seed(seed)
+    args = SimpleNamespace(baseline=baseline, enc_out_ch=12, backbone_dim=8, shared_out_ch=16, num_classes=2, use_norm=False,
+                           use_cosine=False, proj_ch=16, win_len=64)
+    WT.DEVICE = torch.device("cpu")
+    model = WT.build_model(args, synchronized)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if ".ln" in k:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    flat = {f"state0/{k}": v for k, v in _state(model).items()}
+    batches = [synth_weargait_batch(B, seed=400 + i) for i in range(2)]
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    ce = torch.nn.CrossEntropyLoss()
+    for st in range(steps):
+        xs, y = batches[st % 2]
+        r = np.random.default_rng(600 + st)
+        ys = [y, y, y] if synchronized else [y, r.permutation(y), r.permutation(y)]
+        yt = [torch.from_numpy(v) for v in ys]
+        model.train()
+        lw, li, lm = model(*[torch.from_numpy(x) for x in xs])
+        L = [ce(lw, yt[0]), ce(li, yt[1]), ce(lm, yt[2])]
+        WT.step_cagrad_three(model, L[0], L[1], L[2], opt, None)          # baselines: plain averaged loss (:244-248)
+        flat[f"s{st}/logits"] = np.stack([_np(lw), _np(li), _np(lm)])
+        flat[f"s{st}/losses"] = np.array([float(l.detach()) for l in L])
+        for k, v in _grads(model).items():
+            if v is not None:
+                flat[f"s{st}/grad:{k}"] = v
+        for k, v in _state(model).items():
+            flat[f"s{st}/param:{k}"] = v
+        for j in range(3):
+            flat[f"s{st}/y{j}"] = ys[j]
+    for i, (xs, _) in enumerate(batches):
+        for j, x in enumerate(xs):
+            flat[f"x{i}_{j}"] = x
+    flat["meta"] = json.dumps(dict(baseline=baseline, synchronized=synchronized, B=B, steps=steps))
+    np.savez_compressed(OUT / f"{name}.npz", **flat)
+    print(f"  wrote {name}.npz ({(OUT / (name + '.npz')).stat().st_size / 1024:.0f} KiB, {len(flat)} arrays)")
+
+
 # ------------------------------------------------------------------ single-modality paths
 def single_modality_case(name, seed=5, B=6):
     FT.set_random_seed(seed)
@@ -431,6 +473,10 @@ def main():
         "fog_sync_ce_nc": lambda: fog_case("fog_sync_ce_nc", dataset="fog", synchronized=True, wm="ce", use_nc=True, steps=2),
         "fbg_async_classwt": lambda: fog_case("fbg_async_classwt", dataset="fbg", synchronized=False, wm="class_wt", steps=2),
         "single_modality": lambda: single_modality_case("single_modality"),
+        "bl_late_sync": lambda: baseline_case("bl_late_sync", "late_fusion", True),
+        "bl_late_async": lambda: baseline_case("bl_late_async", "late_fusion", False),
+        "bl_shared_latent_sync": lambda: baseline_case("bl_shared_latent_sync", "shared_latent", True),
+        "bl_shared_latent_async": lambda: baseline_case("bl_shared_latent_async", "shared_latent", False),
         "cagrad_corpus": lambda: cagrad_corpus("cagrad_corpus"),
         "data_path": lambda: data_case("data_path"),
     }

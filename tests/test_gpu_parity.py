@@ -598,7 +598,7 @@ def test_single_modality_paths_match_reference(gk):
         lg = m(dev(g[xk]))
         close(lg.detach().cpu().numpy(), g[f"{mod}/logits"], 2e-5, f"{mod} logits")
         loss = gk.CrossEntropyLoss()(lg, y); loss.backward()
-        close(float(loss), g[f"{mod}/loss"], 2e-5, "loss")
+        close(float(loss.detach()), g[f"{mod}/loss"], 2e-5, "loss")
         named = dict(m.named_parameters())
         for k, v in sub(sub(g, mod), "grad").items():
             close(named[k].grad.cpu().numpy(), v, 5e-5, f"{mod} grad {k}")
@@ -619,3 +619,68 @@ def test_single_modality_paths_match_reference(gk):
                 close(named[k].grad.cpu().numpy(), v, 5e-5, f"wg {mod} grad {k}")
         others = [p for n_, p in named.items() if n_.startswith("enc_") and not n_.startswith({"walkway": "enc_w", "insole": "enc_i", "imu": "enc_m"}[mod])]
         assert all(p.grad is None for p in others)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fusion baselines (weargait_train.py --baseline late_fusion | shared_latent): plain mean of the three CE losses
+BL_CASES = ["bl_late_sync", "bl_late_async", "bl_shared_latent_sync", "bl_shared_latent_async"]
+
+
+def bl_model(gk, g):
+    meta = g["meta"]
+    kw = dict(enc_out_ch=12, backbone_dim=8, shared_out_ch=16, num_classes=2, synchronized=meta["synchronized"])
+    if meta["baseline"] == "shared_latent":
+        m = gk.SharedLatent3(proj_ch=16, **kw)
+    else:
+        m = gk.LateFusion3(**kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", BL_CASES)
+def test_fusion_baseline_autograd_training_matches_reference(gk, name):
+    g = load_golden(name); meta = g["meta"]
+    m = bl_model(gk, g)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    ce = torch.nn.CrossEntropyLoss()
+    for st in range(meta["steps"]):
+        xs = [dev(g[f"x{st % 2}_{j}"]) for j in range(3)]; ys = [dev(g[f"s{st}/y{j}"]) for j in range(3)]
+        m.train()
+        lg = m(*xs)
+        ref = sub(g, f"s{st}")
+        close(torch.stack([l.detach() for l in lg]).cpu().numpy(), ref["logits"], 2e-5, "logits")
+        L = [ce(l, y) for l, y in zip(lg, ys)]
+        close(torch.stack([l.detach() for l in L]).cpu().numpy(), ref["losses"], 2e-5, "losses")
+        opt.zero_grad(set_to_none=True)
+        torch.stack(L).mean().backward()                      # step_cagrad_three with cagrad=None (:244-248)
+        named = dict(m.named_parameters())
+        n_checked = 0
+        for k, v in ref.items():
+            if k.startswith("grad:"):
+                close(named[k[5:]].grad.cpu().numpy(), v, 5e-5, f"step {st} grad {k[5:]}"); n_checked += 1
+        assert n_checked >= 14
+        assert named["enc_i.ln1.weight"].grad is None
+        opt.step()
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+@pytest.mark.parametrize("name", ["bl_shared_latent_sync", "bl_shared_latent_async", "bl_late_async"])
+def test_fusion_baseline_fused_step_matches_reference(gk, name):
+    """The plain averaged step is the fused step in GAITK_SOLVER_MEAN mode (shared grad = mean of the task rows), no
+    clipping and private gradients scaled by 1/3."""
+    g = load_golden(name); meta = g["meta"]
+    m = bl_model(gk, g)
+    crit = [gk.CrossEntropyLoss() for _ in range(3)]
+    step = gk.FusedTrainStep(m, crit, cagrad_c=0.0, max_norm=0.0, private_mult=1.0 / 3.0, solver=gk.SOLVER_MEAN)
+    for st in range(meta["steps"]):
+        xs = [dev(g[f"x{st % 2}_{j}"]) for j in range(3)]; ys = [dev(g[f"s{st}/y{j}"]) for j in range(3)]
+        loss, _ = step.step(xs, ys)
+        ref = sub(g, f"s{st}")
+        close(loss.cpu().numpy()[:3], ref["losses"], 2e-5, "losses")
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")

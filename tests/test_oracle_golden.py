@@ -1,3 +1,4 @@
+import json
 """Pins the CPU oracle (oracle/gait_oracle.py) to golden vectors produced by
 running the reference itself (oracle/make_golden.py).  CPU only."""
 import numpy as np
@@ -180,3 +181,30 @@ def test_single_modality_paths_match_reference():
         for k, v in sub(sub(sub(g, "wg"), mod), "grad").items():
             if k in p:
                 _close(p[k].grad.numpy(), v, rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["bl_late_sync", "bl_late_async", "bl_shared_latent_sync", "bl_shared_latent_async"])
+def test_fusion_baselines_match_reference(name):
+    """LateFusion3 / SharedLatent3 trained the way ``--baseline`` trains them (plain mean of the CE losses)."""
+    z = load_golden(name)
+    meta = z["meta"]
+    sync = meta["synchronized"]
+    p = O.canonical_params(sub(z, "state0"), sync)
+    bufs = {}
+    for st in range(meta["steps"]):
+        xs = [torch.from_numpy(z[f"x{st % 2}_{j}"]) for j in range(3)]
+        ys = [torch.from_numpy(z[f"s{st}/y{j}"]) for j in range(3)]
+        out = O.baseline_train_step(p, bufs, xs, ys, kind=meta["baseline"], synchronized=sync)
+        for j in range(3):
+            _close(out["logits"][j].numpy(), z[f"s{st}/logits"][j])
+        _close(np.array(out["losses"]), z[f"s{st}/losses"])
+        for k, g in out["grads"].items():
+            gk = f"s{st}/grad:{k}"
+            if gk not in z and k.startswith("head_w."):      # named_parameters() de-duplicates to the first name
+                gk = f"s{st}/grad:_shared_head.{k[7:]}"
+            if g is None:
+                assert gk not in z, k
+            else:
+                _close(g.numpy(), z[gk])
+        for k, v in p.items():
+            _close(v.detach().numpy(), z[f"s{st}/param:{k}"], rtol=1e-5, atol=1e-6)

@@ -1,14 +1,14 @@
 """gaitk -- B200 (sm_100a) implementation of the gait training hot path behind the reference's own
 module API.  See DESIGN.md / INTEGRATION.md at the repository root."""
 from . import _lib
-from ._lib import GaitkError, lib, DTYPE_F32, DTYPE_TF32, SOLVER_SLSQP, SOLVER_EXACT
+from ._lib import GaitkError, lib, DTYPE_F32, DTYPE_TF32, SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN
 from .plan import Plan, FlatParamModule
-from .weargait_encoders import WearGaitThreeModal
+from .weargait_encoders import WearGaitThreeModal, LateFusion3, SharedLatent3
 from .feature_encoder import MultiModalMultiTaskModel, SensorModalityModel, SkelModalityModel
 from .classification_losses import GCLLoss, LDAMLoss, CrossEntropyLoss, make_loss_desc, criterion_spec
 from .multitask_weighting import CAGrad
 from .fused_step import FusedTrainStep
 from . import dist
 
-__all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "MultiModalMultiTaskModel", "SensorModalityModel", "SkelModalityModel",
+__all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "LateFusion3", "SharedLatent3", "MultiModalMultiTaskModel", "SensorModalityModel", "SkelModalityModel",
            "GCLLoss", "LDAMLoss", "CrossEntropyLoss", "make_loss_desc", "criterion_spec", "CAGrad", "FusedTrainStep"]

@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("GAITK_LIB", _HERE / "libgaitk.so"))
 MAX_STREAMS, MAX_CLASSES = 3, 4
 FAMILY_WEARGAIT, FAMILY_FOG = 0, 1
 DTYPE_F32, DTYPE_TF32 = 0, 1
-SOLVER_SLSQP, SOLVER_EXACT = 0, 1
+SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN = 0, 1, 2
 
 EXPORTS = [
     "gaitk_version", "gaitk_last_error", "gaitk_plan_create", "gaitk_plan_destroy", "gaitk_param_count",

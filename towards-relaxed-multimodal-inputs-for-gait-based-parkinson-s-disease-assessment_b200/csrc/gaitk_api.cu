@@ -37,11 +37,11 @@ typedef void (*StreamKernelTcFn)(const StreamArgs, const TcPlan);
 
 struct StreamPlan {
     int enc, CIN, T_in, T, W, rows_in, rows, halo, RBi, RB, pool_sensor;
-    int H, C, S, NFL, KT1, skip_identity;
+    int H, C, S, NFL, KT1, skip_identity, PROJ;
     StreamKernelFn fn;
     SmemPlan sp; GradOff go; int NGP; size_t smem_bytes; int ctas_per_sm;
     StreamKernelTcFn fn_tc; TcPlan tp; size_t smem_tc; int ctas_tc;      // tensor-core variant (nullptr when unavailable)
-    int p_w1, p_b1, p_w2, p_b2, p_wsk, p_bsk, p_lng, p_lnb, p_hng, p_hnb, p_hw, p_hb;   // param indices (-1 = none)
+    int p_w1, p_b1, p_w2, p_b2, p_wsk, p_bsk, p_lng, p_lnb, p_hng, p_hnb, p_hw, p_hb, p_wp, p_bp;   // param indices (-1 = none)
     int nseg; Seg seg[MAX_SEG];
 };
 
@@ -67,11 +67,18 @@ static int add_param(gaitk_plan* pl, const std::string& name, int group, int d0,
 // kernel instantiations -------------------------------------------------------------------
 template <class Cfg> static StreamKernelFn kfn() { return &stream_kernel<Cfg>; }
 
-struct KernelKey { int enc, CIN, KT1, H, C, S, NFL; };
+struct KernelKey { int enc, CIN, KT1, H, C, S, NFL, PROJ; };
 static StreamKernelFn find_kernel(const KernelKey& k) {
 #define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
-    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
         return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
+#define GK_CASE_P(e_, ci_, kt_, h_, c_, s_, nfl_, p_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == p_) \
+        return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_, p_>>();
+    // SharedLatent3 (weargait_encoders.py:284-322): per-stream Linear(12 -> proj_ch=16) before the backbone
+    GK_CASE_P(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4, 16)
+    GK_CASE_P(ENC_INSOLE, 13, 5, 24, 12, 16, 4, 16)
+    GK_CASE_P(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4, 16)
     // WearGait defaults (weargait_train.py:655-673): C=12, H=24, S=16, bdim=8
     GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
     GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
@@ -82,13 +89,14 @@ static StreamKernelFn find_kernel(const KernelKey& k) {
     GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
     GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
 #undef GK_CASE
+#undef GK_CASE_P
     return nullptr;
 }
 
 template <class Cfg> static StreamKernelTcFn kfn_tc() { return &stream_kernel_tc<Cfg>; }
 static StreamKernelTcFn find_kernel_tc(const KernelKey& k) {
 #define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
-    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
         return kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
     GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
     GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
@@ -109,6 +117,7 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     sp.enc = enc; sp.CIN = CIN; sp.KT1 = KT1; sp.H = H; sp.C = d.enc_out_ch; sp.S = d.shared_out_ch;
     sp.T_in = T_in; sp.T = T; sp.pool_sensor = pool_sensor;
     sp.skip_identity = (enc == ENC_INSOLE && H == sp.C);
+    sp.PROJ = (d.family == GAITK_FAMILY_WEARGAIT) ? d.reserved[0] : 0;      // proj_ch
     const int NF = d.backbone_dim * d.shared_out_ch;
     if (NF % 32 != 0 || NF > 512) return fail(GAITK_E_SHAPE, "backbone_dim*shared_out_ch = %d must be a multiple of 32 (<= 512)", NF);
     if (sp.S % 4 != 0) return fail(GAITK_E_SHAPE, "shared_out_ch must be a multiple of 4");
@@ -118,7 +127,7 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     while (sp.W & (sp.W - 1)) --sp.W;                   // power of two (row <-> (t, w) by shifts)
     sp.rows = T * sp.W; sp.rows_in = T_in * sp.W; sp.halo = (KT1 / 2 > 1 ? KT1 / 2 : 1) * sp.W;
     sp.RB = round_rb(sp.rows, sp.halo); sp.RBi = round_rb(sp.rows_in, sp.halo);
-    KernelKey key = {enc, CIN, KT1, H, sp.C, sp.S, sp.NFL};
+    KernelKey key = {enc, CIN, KT1, H, sp.C, sp.S, sp.NFL, sp.PROJ};
     sp.fn = find_kernel(key);
     if (!sp.fn)
         return fail(GAITK_E_SHAPE, "no sm_100a kernel instantiated for stream %d (enc=%d Cin=%d k=%d H=%d C=%d S=%d NF=%d); "
@@ -126,6 +135,7 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     // ---- shared memory plan (floats)
     const int CI4 = (CIN + 3) / 4, C4 = (sp.C + 3) / 4, CP = C4 * 4, H4 = (H + 3) / 4, S4 = sp.S / 4;
     const int O1 = (enc == ENC_INSOLE) ? H4 * 4 : CP;
+    const int CB = sp.PROJ ? sp.PROJ : sp.C, CB4 = (CB + 3) / 4, CBP = CB4 * 4;
     SmemPlan& m = sp.sp; memset(&m, 0, sizeof(m));
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
@@ -140,11 +150,12 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     m.W1F = take(KT1 * CI4 * 4 * O1); m.B1 = take(O1);
     if (enc == ENC_INSOLE) { m.W2F = take(3 * H4 * 4 * CP); m.B2 = take(CP); m.W2D = take(3 * CP * H4 * 4); }
     m.LNG = take(CP); m.LNB = take(CP);
-    m.WBF = take(3 * CP * sp.S); m.BB = take(sp.S); m.WBD = take(3 * sp.S * CP);
+    m.WBF = take(3 * CBP * sp.S); m.BB = take(sp.S); m.WBD = take(3 * sp.S * CBP);
+    if (sp.PROJ) { m.L = take(CB4 * sp.RB * 4); m.DL = take(CB4 * sp.RB * 4); m.WPF = take(CP * CBP); m.BP = take(CBP); m.WPD = take(sp.PROJ * CP); }
     m.HW = take(KMAX * NF); m.HB = take(KMAX); m.HNG = take(NF); m.HNB = take(NF); m.INW = take(KMAX);
     m.P = take(WMAX * NF); m.DP = take(WMAX * NF); m.LOGIT = take(WMAX * KMAX);
     m.BINS = take(2 * d.backbone_dim + 4 * T + 2 * T_in + 8);
-    int nblk_max = std::max(std::max(KT1 * CI4 * (O1 / 4), 3 * C4 * S4), enc == ENC_INSOLE ? 3 * H4 * C4 : 0);
+    int nblk_max = std::max(std::max(KT1 * CI4 * (O1 / 4), 3 * CB4 * S4), enc == ENC_INSOLE ? 3 * H4 * C4 : 0);
     m.STAGE = take(16 * std::max(std::max(NF, 256), std::max(nblk_max, NT)));
     m.total = o;
     sp.smem_bytes = (size_t)o * sizeof(float);
@@ -156,7 +167,7 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     if (occ < 1) return fail(GAITK_E_SHAPE, "stream %d kernel does not fit on an SM", s);
     sp.ctas_per_sm = occ;
     // ---- tensor-core variant (tcgen05 + mma.sync, tf32): full 128-row tiles only
-    sp.fn_tc = (sp.rows == NT && T_in == T) ? find_kernel_tc(key) : nullptr;
+    sp.fn_tc = (sp.rows == NT && T_in == T && sp.PROJ == 0) ? find_kernel_tc(key) : nullptr;
     if (sp.fn_tc) {
         auto ev = [](int x) { return (x + 1) / 2 * 2; };
         const int KX = ev(CI4), KH = ev(H4), KC = ev(C4), KS = ev(S4);
@@ -214,6 +225,7 @@ static void layout_stream_grads(gaitk_plan* pl, int s) {
     };
     seg(sp.p_w1, go.w1); seg(sp.p_b1, go.b1); seg(sp.p_w2, go.w2); seg(sp.p_b2, go.b2);
     seg(sp.p_wsk, go.wsk); seg(sp.p_bsk, go.bsk); seg(sp.p_lng, go.lng); seg(sp.p_lnb, go.lnb);
+    seg(sp.p_wp, go.wp); seg(sp.p_bp, go.bp);
     seg(pl->p_wbb, go.wbb); seg(pl->p_bbb, go.bbb);
     seg(sp.p_hng, go.hng); seg(sp.p_hnb, go.hnb); seg(sp.p_hw, go.hw); seg(sp.p_hb, go.hb);
     go.total = o;
@@ -249,7 +261,7 @@ extern "C" int gaitk_plan_create(const gaitk_model_desc* desc, int device, gaitk
     };
     for (int s = 0; s < GAITK_MAX_STREAMS; ++s) {
         StreamPlan& sp = pl->st[s];
-        sp.p_w1 = sp.p_b1 = sp.p_w2 = sp.p_b2 = sp.p_wsk = sp.p_bsk = sp.p_lng = sp.p_lnb = sp.p_hng = sp.p_hnb = sp.p_hw = sp.p_hb = -1;
+        sp.p_w1 = sp.p_b1 = sp.p_w2 = sp.p_b2 = sp.p_wsk = sp.p_bsk = sp.p_lng = sp.p_lnb = sp.p_hng = sp.p_hnb = sp.p_hw = sp.p_hb = sp.p_wp = sp.p_bp = -1;
     }
     if (d.family == GAITK_FAMILY_WEARGAIT) {
         // named_parameters() order of WearGaitThreeModal (weargait_encoders.py:121-141)
@@ -265,9 +277,16 @@ extern "C" int gaitk_plan_create(const gaitk_model_desc* desc, int device, gaitk
         i.p_wsk = add_param(pl, "enc_i.skip.weight", 2, C, H, 1); i.p_bsk = add_param(pl, "enc_i.skip.bias", 2, C);
         m.p_w1 = add_param(pl, "enc_m.conv.weight", 3, C, 24, 3); m.p_b1 = add_param(pl, "enc_m.conv.bias", 3, C);
         m.p_lng = add_param(pl, "enc_m.ln.weight", 3, C); m.p_lnb = add_param(pl, "enc_m.ln.bias", 3, C);
-        pl->p_wbb = add_param(pl, "backbone.conv.weight", 0, S, C, 3); pl->p_bbb = add_param(pl, "backbone.conv.bias", 0, S);
+        const int proj = d.reserved[0];                       // SharedLatent3 projection width (0 = WearGaitThreeModal)
+        if (proj > 0) {
+            w.p_wp = add_param(pl, "proj_w.weight", 1, proj, C); w.p_bp = add_param(pl, "proj_w.bias", 1, proj);
+            i.p_wp = add_param(pl, "proj_i.weight", 2, proj, C); i.p_bp = add_param(pl, "proj_i.bias", 2, proj);
+            m.p_wp = add_param(pl, "proj_m.weight", 3, proj, C); m.p_bp = add_param(pl, "proj_m.bias", 3, proj);
+        }
+        pl->p_wbb = add_param(pl, "backbone.conv.weight", 0, S, proj > 0 ? proj : C, 3); pl->p_bbb = add_param(pl, "backbone.conv.bias", 0, S);
         if (sync) {
-            head("head_w.", 0, w);
+            // _shared_or_three_heads assigns _shared_head first (weargait_encoders.py:306), WearGaitThreeModal head_w first (:135)
+            head(proj > 0 ? "_shared_head." : "head_w.", 0, w);
             i.p_hng = m.p_hng = w.p_hng; i.p_hnb = m.p_hnb = w.p_hnb; i.p_hw = m.p_hw = w.p_hw; i.p_hb = m.p_hb = w.p_hb;
         } else {
             head("head_w.", 1, w); head("head_i.", 2, i); head("head_m.", 3, m);
@@ -371,6 +390,7 @@ static void fill_args(const gaitk_plan* pl, int s, const float* params, const fl
     a.wsk = pp(params, pl, sp.p_wsk); a.bsk = pp(params, pl, sp.p_bsk); a.lng = pp(params, pl, sp.p_lng); a.lnb = pp(params, pl, sp.p_lnb);
     a.wbb = pp(params, pl, pl->p_wbb); a.bbb = pp(params, pl, pl->p_bbb);
     a.hng = pp(params, pl, sp.p_hng); a.hnb = pp(params, pl, sp.p_hnb); a.hw = pp(params, pl, sp.p_hw); a.hb = pp(params, pl, sp.p_hb);
+    a.wp = pp(params, pl, sp.p_wp); a.bp = pp(params, pl, sp.p_bp);
     a.head_norm = sp.p_hng >= 0; a.head_cos = pl->d.use_cosine != 0; a.skip_identity = sp.skip_identity;
     a.scale = 1.f; for (int k = 0; k < KMAX; ++k) { a.margin[k] = 0.f; a.cls_w[k] = 1.f; }
     a.go = sp.go; a.NGP = sp.NGP;

@@ -32,7 +32,7 @@ enum Mode { MODE_FWD = 0, MODE_FUSED = 1, MODE_BWD_EXT = 2 };
 
 // stream-local gradient layout (offsets in floats into a partial-gradient row; -1 = absent)
 struct GradOff {
-    int w1, b1, w2, b2, wsk, bsk, lng, lnb, wbb, bbb, hng, hnb, hw, hb;
+    int w1, b1, w2, b2, wsk, bsk, lng, lnb, wbb, bbb, hng, hnb, hw, hb, wp, bp;
     int total;      // NG
 };
 
@@ -45,6 +45,7 @@ struct StreamArgs {
     int mode, zero_input, pool_sensor;
     // parameters (global memory, PyTorch layouts)
     const float *w1, *b1, *w2, *b2, *wsk, *bsk, *lng, *lnb, *wbb, *bbb, *hng, *hnb, *hw, *hb;
+    const float *wp, *bp;          // optional per-stream projection Linear(C -> PROJ) between encoder and backbone (SharedLatent3)
     int head_norm, head_cos, skip_identity;
     // loss
     const long long* y;
@@ -133,7 +134,7 @@ __device__ __forceinline__ void gelu_fwd_fast(float a, float& g, float& dg) {
 }
 // ------------------------------------------------------------------------------------------
 // compile-time description of one stream
-template <int ENC_, int CIN_, int KT1_, int H_, int C_, int S_, int NFL_>
+template <int ENC_, int CIN_, int KT1_, int H_, int C_, int S_, int NFL_, int PROJ_ = 0>
 struct StreamCfg {
     static constexpr int ENC = ENC_;
     static constexpr int CIN = CIN_;                 // real input channels
@@ -147,6 +148,10 @@ struct StreamCfg {
     static constexpr int S = S_;                     // backbone channels (multiple of 4)
     static constexpr int S4 = S_ / 4;
     static constexpr int NFL = NFL_;                 // head features per lane (NF = 32 * NFL)
+    static constexpr int PROJ = PROJ_;               // per-stream projection width (0 = none)
+    static constexpr int CB = PROJ_ ? PROJ_ : C_;    // backbone input channels
+    static constexpr int CB4 = (CB + 3) / 4;
+    static constexpr int CBP = CB4 * 4;
     static constexpr int O1 = (ENC_ == ENC_INSOLE) ? H4 * 4 : CP;   // padded outputs of the first conv
 };
 
@@ -155,6 +160,7 @@ struct SmemPlan {
     int X, HA, D1, XH, D, F, RSTD, Z, A;            // activation buffers
     int W1F, B1, W2F, B2, W2D, LNG, LNB, WBF, BB, WBD, HW, HB, HNG, HNB, INW;   // weights
     int P, DP, LOGIT, BINS, STAGE;                   // head / pooling scratch
+    int L, DL, WPF, BP, WPD;                         // projection stage (SharedLatent3)
     int total;
 };
 

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     constexpr int ENC = Cfg::ENC, CIN = Cfg::CIN, CI4 = Cfg::CI4, KT1 = Cfg::KT1, H = Cfg::H, H4 = Cfg::H4;
     constexpr int C = Cfg::C, C4 = Cfg::C4, CP = Cfg::CP, S = Cfg::S, S4 = Cfg::S4, NFL = Cfg::NFL, O1 = Cfg::O1;
+    constexpr int PROJ = Cfg::PROJ, CB = Cfg::CB, CB4 = Cfg::CB4, CBP = Cfg::CBP;
+    static_assert(PROJ == 0 || (ENC != ENC_CONV_POOL && ENC != ENC_LINEAR_LN_RELU), "projection stage: WearGait encoders");
     const int W = A.W, halo = A.halo, RB = A.RB, RBi = A.RBi, rows = A.rows, rows_in = A.rows_in, T = A.T, T_in = A.T_in;
     const int K = A.K, NF = A.NF, bdim = A.bdim;
     const bool train = A.mode != MODE_FWD;
@@ -128,6 +130,8 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     int* bins = reinterpret_cast<int*>(sm + SP.BINS);   // [0,bdim) start, [bdim,2bdim) end, then per-t lo / hi, then
                                                         // encoder-pool tables (CONV_POOL)
     float* stage = sm + SP.STAGE;
+    float* Ls = sm + SP.L; float* DLs = sm + SP.DL; float* wpf = sm + SP.WPF; float* bps = sm + SP.BP; float* wpd = sm + SP.WPD;
+    float* BBin = PROJ ? Ls : Fs;                        // what the backbone convolves
 
     // ---- one-time setup: zero everything (halos, padded channels), stage weights, bin tables
     for (int i = tid; i < SP.total; i += NT) sm[i] = 0.f;
@@ -155,11 +159,20 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     if constexpr (ENC != ENC_CONV_POOL) {
         for (int i = tid; i < C; i += NT) { lngs[i] = A.lng[i]; lnbs[i] = A.lnb[i]; }
     }
-    for (int i = tid; i < S * C * 3; i += NT) {
-        const int o = i / (C * 3), ci = (i / 3) % C, tap = i % 3;
+    for (int i = tid; i < S * CB * 3; i += NT) {
+        const int o = i / (CB * 3), ci = (i / 3) % CB, tap = i % 3;
         const float w = A.wbb[i];
-        wbf[(tap * CP + ci) * S + o] = w;
-        wbd[((2 - tap) * S + o) * CP + ci] = w;
+        wbf[(tap * CBP + ci) * S + o] = w;
+        wbd[((2 - tap) * S + o) * CBP + ci] = w;
+    }
+    if constexpr (PROJ > 0) {
+        // Linear (PROJ, C): forward layout [ci][o] (a 1-tap conv), backward keeps PyTorch's [o][ci]
+        for (int i = tid; i < PROJ * C; i += NT) {
+            const int o = i / C, ci = i - o * C;
+            wpf[ci * CBP + o] = A.wp[i];
+            wpd[o * CP + ci] = A.wp[i];
+        }
+        for (int i = tid; i < PROJ; i += NT) bps[i] = A.bp[i];
     }
     for (int i = tid; i < S; i += NT) bbs[i] = A.bbb[i];
     for (int i = tid; i < K * NF; i += NT) hws[i] = A.hw[i];
@@ -203,13 +216,17 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     // ---- persistent accumulators
     Wgrad<KT1, CI4, O1 / 4> g_w1;
     Wgrad<3, (ENC == ENC_INSOLE ? H4 : 1), (ENC == ENC_INSOLE ? C4 : 1)> g_w2;
-    Wgrad<3, C4, S4> g_wb;
+    Wgrad<3, CB4, S4> g_wb;
+    Wgrad<1, (PROJ ? C4 : 1), (PROJ ? CB4 : 1)> g_wp;
+    float g_bp[PROJ ? CBP : 4];
     float g_b1[O1], g_b2[ENC == ENC_INSOLE ? CP : 4], g_lng[CP], g_lnb[CP], g_bb[S];
     HeadState<NFL, S> head; head.zero();
     HeadCtx hc; hc.Zs = Zs; hc.RB = RB; hc.halo = halo; hc.W = W; hc.S = S; hc.bin_s = bins; hc.bin_e = bins + bdim;
     hc.hws = hws; hc.hbs = hbs; hc.hngs = hngs; hc.hnbs = hnbs; hc.inws = inws; hc.DPs = DPs; hc.Ps = nullptr; hc.ys = nullptr;
     if (train) {
-        g_w1.zero(); g_w2.zero(); g_wb.zero();
+        g_w1.zero(); g_w2.zero(); g_wb.zero(); g_wp.zero();
+#pragma unroll
+        for (int i = 0; i < (PROJ ? CBP : 4); ++i) g_bp[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < O1; ++i) g_b1[i] = 0.f;
 #pragma unroll
@@ -297,13 +314,23 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
                 }
                 store_row<CP>(Fs, RB, halo, r, f);
                 if (train) { store_row<CP>(XHs, RB, halo, r, xh); RSTDs[r] = rstd; }
+                if constexpr (PROJ > 0) {
+                    float l[CBP];
+#pragma unroll
+                    for (int j = 0; j < CBP; ++j) l[j] = j < PROJ ? bps[j] : 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                        for (int j = 0; j < CBP; ++j) l[j] = fmaf(f[cc], wpf[cc * CBP + j], l[j]);
+                    store_row<CBP>(Ls, RB, halo, r, l);
+                }
             }
             __syncthreads();
         }
         // ================= shared backbone forward: conv3 -> ReLU
         for (int r = tid; r < rows; r += NT) {
             float z[S];
-            conv_row<3, C4, S>(Fs, RB, halo, W, r, wbf, bbs, z);
+            conv_row<3, CB4, S>(BBin, RB, halo, W, r, wbf, bbs, z);
 #pragma unroll
             for (int s = 0; s < S; ++s) z[s] = fmaxf(z[s], 0.f);
             store_row<S>(Zs, RB, halo, r, z);
@@ -329,7 +356,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             store_row<S>(Zs, RB, halo, r, dz);
         }
         __syncthreads();
-        g_wb.accumulate(Fs, RB, Zs, RB, halo, W, rows, tid);
+        g_wb.accumulate(BBin, RB, Zs, RB, halo, W, rows, tid);
         // dgrad into the encoder output + encoder-specific backward up to the first-conv pre-activation
         if constexpr (ENC == ENC_CONV_POOL) {
             for (int r = tid; r < rows; r += NT) {
@@ -367,7 +394,21 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         } else {
             for (int r = tid; r < rows; r += NT) {
                 float df[CP], xh[CP], dxh[CP], dg[CP], da[CP];
-                conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
+                if constexpr (PROJ > 0) {
+                    float dl[CBP];
+                    conv_row<3, S4, CBP>(Zs, RB, halo, W, r, wbd, nullptr, dl);
+#pragma unroll
+                    for (int j = 0; j < CBP; ++j) g_bp[j] += dl[j];
+                    store_row<CBP>(DLs, RB, halo, r, dl);
+#pragma unroll
+                    for (int cc = 0; cc < CP; ++cc) df[cc] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < PROJ; ++j)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) df[cc] = fmaf(dl[j], wpd[j * CP + cc], df[cc]);
+                } else {
+                    conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
+                }
                 load_row<CP>(XHs, RB, halo, r, xh);
                 const float rstd = RSTDs[r];
                 if constexpr (ENC == ENC_LINEAR_LN_RELU) {
@@ -414,6 +455,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             } else {
                 g_w1.accumulate(Xs, RBi, XHs, RB, halo, W, rows, tid);
             }
+            if constexpr (PROJ > 0) g_wp.accumulate(Fs, RB, DLs, RB, halo, W, rows, tid);
         }
         __syncthreads();
     }
@@ -436,7 +478,11 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         flush_rowacc<CP>(g_lng, C, stage, out + go.lng, nullptr, tid);
         flush_rowacc<CP>(g_lnb, C, stage, out + go.lnb, nullptr, tid);
     }
-    g_wb.flush(stage, out + go.wbb, nullptr, C, S, tid);
+    g_wb.flush(stage, out + go.wbb, nullptr, CB, S, tid);
+    if constexpr (PROJ > 0) {
+        g_wp.flush(stage, out + go.wp, nullptr, C, PROJ, tid);
+        flush_rowacc<CBP>(g_bp, PROJ, stage, out + go.bp, nullptr, tid);
+    }
     flush_rowacc<S>(g_bb, S, stage, out + go.bbb, nullptr, tid);
     head.flush(A, stage, out, tid);
 }

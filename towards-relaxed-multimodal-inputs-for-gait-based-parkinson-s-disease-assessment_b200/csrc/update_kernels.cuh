@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
         Quad3 q;
         for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) q.A[i][j] = (double)a[i][j];
         double w[3] = {0, 0, 0}; double c = 0; int iters = 0;
-        cagrad_weights(&a[0][0], n, U.alpha, U.solver, w, &c, &iters);
+        const bool plain_mean = U.solver == 2;             // GAITK_SOLVER_MEAN: torch.stack(losses).mean().backward()
+        if (plain_mean) { for (int i = 0; i < n; ++i) w[i] = 1.0 / n; }
+        else cagrad_weights(&a[0][0], n, U.alpha, U.solver, w, &c, &iters);
         q.c = c;
         for (int i = 0; i < n; ++i) { q.Ab[i] = 0; for (int j = 0; j < n; ++j) q.Ab[i] += q.A[i][j] / n; }
         // gw = G w with w cast to fp32 as torch.Tensor(w_cpu) does (:719)
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
         const double lam = c / (sqrt(gw2 > 0 ? gw2 : 0) + 1e-8);
         // g = n * (mean_i G_i + lam * sum_i w_i G_i) / (1 + alpha^2)  = sum_i k_i G_i
         double k[3], norm2 = 0;
-        for (int i = 0; i < n; ++i) k[i] = (double)n * (1.0 / n + lam * w[i]) / (1.0 + (double)U.alpha * U.alpha);
+        for (int i = 0; i < n; ++i)
+            k[i] = plain_mean ? 1.0 / n : (double)n * (1.0 / n + lam * w[i]) / (1.0 + (double)U.alpha * U.alpha);
         for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) norm2 += k[i] * q.A[i][j] * k[j];
         const double norm = sqrt(norm2 > 0 ? norm2 : 0);
         double clip = 1.0;

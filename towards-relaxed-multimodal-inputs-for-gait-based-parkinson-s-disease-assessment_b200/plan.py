@@ -24,7 +24,7 @@ class ParamInfo:
 class Plan:
     def __init__(self, *, family: int, T: int, enc_out_ch: int, shared_out_ch: int, backbone_dim: int,
                  num_classes: int, use_norm=False, use_cosine=False, synchronized=True, skel_in_dim=0,
-                 sensor_in_ch=0, sensor_len=0, sensor_out_len=0, device: Optional[torch.device] = None):
+                 sensor_in_ch=0, sensor_len=0, sensor_out_len=0, proj_ch=0, device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise _lib.GaitkError("gaitk needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -33,6 +33,7 @@ class Plan:
                            use_cosine=int(bool(use_cosine)), synchronized=int(bool(synchronized)),
                            skel_in_dim=skel_in_dim, sensor_in_ch=sensor_in_ch, sensor_len=sensor_len,
                            sensor_out_len=sensor_out_len)
+        d.reserved[0] = int(proj_ch)
         self.desc = d
         h = C.c_void_p()
         check(lib().gaitk_plan_create(C.byref(d), self.device.index or 0, C.byref(h)), "gaitk_plan_create")

@@ -214,3 +214,106 @@ class WearGaitThreeModal(FlatParamModule):
         if self._shared_head is not None:
             params += list(self._shared_head.parameters())
         return params
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fusion baselines reachable through ``weargait_train.py --baseline`` (weargait_encoders.py:199-322)
+def _shared_or_three_heads(feat_dim, num_classes, synchronized, use_norm, use_cosine):
+    """weargait_encoders.py:199-207."""
+    if synchronized:
+        shared = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+        return shared, shared, shared, shared
+    hw = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+    hi = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+    hm = TaskHead(feat_dim, num_classes, use_norm=use_norm, use_cosine=use_cosine)
+    return None, hw, hi, hm
+
+
+class _ThreeStreamBase(FlatParamModule):
+    """Common plumbing of the 3-stream fusion baselines (same plan family as WearGaitThreeModal)."""
+    _proj_ch = 0
+
+    def _build(self, enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized, proj_ch=0):
+        self.synchronized = synchronized
+        self.enc_w = WalkwayEncoder(out_ch=enc_out_ch)
+        self.enc_i = InsoleEncoderDeep(in_ch=13, out_ch=enc_out_ch)
+        self.enc_m = IMUEncoderShallow(in_ch=24, out_ch=enc_out_ch)
+        if proj_ch:
+            self.proj_w = nn.Linear(enc_out_ch, proj_ch)
+            self.proj_i = nn.Linear(enc_out_ch, proj_ch)
+            self.proj_m = nn.Linear(enc_out_ch, proj_ch)
+        self.backbone = SharedBackbone(in_ch=proj_ch or enc_out_ch, out_ch=shared_out_ch, bdim=backbone_dim)
+        feat_dim = shared_out_ch * backbone_dim
+        self._shared_head, self.head_w, self.head_i, self.head_m = _shared_or_three_heads(
+            feat_dim, num_classes, synchronized, use_norm, use_cosine)
+        self._cfg = dict(enc_out_ch=enc_out_ch, backbone_dim=backbone_dim, shared_out_ch=shared_out_ch,
+                         num_classes=num_classes, use_norm=bool(use_norm), use_cosine=bool(use_cosine))
+        self._proj_ch = int(proj_ch)
+        self._T = None
+
+    def _plan_kwargs(self):
+        if self._T is None:
+            raise _lib.GaitkError("window length unknown: call the model on a batch first")
+        c = self._cfg
+        return dict(family=_lib.FAMILY_WEARGAIT, T=self._T, enc_out_ch=c["enc_out_ch"], shared_out_ch=c["shared_out_ch"],
+                    backbone_dim=c["backbone_dim"], num_classes=c["num_classes"], use_norm=c["use_norm"],
+                    use_cosine=c["use_cosine"], synchronized=self.synchronized, proj_ch=self._proj_ch)
+
+    def _plan_name_map(self):
+        if not self.synchronized or self._proj_ch:
+            return None                       # names coincide (the plan already calls the sync head _shared_head. with proj)
+        mp = {pi.name: pi.name for pi in self.plan().params}
+        for k in list(mp):
+            if k.startswith("head_w."):
+                mp[k] = "_shared_head." + k[len("head_w."):]
+        return mp
+
+    def set_window(self, T: int):
+        if self._T != T:
+            self._T = int(T)
+            object.__setattr__(self, "_plan", None); object.__setattr__(self, "_flat", None)
+        return self
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        object.__setattr__(self, "_flat", None)
+        return out
+
+    def _streams(self, xw, xi, xm):
+        self.set_window(xw.shape[1])
+        return run_streams(self, [xw, xi, xm], 0b111)
+
+
+class LateFusion3(_ThreeStreamBase):
+    """weargait_encoders.py:247-282.  Sync: the shared head sees the mean of the three latent vectors; the head is
+    linear, so W * mean_s(r_s) + b == mean_s(W r_s + b): the fused logits are the mean of the per-stream logits of the
+    shared-head model, and the backward is the fused stream kernels with dlogits / 3.  Async: per-stream heads on
+    per-stream latents (no fusion), i.e. the three-stream model itself."""
+
+    def __init__(self, enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm=False, use_cosine=False,
+                 synchronized=True):
+        super().__init__()
+        if synchronized and (use_norm or use_cosine):
+            raise _lib.GaitkError("LateFusion3 with a normalising head is not linear in the latent; the trainer never builds it "
+                                  "(weargait_train.py:513-524 passes neither use_norm nor use_cosine)")
+        self._build(enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized)
+
+    def forward(self, xw, xi, xm):
+        lw, li, lm = self._streams(xw, xi, xm)
+        if self.synchronized:
+            logits = (lw + li + lm) / 3.0
+            return logits, logits, logits
+        return lw, li, lm
+
+
+class SharedLatent3(_ThreeStreamBase):
+    """weargait_encoders.py:284-322: encoder -> per-stream Linear(enc_out_ch -> proj_ch) -> shared backbone -> head(s).
+    The projection is an extra stage inside the fused stream kernel (fp32 path)."""
+
+    def __init__(self, enc_out_ch, proj_ch, backbone_dim, shared_out_ch, num_classes, use_norm=False, use_cosine=False,
+                 synchronized=True):
+        super().__init__()
+        self._build(enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized, proj_ch=proj_ch)
+
+    def forward(self, xw, xi, xm):
+        return tuple(self._streams(xw, xi, xm))
