@@ -424,6 +424,37 @@ def data_case(name):
         flat["sync_batch_y"] = b["y"].numpy()
         folds = DW.make_fixed_balanced_folds_no_overlap(sids[:3], sids[3:], n_folds=1, per_class=1, seed=43)
         flat["fold0_test"] = np.array(folds[0][1])
+        folds = DW.make_fixed_balanced_folds_no_overlap(sids[:3], sids[3:], n_folds=3, per_class=1, seed=7)
+        flat["folds3_seed7"] = np.array([[",".join(tr), ",".join(te)] for tr, te in folds])
+        # loader order: what the trainer sees over two epochs (train pass, then test pass, sharing one generator,
+        # weargait_train.py:551,573-589; make_sync_loaders/make_async_loaders :420-455)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr, te = DW.make_sync_loaders(prep, subj2label, batch_size=4, num_workers=0, seed=43)
+            for ep in range(2):
+                for nm, ld in (("train", tr), ("test", te)):
+                    ks, ys = [], []
+                    for b in ld:
+                        ks += [k[0].split("|")[0] + "|" + k[0].split("|")[2] for k in b["keys"]]; ys += b["y"].tolist()
+                    flat[f"loader_sync/{nm}_ep{ep}_keys"] = np.array(ks); flat[f"loader_sync/{nm}_ep{ep}_y"] = np.array(ys)
+                    if ep == 0 and nm == "train":
+                        for j in range(3):
+                            flat[f"loader_sync/last_batch_x{j}"] = b["xs"][j].numpy()
+            tr, te = DW.make_async_loaders(prep, subj2label, batch_size=4, num_workers=0, seed=43)
+            for ep in range(1, 3):
+                tr.dataset.reseed(43 + ep)                                  # weargait_train.py:574-575
+                for nm, ld in (("train", tr), ("test", te)):
+                    ks = {m: [] for m in ds.modalities}; ys = {m: [] for m in ds.modalities}
+                    for b in ld:
+                        for m in ds.modalities:
+                            ks[m] += list(b["keys"][m]); ys[m] += b["y"][m].tolist()
+                    for m in ds.modalities:
+                        flat[f"loader_async/{nm}_ep{ep}_keys/{m}"] = np.array(ks[m])
+                        flat[f"loader_async/{nm}_ep{ep}_y/{m}"] = np.array(ys[m])
+                    if ep == 1 and nm == "train":
+                        for m in ds.modalities:
+                            flat[f"loader_async/last_batch/{m}"] = b[m].numpy()
     # A5 FoG clip prep
     for i, (T_, Ts) in enumerate([(57, 300), (101, 426), (140, 500)]):
         pose = rng.random((T_, 7, 3)) * 5 - 1; sens = rng.standard_normal((Ts, 6))

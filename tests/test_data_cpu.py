@@ -1,0 +1,131 @@
+"""Host-side integer logic of the device-resident data path (dataloader_weargait.py of the package) against the
+golden vectors dumped from the reference's own prepare_split / datasets / loaders.  No GPU: the stores hold dummy CPU
+frames, only the window tables, index maps, permutations and the loader ORDER are checked."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+MODS = ("walkway", "insole", "imu")
+
+
+@pytest.fixture(scope="module")
+def dl():
+    import gaitk
+    return gaitk.dataloader_weargait
+
+
+@pytest.fixture(scope="module")
+def fold(dl):
+    g = load_golden("data_path")
+    sids = [str(s) for s in g["sids"]]
+    train = [str(s) for s in g["train"]]; test = [str(s) for s in g["test"]]
+
+    def store(subs, m):
+        keys, starts, base = [], [], 0
+        for s in subs:
+            n = g[f"raw/{s}/{m}"].shape[0]
+            for wid, s0, _ in dl.window_indices(n, 64, 64):
+                keys.append(f"{s}|{m}|{wid}"); starts.append(base + s0)
+            base += n
+        return dl.WindowStore(m, torch.zeros(base, dl.MODALITY_DIM[m]), 64, keys, np.array(starts, dtype=np.int64))
+
+    prep = {"train_stores": {m: store(train, m) for m in MODS}, "test_stores": {m: store(test, m) for m in MODS}}
+    prep["train_sync"] = dl.build_sync_pairs(prep["train_stores"], train, MODS)
+    prep["test_sync"] = dl.build_sync_pairs(prep["test_stores"], test, MODS)
+    return g, sids, prep, dl.build_subj2label(sids[:3], sids[3:])
+
+
+def test_window_indices_match_reference(dl):
+    g = load_golden("data_path")
+    for i, (n, w, h) in enumerate(g["win_cases"]):
+        got = np.array(dl.window_indices(int(n), int(w), int(h)), dtype=np.int64).reshape(-1, 3)
+        assert np.array_equal(got, g[f"win_{i}"]), (n, w, h)
+
+
+def test_store_keys_and_sync_pairs_match_reference(fold):
+    g, sids, prep, _ = fold
+    for split in ("train", "test"):
+        for m in MODS:
+            assert sorted(prep[f"{split}_stores"][m].keys()) == [str(k) for k in g[f"{split}_keys/{m}"]]
+        got = [[p[0].split("|")[0], p[0].split("|")[2]] for p in prep[f"{split}_sync"]]
+        assert got == [[str(a), str(b)] for a, b in g[f"{split}_sync"]]
+    # the subject with fewer insole frames than one window is dropped from the sync map
+    assert not any(p[0].startswith(sids[4] + "|") for p in prep["train_sync"])
+
+
+def test_async_permutations_match_reference(fold, dl):
+    g, sids, prep, s2l = fold
+    ds = dl.WearGaitMultiAsyncDataset(prep["train_stores"], MODS, s2l, seed=43)
+    assert np.array_equal(np.array([ds._perms[m] for m in MODS]), g["async_perm_seed43"])
+    ds.reseed(44)
+    assert np.array_equal(np.array([ds._perms[m] for m in MODS]), g["async_perm_seed44"])
+    ks = ds.keys_of([3])
+    assert [ks[m][0] for m in MODS] == [str(k) for k in g["async_item3_keys"]]
+    _, ys = ds.tables()
+    assert [int(y[3]) for y in ys] == [int(v) for v in g["async_item3_y"]]
+
+
+def test_folds_match_reference(fold, dl):
+    g, sids, _, _ = fold
+    f = dl.make_fixed_balanced_folds_no_overlap(sids[:3], sids[3:], n_folds=1, per_class=1, seed=43)
+    assert f[0][1] == [str(s) for s in g["fold0_test"]]
+    f3 = dl.make_fixed_balanced_folds_no_overlap(sids[:3], sids[3:], n_folds=3, per_class=1, seed=7)
+    assert [[",".join(tr), ",".join(te)] for tr, te in f3] == [[str(a), str(b)] for a, b in g["folds3_seed7"]]
+
+
+def test_sync_loader_order_matches_reference(fold, dl):
+    """two epochs of (train pass, test pass) on loaders that share one generator, as the trainer runs them"""
+    g, sids, prep, s2l = fold
+    tr, te = dl.make_sync_loaders(prep, s2l, batch_size=4, num_workers=0, seed=43)
+    assert len(tr) == 3 and len(te) == 2
+    for ep in range(2):
+        for nm, ld in (("train", tr), ("test", te)):
+            ks, ys = [], []
+            for ib in ld.index_batches():
+                ks += [p[0].split("|")[0] + "|" + p[0].split("|")[2] for p in ld.dataset.keys_of(ib.index.tolist())]
+                ys += ib.ys[0].tolist()
+                # the three streams of a sync batch are the same windows
+                for j, m in enumerate(MODS):
+                    st = ld.dataset.stores[j]
+                    want = [st.starts[st.position(p[j])] for p in ld.dataset.keys_of(ib.index.tolist())]
+                    assert ib.win_start[j].tolist() == want
+            assert ks == [str(k) for k in g[f"loader_sync/{nm}_ep{ep}_keys"]], (ep, nm)
+            assert ys == g[f"loader_sync/{nm}_ep{ep}_y"].tolist()
+
+
+def test_async_loader_order_matches_reference(fold, dl):
+    g, sids, prep, s2l = fold
+    tr, te = dl.make_async_loaders(prep, s2l, batch_size=4, num_workers=0, seed=43)
+    for ep in range(1, 3):
+        tr.dataset.reseed(43 + ep)
+        for nm, ld in (("train", tr), ("test", te)):
+            ks = {m: [] for m in MODS}; ys = {m: [] for m in MODS}
+            for ib in ld.index_batches():
+                kk = ld.dataset.keys_of(ib.index.tolist())
+                for j, m in enumerate(MODS):
+                    ks[m] += kk[m]; ys[m] += ib.ys[j].tolist()
+                    st = ld.dataset.stores[m]
+                    assert ib.win_start[j].tolist() == [st.starts[st.position(k)] for k in kk[m]]
+            for m in MODS:
+                assert ks[m] == [str(k) for k in g[f"loader_async/{nm}_ep{ep}_keys/{m}"]], (ep, nm, m)
+                assert ys[m] == g[f"loader_async/{nm}_ep{ep}_y/{m}"].tolist()
+
+
+def test_loader_order_equals_a_real_torch_dataloader(dl):
+    """independent of the golden file: same generator protocol as torch.utils.data.DataLoader on this torch version"""
+    n = 37
+    class DS(torch.utils.data.Dataset):
+        def __len__(self): return n
+        def __getitem__(self, i): return i
+    st = dl.WindowStore("walkway", torch.zeros(n * 64, 2), 64, [f"s|walkway|{i}" for i in range(n)], np.arange(n) * 64)
+    pairs = [(f"s|walkway|{i}",) for i in range(n)]
+    ds = dl.WearGaitSyncDataset((st,), pairs, {"s": 1})
+    g1 = torch.Generator().manual_seed(5); g2 = torch.Generator().manual_seed(5)
+    ref = torch.utils.data.DataLoader(DS(), batch_size=8, shuffle=True, num_workers=0, generator=g1)
+    ref_te = torch.utils.data.DataLoader(DS(), batch_size=8, shuffle=False, num_workers=0, generator=g1)
+    mine = dl.DeviceLoader(ds, 8, True, g2); mine_te = dl.DeviceLoader(ds, 8, False, g2)
+    for _ in range(3):
+        assert [b.tolist() for b in ref] == [ib.index.tolist() for ib in mine.index_batches()]
+        assert [b.tolist() for b in ref_te] == [ib.index.tolist() for ib in mine_te.index_batches()]

@@ -684,3 +684,97 @@ def test_fusion_baseline_fused_step_matches_reference(gk, name):
         for k, v in ref.items():
             if k.startswith("param:"):
                 close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-resident fold preparation + loaders (package dataloader_weargait.py vs the reference's prepare_split/loaders)
+def _golden_frames(g):
+    sids = [str(s) for s in g["sids"]]
+    return sids, {s: {m: g[f"raw/{s}/{m}"] for m in ("walkway", "insole", "imu")} for s in sids}
+
+
+def test_device_prepare_split_matches_reference(gk):
+    dl = gk.dataloader_weargait
+    g = load_golden("data_path")
+    sids, frames = _golden_frames(g)
+    train = [str(s) for s in g["train"]]; test = [str(s) for s in g["test"]]
+    prep = dl.prepare_split(train, test, frames=frames, win=64, hop=64)
+    mean = torch.cat([prep["stats"]["insole"][0], prep["stats"]["imu"][0]]).cpu().numpy()
+    std = torch.cat([prep["stats"]["insole"][1], prep["stats"]["imu"][1]]).cpu().numpy()
+    np.testing.assert_allclose(mean, g["stat_mean"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(std, g["stat_std"], rtol=1e-12)
+    n_checked = 0
+    for split in ("train", "test"):
+        assert [[p[0].split("|")[0], p[0].split("|")[2]] for p in prep[f"{split}_sync"]] == [[str(a), str(b)] for a, b in g[f"{split}_sync"]]
+        for m in ("walkway", "insole", "imu"):
+            st = prep[f"{split}_stores"][m]
+            keys = [str(k) for k in g[f"{split}_keys/{m}"]]
+            assert sorted(st.keys()) == keys
+            if not keys:
+                continue
+            pos = torch.tensor([st.starts[st.position(k)] for k in keys], dtype=torch.int64, device="cuda")
+            win = st.gather(pos).cpu().numpy()
+            ref = g[f"{split}_win/{m}"].astype(np.float32)
+            # statistics agree to ~1e-13 relative, so a float32 z-score may differ from the reference's by one ulp on a
+            # rounding tie; everything else is bit exact
+            same = win == ref
+            assert same.mean() > 0.9999 and np.allclose(win, ref, rtol=2e-7, atol=1e-12), (split, m, same.mean())
+            n_checked += len(keys)
+    assert n_checked > 50
+
+
+def test_device_loaders_yield_reference_batches(gk):
+    dl = gk.dataloader_weargait
+    g = load_golden("data_path")
+    sids, frames = _golden_frames(g)
+    prep = dl.prepare_split([str(s) for s in g["train"]], [str(s) for s in g["test"]], frames=frames)
+    s2l = dl.build_subj2label(sids[:3], sids[3:])
+    tr, te = dl.make_sync_loaders(prep, s2l, batch_size=4, num_workers=0, seed=43, with_keys=True)
+    last = None; ks = []
+    for b in tr:
+        last = b; ks += [k[0].split("|")[0] + "|" + k[0].split("|")[2] for k in b["keys"]]
+    assert ks == [str(k) for k in g["loader_sync/train_ep0_keys"]]
+    for j in range(3):
+        np.testing.assert_allclose(last["xs"][j].cpu().numpy(), g[f"loader_sync/last_batch_x{j}"], rtol=2e-7, atol=1e-12)
+    assert last["y"].dtype == torch.int64 and last["xs"][1].shape == (4, 64, 13)
+    tr, te = dl.make_async_loaders(prep, s2l, batch_size=4, num_workers=0, seed=43, with_keys=True)
+    tr.dataset.reseed(44)
+    for b in tr:
+        last = b
+    for m in ("walkway", "insole", "imu"):
+        np.testing.assert_allclose(last[m].cpu().numpy(), g[f"loader_async/last_batch/{m}"], rtol=2e-7, atol=1e-12)
+        assert last["y"][m].shape == (1,)
+
+
+def test_resident_fold_training_equals_dense_batch_training(gk):
+    """An epoch trained from index batches (windows read from the resident stores by the stream kernels) ends with the
+    same parameters as the same epoch trained from the dense batches the loaders hand to an unmodified trainer loop."""
+    dl = gk.dataloader_weargait
+    rng = np.random.default_rng(3)
+    sids = [f"pd{i}" for i in range(4)] + [f"hc{i}" for i in range(4)]
+    frames = {}
+    for i, s in enumerate(sids):
+        n = int(rng.integers(700, 1500))
+        frames[s] = {"walkway": rng.random((n, 2)), "insole": rng.standard_normal((n - int(rng.integers(0, 70)), 13)) * 3 + 1,
+                     "imu": rng.standard_normal((n - int(rng.integers(0, 70)), 24)) * (2 if i < 4 else 1)}
+    frames[sids[1]]["insole"][5:40, 3] = np.nan
+    s2l = dl.build_subj2label(sids[:4], sids[4:])
+    prep = dl.prepare_split(sids[:3] + sids[4:7], [sids[3], sids[7]], frames=frames)
+    params = []
+    for mode in ("dense", "index"):
+        torch.manual_seed(0)
+        m = gk.WearGaitThreeModal().cuda().set_window(64)      # index batches carry no window length
+        crit = [gk.GCLLoss(cls_num_list=[40, 60], m=0.2, s=25.0, noise_mul=0.0) for _ in range(3)]
+        step = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, dtype=gk.DTYPE_F32)
+        tr, _ = dl.make_sync_loaders(prep, s2l, batch_size=16, seed=43)
+        n = 0
+        for ep in range(2):
+            if mode == "dense":
+                for b in tr:
+                    step.step(b["xs"], [b["y"]] * 3); n += 1
+            else:
+                for ib in tr.index_batches():
+                    step.step(ib.frames, ib.ys, win_start=ib.win_start); n += 1
+        assert n == 2 * len(tr) and n >= 10
+        params.append(m.flat_params().detach().clone())
+    assert torch.equal(params[0], params[1])

@@ -8,6 +8,7 @@ from .feature_encoder import MultiModalMultiTaskModel, SensorModalityModel, Skel
 from .classification_losses import GCLLoss, LDAMLoss, CrossEntropyLoss, make_loss_desc, criterion_spec
 from .multitask_weighting import CAGrad
 from .fused_step import FusedTrainStep
+from . import dataloader_weargait
 from . import dist
 
 __all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "LateFusion3", "SharedLatent3", "MultiModalMultiTaskModel", "SensorModalityModel", "SkelModalityModel",
