@@ -210,6 +210,12 @@ int gaitk_normalize_frames(const double* frames, int64_t N, int D, const double*
  * (dataloader_weargait.py:359-372). */
 int gaitk_window_gather(const float* frames, int D, const int64_t* win_start, int B, int T,
                         int enabled, float* out, void* stream);
+/* relaxed-input evaluation, all seven MASK_COMBOS (weargait_train.py:49-57) from one set of logits: replaces the
+ * seven forward_batch_masked + softmax-ensemble passes of eval_with_mask / eval_all_masks (:360-433) and the per-stream
+ * accuracies of eval_one_epoch (:322-350).  logits[3] are (B, K) fp32 device pointers, y[3] int64 labels per stream
+ * (the same pointer three times in sync mode).  counts (device int32[10]) is ACCUMULATED into: [0..6] hits of the
+ * softmax-mean ensemble per mask in MASK_COMBOS order (against y[0]), [7..9] argmax hits per stream. */
+int gaitk_mask_eval(const float* const* logits, const int64_t* const* y, int B, int K, int32_t* counts, void* stream);
 /* FoG clip preparation (dataloader_fbg_fog.py:24-37,93-113): centre on joint 0, per-clip
  * per-coordinate min-max, zero pad / trim to T_out; fp64 (L, J, 3) clips concatenated in `poses`
  * with clip_start[i], clip_len[i]; out (n_clips, T_out, J*3) fp32. */

@@ -778,3 +778,67 @@ def test_resident_fold_training_equals_dense_batch_training(gk):
         assert n == 2 * len(tr) and n >= 10
         params.append(m.flat_params().detach().clone())
     assert torch.equal(params[0], params[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# relaxed-input evaluation: seven masks from one forward pass (package evaluation.py vs eval_with_mask goldens)
+def test_all_masks_from_one_pass_match_reference(gk):
+    g = load_golden("wg_masks")
+    state = {k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}
+    xs = [torch.from_numpy(g[f"x{j}"]) for j in range(3)]; y = torch.from_numpy(g["y"])
+    names = [str(n) for n in g["mask_names"]]
+    assert names == list(gk.MASK_COMBOS) and [tuple(bool(u) for u in r) for r in g["mask_table"]] == list(gk.MASK_COMBOS.values())
+    m = gk.WearGaitThreeModal(synchronized=True); m.load_state_dict(state, strict=True); m = m.cuda()
+    batch = {"xs": xs, "y": y}
+    table = gk.eval_all_masks(m, [batch], False)
+    for i, nm in enumerate(names):
+        assert abs(table[nm] - float(g["acc_sync"][i])) < 1e-9, (nm, table[nm], g["acc_sync"][i])
+        assert abs(gk.eval_with_mask(m, [batch], False, nm) - float(g["acc_sync"][i])) < 1e-9
+    am = gk.WearGaitThreeModal(synchronized=False)
+    am.load_state_dict({k: v for k, v in state.items() if not k.startswith("_shared")}, strict=True); am = am.cuda()
+    abatch = {"walkway": xs[0], "insole": xs[1], "imu": xs[2], "y": {"walkway": y, "insole": y, "imu": y}}
+    atab = gk.eval_all_masks(am, [abatch, abatch], True)
+    for i, nm in enumerate(names):
+        assert abs(atab[nm]["macro_enabled"] - float(g["acc_async"][i])) < 1e-9, (nm, atab[nm])
+        assert set(atab[nm]) == {s for s, u in zip(("walkway", "insole", "imu"), gk.MASK_COMBOS[nm]) if u} | {"macro_enabled"}
+    # the kernel's ensembles against torch ops on the same logits, larger batch, three classes
+    torch.manual_seed(0)
+    lg = [torch.randn(5000, 3, device="cuda") * 2 for _ in range(3)]; yy = torch.randint(0, 3, (5000,), device="cuda")
+    cnt = torch.zeros(10, dtype=torch.int32, device="cuda")
+    import ctypes as C
+    arr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
+    gk._lib.check(gk.lib().gaitk_mask_eval(arr(lg), arr([yy] * 3), 5000, 3, cnt.data_ptr(), gk._lib.stream_handle()))
+    cnt = cnt.cpu().numpy()
+    for i, mask in enumerate(gk.MASK_COMBOS.values()):
+        probs = [torch.softmax(l, 1) for l, u in zip(lg, mask) if u]
+        assert int(((sum(probs) / len(probs)).argmax(1) == yy).sum()) == cnt[i]
+    for s in range(3):
+        assert int((lg[s].argmax(1) == yy).sum()) == cnt[7 + s]
+
+
+def test_eval_one_epoch_on_resident_loader_matches_dense_torch(gk):
+    dl = gk.dataloader_weargait
+    rng = np.random.default_rng(5)
+    sids = [f"pd{i}" for i in range(3)] + [f"hc{i}" for i in range(3)]
+    frames = {s: {"walkway": rng.random((400, 2)), "insole": rng.standard_normal((380, 13)), "imu": rng.standard_normal((390, 24)) * (2 if i < 3 else 1)}
+              for i, s in enumerate(sids)}
+    s2l = dl.build_subj2label(sids[:3], sids[3:])
+    prep = dl.prepare_split(sids[:2] + sids[3:5], [sids[2], sids[5]], frames=frames)
+    torch.manual_seed(1)
+    m = gk.WearGaitThreeModal().cuda()
+    crit = [gk.CrossEntropyLoss() for _ in range(3)]
+    _, te = dl.make_sync_loaders(prep, s2l, batch_size=4, seed=1)
+    loss, acc, ens = gk.eval_one_epoch(m, te, False, crit)
+    # the reference's loop (weargait_train.py:322-350) with torch ops on the dense batches of the same loader
+    _, te2 = dl.make_sync_loaders(prep, s2l, batch_size=4, seed=1)
+    n = 0; ls = np.zeros(3); ac = np.zeros(3); corr = tot = 0
+    with torch.no_grad():
+        for b in te2:
+            lg = m(*b["xs"]); y = b["y"]
+            ls += np.array([float(torch.nn.functional.cross_entropy(l, y)) for l in lg])
+            ac += np.array([(l.argmax(1) == y).float().mean().item() * 100 for l in lg]); n += 1
+            p = sum(torch.softmax(l, 1) for l in lg) / 3.0
+            corr += int((p.argmax(1) == y).sum()); tot += y.numel()
+    np.testing.assert_allclose(loss, ls / n, rtol=2e-6)
+    np.testing.assert_allclose(acc, ac / n, rtol=1e-12)
+    assert abs(ens - 100.0 * corr / tot) < 1e-9

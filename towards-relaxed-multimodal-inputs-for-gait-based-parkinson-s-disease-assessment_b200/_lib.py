@@ -25,7 +25,7 @@ EXPORTS = [
     "gaitk_stream_in_len", "gaitk_stream_geometry", "gaitk_workspace_bytes", "gaitk_forward", "gaitk_loss", "gaitk_backward",
     "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_cagrad", "gaitk_cagrad_solve_host",
     "gaitk_sgd", "gaitk_window_indices", "gaitk_stats_accumulate", "gaitk_stats_finalize",
-    "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
+    "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_mask_eval", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
     "gaitk_umma_selftest",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.gaitk_stats_finalize.argtypes = [vp, i32, vp, vp, vp]; L.gaitk_stats_finalize.restype = i32
     L.gaitk_normalize_frames.argtypes = [vp, i64, i32, vp, vp, vp, vp]; L.gaitk_normalize_frames.restype = i32
     L.gaitk_window_gather.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]; L.gaitk_window_gather.restype = i32
+    L.gaitk_mask_eval.argtypes = [pp, pp, i32, i32, vp, vp]; L.gaitk_mask_eval.restype = i32
     L.gaitk_fog_prepare_pose.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]; L.gaitk_fog_prepare_pose.restype = i32
     L.gaitk_fog_prepare_sensor.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]; L.gaitk_fog_prepare_sensor.restype = i32
     L.gaitk_umma_selftest.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp]; L.gaitk_umma_selftest.restype = i32

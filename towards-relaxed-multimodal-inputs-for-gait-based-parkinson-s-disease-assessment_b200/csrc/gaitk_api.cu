@@ -784,6 +784,75 @@ extern "C" int gaitk_window_gather(const float* frames, int D, const int64_t* wi
     LAUNCH_CHECK();
     return 0;
 }
+// Relaxed-input evaluation: all seven presence masks of MASK_COMBOS (weargait_train.py:49-57) from ONE set of logits.
+// eval_with_mask (:391-433) only ever reads the logits of the ENABLED streams, and a stream's logits depend on its own
+// input alone, so the zero-filled forward passes of the reference add nothing: per window the three softmax rows are
+// formed once, the seven ensembles (mean of the enabled rows, first-index argmax) are compared with the label, and the
+// per-stream argmax hits (the async flavour and eval_one_epoch :322-350) are counted alongside.
+// counts[0..6] = ensemble hits per mask in MASK_COMBOS order, counts[7..9] = per-stream hits (own labels), int32.
+__global__ void __launch_bounds__(256) mask_eval_kernel(const float* __restrict__ lw, const float* __restrict__ li,
+                                                        const float* __restrict__ lm, const long long* __restrict__ yw,
+                                                        const long long* __restrict__ yi, const long long* __restrict__ ym,
+                                                        int B, int K, int* __restrict__ counts) {
+    int c[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) c[i] = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const float* L[3] = {lw + (size_t)b * K, li + (size_t)b * K, lm + (size_t)b * K};
+        const long long Y[3] = {yw[b], yi[b], ym[b]};
+        float p[3][KMAX];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            float z[KMAX], mx = -INFINITY; int am = 0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) { z[k] = k < K ? L[s][k] : -INFINITY; if (z[k] > mx) { mx = z[k]; am = k; } }
+            c[7 + s] += (am == (int)Y[s]);
+            float e[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) e[k] = k < K ? expf(z[k] - mx) : 0.f;
+            // butterfly order of ATen's warp softmax (persistent_softmax.cuh): (e0 + e2) + (e1 + e3)
+            const float sum = K <= 2 ? e[0] + e[1] : (e[0] + e[2]) + (e[1] + e[3]);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) p[s][k] = e[k] / sum;
+        }
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            // MASK_COMBOS order: W, I, M, W+I, W+M, I+M, W+I+M
+            const bool uw = (m == 0 || m == 3 || m == 4 || m == 6), ui = (m == 1 || m == 3 || m == 5 || m == 6),
+                       um = (m == 2 || m == 4 || m == 5 || m == 6);
+            const int n = (int)uw + (int)ui + (int)um;
+            const float inv = 1.0f / (float)n;                 // tensor / python-int on CUDA multiplies by the reciprocal
+            float best = -INFINITY; int am = 0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (k >= K) break;
+                float a = 0.f;                                  // sum(probs): 0 + p_first + ...
+                if (uw) a = a + p[0][k];
+                if (ui) a = a + p[1][k];
+                if (um) a = a + p[2][k];
+                a = a * inv;
+                if (a > best) { best = a; am = k; }
+            }
+            c[m] += (am == (int)Y[0]);                          // sync: one label per window (yw)
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        int v = c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(counts + i, v);
+    }
+}
+extern "C" int gaitk_mask_eval(const float* const* logits, const int64_t* const* y, int B, int K, int32_t* counts, void* stream) {
+    if (!logits || !y || !counts || !logits[0] || !logits[1] || !logits[2] || !y[0] || !y[1] || !y[2])
+        return fail(GAITK_E_BADARG, "null argument");
+    if (K < 2 || K > KMAX) return fail(GAITK_E_SHAPE, "num_classes must be in [2,%d]", KMAX);
+    if (B <= 0) return 0;
+    mask_eval_kernel<<<std::min((B + 255) / 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(
+        logits[0], logits[1], logits[2], (const long long*)y[0], (const long long*)y[1], (const long long*)y[2], B, K, counts);
+    LAUNCH_CHECK();
+    return 0;
+}
 // FoG pose clip: subtract joint 0, per-coordinate min-max over (L, J) of the CENTRED clip, pad/trim to T_out.
 // One CTA per clip.  fp64 arithmetic in the reference's operation order, then cast to fp32.
 __global__ void __launch_bounds__(128) fog_pose_kernel(const double* __restrict__ poses, const long long* __restrict__ cs,
