@@ -14,6 +14,9 @@
 #include "../../include/gaitk.h"
 #include "stream_kernel.cuh"
 #include "stream_kernel_tc.cuh"
+#ifdef GAITK_WITH_TC2        // two-threads-per-row experiment (slower): opt-in build
+#include "stream_kernel_tc2.cuh"
+#endif
 #include "update_kernels.cuh"
 #include "umma_selftest.cuh"
 
@@ -41,6 +44,7 @@ struct StreamPlan {
     StreamKernelFn fn;
     SmemPlan sp; GradOff go; int NGP; size_t smem_bytes; int ctas_per_sm;
     StreamKernelTcFn fn_tc; TcPlan tp; size_t smem_tc; int ctas_tc;      // tensor-core variant (nullptr when unavailable)
+    int tc_threads;                                                    // 128 (one thread per row) or 256 (two per row)
     int p_w1, p_b1, p_w2, p_b2, p_wsk, p_bsk, p_lng, p_lnb, p_hng, p_hnb, p_hw, p_hb, p_wp, p_bp;   // param indices (-1 = none)
     int nseg; Seg seg[MAX_SEG];
 };
@@ -93,11 +97,11 @@ static StreamKernelFn find_kernel(const KernelKey& k) {
     return nullptr;
 }
 
-template <class Cfg> static StreamKernelTcFn kfn_tc() { return &stream_kernel_tc<Cfg>; }
-static StreamKernelTcFn find_kernel_tc(const KernelKey& k) {
+template <class Cfg, bool FX> static StreamKernelTcFn kfn_tc() { return &stream_kernel_tc<Cfg, FX>; }
+static StreamKernelTcFn find_kernel_tc(const KernelKey& k, bool fixed_geometry) {
 #define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
     if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
-        return kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
+        return fixed_geometry ? kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>, true>() : kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>, false>();
     GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
     GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
     GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
@@ -105,9 +109,24 @@ static StreamKernelTcFn find_kernel_tc(const KernelKey& k) {
     return nullptr;
 }
 
+#ifdef GAITK_WITH_TC2
+template <class Cfg> static StreamKernelTcFn kfn_tc2() { return &stream_kernel_tc2<Cfg>; }
+// two-threads-per-row variant: compile-time geometry T = 64, W = 2, bdim = 8
+static StreamKernelTcFn find_kernel_tc2(const KernelKey& k) {
+#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
+        return kfn_tc2<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
+    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
+    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
+    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
+#undef GK_CASE
+    return nullptr;
+}
+#endif
+
 static int round_rb(int rows, int halo) {          // rows per chunk, == 1 (mod 8): conflict-free chunk planes
     int rb = rows + 2 * halo;
-    while (rb % 8 != 1) ++rb;
+    while (rb % 8 != GAITK_RB_MOD) ++rb;
     return rb;
 }
 
@@ -167,7 +186,8 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     if (occ < 1) return fail(GAITK_E_SHAPE, "stream %d kernel does not fit on an SM", s);
     sp.ctas_per_sm = occ;
     // ---- tensor-core variant (tcgen05 + mma.sync, tf32): full 128-row tiles only
-    sp.fn_tc = (sp.rows == NT && T_in == T && sp.PROJ == 0) ? find_kernel_tc(key) : nullptr;
+    const bool fixed_geo = T == 64 && sp.W == 2 && d.backbone_dim == 8;     // WearGait default window: compile-time geometry
+    sp.fn_tc = (sp.rows == NT && T_in == T && sp.PROJ == 0) ? find_kernel_tc(key, fixed_geo) : nullptr;
     if (sp.fn_tc) {
         auto ev = [](int x) { return (x + 1) / 2 * 2; };
         const int KX = ev(CI4), KH = ev(H4), KC = ev(C4), KS = ev(S4);
@@ -192,6 +212,14 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
         sp.smem_tc = (size_t)q * sizeof(float);
         if (sp.smem_tc > 200 * 1024) sp.fn_tc = nullptr;
     }
+    sp.tc_threads = NT;
+#ifdef GAITK_WITH_TC2
+    if (sp.fn_tc && fixed_geo) {
+        const char* v = getenv("GAITK_TC_VARIANT");          // 2 = two threads per row (stream_kernel_tc2)
+        StreamKernelTcFn f2 = (v && atoi(v) == 2) ? find_kernel_tc2(key) : nullptr;
+        if (f2) { sp.fn_tc = f2; sp.tc_threads = NT2; }
+    }
+#endif
     if (sp.fn_tc) {
         CUDA_TRY(cudaFuncSetAttribute((const void*)sp.fn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_tc));
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate TMEM although
@@ -200,7 +228,7 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
         // memory / TMEM columns and let the hardware co-schedule what it can.
         cudaFuncAttributes fa;
         CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)sp.fn_tc));
-        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NT;
+        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * sp.tc_threads;
         const size_t smem_per_cta = sp.smem_tc + fa.sharedSizeBytes + 1024;
         int by_regs = 65536 / std::max(regs_per_cta, 1), by_smem = (int)((size_t)227 * 1024 / smem_per_cta);
         int occ2 = std::max(1, std::min(std::min(by_regs, by_smem), 16));      // 32 TMEM columns per CTA -> <= 16
@@ -398,7 +426,7 @@ static void fill_args(const gaitk_plan* pl, int s, const float* params, const fl
 
 static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int grid, cudaStream_t st, int dtype = GAITK_DTYPE_F32) {
     const StreamPlan& sp = pl->st[s];
-    if (dtype == GAITK_DTYPE_TF32) sp.fn_tc<<<grid, NT, sp.smem_tc, st>>>(a, sp.tp);
+    if (dtype == GAITK_DTYPE_TF32) sp.fn_tc<<<grid, sp.tc_threads, sp.smem_tc, st>>>(a, sp.tp);
     else sp.fn<<<grid, NT, sp.smem_bytes, st>>>(a, sp.sp);
     LAUNCH_CHECK();
     return 0;

@@ -26,6 +26,12 @@ namespace gaitk {
 constexpr int NT = 128;        // threads per CTA == rows per slot
 constexpr int KMAX = 4;        // GAITK_MAX_CLASSES
 constexpr int WMAX = 4;        // windows per tile (one warp each in the head phase)
+// rows per chunk plane (RB) modulo 8.  Row-wise float4 accesses are conflict-free for any RB (a quarter warp reads
+// 128 contiguous bytes); the mma.sync fragment loads of the weight gradients read lanes (g, t) -> channel g, row t:
+// chunk g >> 2, word 4 t + (g & 3), so the two chunks must sit 16 banks apart: 4 RB = 16 (mod 32)  <=>  RB = 4 (mod 8).
+#ifndef GAITK_RB_MOD
+#define GAITK_RB_MOD 4
+#endif
 
 enum EncKind { ENC_CONV_GELU_LN = 0, ENC_INSOLE = 1, ENC_LINEAR_LN_RELU = 2, ENC_CONV_POOL = 3 };
 enum Mode { MODE_FWD = 0, MODE_FUSED = 1, MODE_BWD_EXT = 2 };

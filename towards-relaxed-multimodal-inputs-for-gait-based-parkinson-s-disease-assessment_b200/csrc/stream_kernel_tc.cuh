@@ -96,6 +96,67 @@ struct WgradMma {
             }
         }
     }
+    // same, over the K (row) range [r_begin, r_end) only: two thread groups may split the rows of a tile
+    __device__ __forceinline__ void accumulate_range(const float* __restrict__ in, int RBin, const float* __restrict__ dout, int RBout,
+                                                     int halo, int W, int r_begin, int r_end, int wrp, int lane) {
+        const int g = lane >> 2, t = lane & 3;
+        int aoff[MTW][2];
+#pragma unroll
+        for (int i = 0; i < MTW; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int j = (wrp + 4 * i) * 16 + g + 8 * h;
+                if (j >= J) j = 0;
+                const int tap = j / CIP, ci = j - tap * CIP;
+                aoff[i][h] = ((ci >> 2) * RBin + halo + (tap - KT / 2) * W + t) * 4 + (ci & 3);
+            }
+        }
+        int boff[NT8];
+#pragma unroll
+        for (int n = 0; n < NT8; ++n) { const int c = n * 8 + g; boff[n] = ((c >> 2) * RBout + halo + t) * 4 + (c & 3); }
+#pragma unroll 4
+        for (int r0 = r_begin; r0 < r_end; r0 += 8) {
+            uint32_t b[NT8][2];
+#pragma unroll
+            for (int n = 0; n < NT8; ++n) {
+                b[n][0] = __float_as_uint(dout[boff[n] + r0 * 4]);
+                b[n][1] = __float_as_uint(dout[boff[n] + r0 * 4 + 16]);
+            }
+#pragma unroll
+            for (int i = 0; i < MTW; ++i) {
+                if (wrp + 4 * i >= MT) continue;
+                uint32_t a[4];
+                a[0] = __float_as_uint(in[aoff[i][0] + r0 * 4]);
+                a[1] = __float_as_uint(in[aoff[i][1] + r0 * 4]);
+                a[2] = __float_as_uint(in[aoff[i][0] + r0 * 4 + 16]);
+                a[3] = __float_as_uint(in[aoff[i][1] + r0 * 4 + 16]);
+#pragma unroll
+                for (int n = 0; n < NT8; ++n) mma_sync_tf32(acc[i][n], a, b[n]);
+            }
+        }
+    }
+    // flush with an optional read-modify-write (second partial sum of a K-split tile)
+    __device__ __forceinline__ void flush_acc(float* dst, float* dst2, int CIN, int COUT, int wrp, int lane, bool add) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int i = 0; i < MTW; ++i) {
+            if (wrp + 4 * i >= MT) continue;
+#pragma unroll
+            for (int n = 0; n < NT8; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = (wrp + 4 * i) * 16 + g + 8 * (e >> 1), co = n * 8 + 2 * t + (e & 1);
+                    if (j >= J) continue;
+                    const int tap = j / CIP, ci = j - tap * CIP;
+                    if (ci < CIN && co < COUT) {
+                        float* q = dst + (co * CIN + ci) * KT + tap;
+                        const float v = add ? *q + acc[i][n][e] : acc[i][n][e];
+                        *q = v;
+                        if (dst2 && tap == KT / 2) dst2[co * CIN + ci] = v;
+                    }
+                }
+        }
+    }
     // each tile has exactly one owner: write straight into the PyTorch weight layout (CO, CI, KT);
     // dst2 (optional) receives the centre tap as (CO, CI, 1) -- the folded 1x1 skip
     __device__ __forceinline__ void flush(float* dst, float* dst2, int CIN, int COUT, int wrp, int lane) {
@@ -179,7 +240,14 @@ __device__ __forceinline__ void tmem_row(uint32_t taddr, float (&v)[N]) {
 #define PH(i) do { } while (0)
 #endif
 
-template <class Cfg>
+// FX: the WearGait default geometry (T = 64 -> W = 2 windows per 128-row tile, 8 pooling bins) as compile-time
+// constants, so that shared-memory addressing folds into immediates; FX = false keeps every 128-row geometry.
+__host__ __device__ constexpr int tc_round_rb(int rows, int halo) {
+    int rb = rows + 2 * halo;
+    while (rb % 8 != GAITK_RB_MOD) ++rb;
+    return rb;
+}
+template <class Cfg, bool FX>
 __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(const StreamArgs A, const TcPlan SP) {
     extern __shared__ __align__(1024) float sm[];
     __shared__ uint64_t bar, ldbar;
@@ -201,8 +269,10 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     constexpr int NC = ((C + 15) / 16) * 16, NS = ((S + 15) / 16) * 16, NH = ((H + 15) / 16) * 16;
     constexpr int O1 = (ENC == ENC_INSOLE) ? H4 * 4 : CP;
     static_assert(N1 <= 32 && NC <= 32 && NS <= 32 && (H == 0 || NH <= 32), "accumulator fits 32 TMEM columns");
-    const int W = A.W, halo = A.halo, RB = A.RB, rows = A.rows, T = A.T;
-    const int K = A.K, NF = A.NF, bdim = A.bdim;
+    constexpr int FX_HALO = (KT1 / 2 > 1 ? KT1 / 2 : 1) * 2;
+    const int W = FX ? 2 : A.W, halo = FX ? FX_HALO : A.halo, RB = FX ? tc_round_rb(128, FX_HALO) : A.RB;
+    const int rows = FX ? 128 : A.rows, T = FX ? 64 : A.T;
+    const int K = A.K, NF = A.NF, bdim = FX ? 8 : A.bdim;
     const bool train = A.mode != MODE_FWD;
 
     float* Xs = sm + SP.X; float* HAs = sm + SP.HA; float* D1s = sm + SP.D1; float* XHs = sm + SP.XH;
@@ -300,7 +370,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     float* Ps = sm + SP.P;
     hc.Ps = pool_shfl ? Ps : nullptr;
     hc.ys = nullptr;
-    const int logW = 31 - __clz(W);                      // W is a power of two (planner)
+    const int logW = FX ? 1 : 31 - __clz(W);             // W is a power of two (planner)
     g_w1.zero(); g_w2.zero(); g_wb.zero();
 #pragma unroll
     for (int i = 0; i < O1; ++i) g_b1[i] = 0.f;

@@ -85,6 +85,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // TMEM -> registers: this thread's lane (row), N consecutive fp32 columns starting at taddr
+__device__ __forceinline__ void ld_x2(uint32_t taddr, float* v) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1);
+}
 __device__ __forceinline__ void ld_x4(uint32_t taddr, float* v) {
     uint32_t r0, r1, r2, r3;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
