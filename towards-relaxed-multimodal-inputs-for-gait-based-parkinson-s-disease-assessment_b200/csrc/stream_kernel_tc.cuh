@@ -438,22 +438,25 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         if (!A.zero_input) {
             umma::mbar_wait(&ldbar, ldphase); ldphase ^= 1u;
             PH(0);
-            if constexpr (CIN % 4 == 0) {
-                const int pw4 = per_win / 4;
-                for (int e = tid; e < W * pw4; e += NT) {
-                    const int w = (e >= pw4) + (e >= 2 * pw4) + (e >= 3 * pw4), rem = e - w * pw4;               // W <= 4
-                    const int t = rem / (CIN / 4), c4 = rem - t * (CIN / 4);
-                    float4 v = reinterpret_cast<const float4*>(STGs)[e];
-                    if (win0 + w >= A.B) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    reinterpret_cast<float4*>(Xs)[c4 * RB + halo + (t << logW) + w] =
-                        make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
-                }
-            } else {
-                for (int e = tid; e < W * per_win; e += NT) {
-                    const int w = (e >= per_win) + (e >= 2 * per_win) + (e >= 3 * per_win), rem = e - w * per_win;   // W <= 4
-                    const int t = rem / CIN, c = rem - t * CIN;
-                    const float v = (win0 + w < A.B) ? STGs[e] : 0.f;
-                    Xs[((c >> 2) * RB + halo + (t << logW) + w) * 4 + (c & 3)] = umma::to_tf32(v);
+            // thread r converts row r = (t, w): CIN consecutive floats of window w's frame t -> one 16-byte word per chunk
+            {
+                const int t = r >> logW, w = r & (W - 1);
+                const bool live = win0 + w < A.B;
+                const float* src = STGs + w * per_win + t * CIN;
+                float4* dst = reinterpret_cast<float4*>(Xs) + (halo + r);
+                if constexpr (CIN % 4 == 0) {
+#pragma unroll
+                    for (int c4 = 0; c4 < CI4; ++c4) {
+                        float4 v = reinterpret_cast<const float4*>(src)[c4];
+                        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        dst[c4 * RB] = make_float4(umma::to_tf32(v.x), umma::to_tf32(v.y), umma::to_tf32(v.z), umma::to_tf32(v.w));
+                    }
+                } else {
+                    float v[CI4 * 4];
+#pragma unroll
+                    for (int c = 0; c < CI4 * 4; ++c) v[c] = (c < CIN && live) ? umma::to_tf32(src[c]) : 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < CI4; ++c4) dst[c4 * RB] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
                 }
             }
         }
