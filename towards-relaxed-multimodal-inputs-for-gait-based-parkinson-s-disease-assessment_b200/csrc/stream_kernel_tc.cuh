@@ -42,11 +42,19 @@ __device__ __forceinline__ void mma_sync_tf32(float (&d)[4], const uint32_t (&a)
 
 // dW[j][n] += sum_r IN[r + (tap - KT/2) W][ci] * DOUT[r][n],   j = tap * CIP + ci.
 // 16 x 8 output tiles; M-tile mt belongs to warp mt % 4 (all its N-tiles), accumulators persist in registers.
+// The MMA's row / column indices are PERMUTED so that a lane's fragment elements are adjacent in shared memory and
+// come in with one 64-bit load each (half the load instructions of the natural order):
+//   MMA row m of M-tile mt      <->  j  = 16 mt + 2 (m & 7) + (m >> 3)     (a0, a1 = channels ci, ci + 1 of one row)
+//   MMA col n of N-tile 2p + q  <->  co = 16 p + 2 n + q                    (b of tiles 2p, 2p+1 = channels co, co + 1)
+//   a last unpaired N-tile i    <->  co = 8 i + n
+// Half-warp wavefronts of these loads touch 32 distinct banks for RB = 4 (mod 8).
 template <int KT, int CIP, int NOUT>
 struct WgradMma {
+    static_assert(CIP % 4 == 0 && NOUT % 8 == 0, "");
     static constexpr int J = KT * CIP;
     static constexpr int MT = (J + 15) / 16;
     static constexpr int NT8 = NOUT / 8;
+    static constexpr int NP = NT8 / 2;                // paired N-tiles
     static constexpr int MTW = (MT + 3) / 4;
     float acc[MTW][NT8][4];
 
@@ -58,84 +66,54 @@ struct WgradMma {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.f;
     }
-    __device__ __forceinline__ void accumulate(const float* __restrict__ in, int RBin, const float* __restrict__ dout, int RBout,
-                                               int halo, int W, int rows, int wrp, int lane) {
-        const int g = lane >> 2, t = lane & 3;
-        int aoff[MTW][2];
-#pragma unroll
-        for (int i = 0; i < MTW; ++i) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                int j = (wrp + 4 * i) * 16 + g + 8 * h;
-                if (j >= J) j = 0;                               // padding rows of the last tile: results ignored
-                const int tap = j / CIP, ci = j - tap * CIP;
-                aoff[i][h] = ((ci >> 2) * RBin + halo + (tap - KT / 2) * W + t) * 4 + (ci & 3);
-            }
-        }
-        int boff[NT8];
-#pragma unroll
-        for (int n = 0; n < NT8; ++n) { const int c = n * 8 + g; boff[n] = ((c >> 2) * RBout + halo + t) * 4 + (c & 3); }
-#pragma unroll 4
-        for (int r0 = 0; r0 < rows; r0 += 8) {
-            uint32_t b[NT8][2];
-#pragma unroll
-            for (int n = 0; n < NT8; ++n) {
-                b[n][0] = __float_as_uint(dout[boff[n] + r0 * 4]);
-                b[n][1] = __float_as_uint(dout[boff[n] + r0 * 4 + 16]);
-            }
-#pragma unroll
-            for (int i = 0; i < MTW; ++i) {
-                if (wrp + 4 * i >= MT) continue;
-                uint32_t a[4];
-                a[0] = __float_as_uint(in[aoff[i][0] + r0 * 4]);
-                a[1] = __float_as_uint(in[aoff[i][1] + r0 * 4]);
-                a[2] = __float_as_uint(in[aoff[i][0] + r0 * 4 + 16]);
-                a[3] = __float_as_uint(in[aoff[i][1] + r0 * 4 + 16]);
-#pragma unroll
-                for (int n = 0; n < NT8; ++n) mma_sync_tf32(acc[i][n], a, b[n]);
-            }
-        }
-    }
-    // same, over the K (row) range [r_begin, r_end) only: two thread groups may split the rows of a tile
+    // rows [r_begin, r_end) of the tile (two thread groups may split the K range)
     __device__ __forceinline__ void accumulate_range(const float* __restrict__ in, int RBin, const float* __restrict__ dout, int RBout,
                                                      int halo, int W, int r_begin, int r_end, int wrp, int lane) {
         const int g = lane >> 2, t = lane & 3;
-        int aoff[MTW][2];
+        int aoff[MTW];
 #pragma unroll
         for (int i = 0; i < MTW; ++i) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                int j = (wrp + 4 * i) * 16 + g + 8 * h;
-                if (j >= J) j = 0;
-                const int tap = j / CIP, ci = j - tap * CIP;
-                aoff[i][h] = ((ci >> 2) * RBin + halo + (tap - KT / 2) * W + t) * 4 + (ci & 3);
-            }
+            int j = (wrp + 4 * i) * 16 + 2 * g;
+            if (j >= J) j = 0;                                   // padding rows of the last tile: results ignored
+            const int tap = j / CIP, ci = j - tap * CIP;
+            aoff[i] = ((ci >> 2) * RBin + halo + (tap - KT / 2) * W + t) * 4 + (ci & 3);
         }
-        int boff[NT8];
+        int boff[NP + 1];
 #pragma unroll
-        for (int n = 0; n < NT8; ++n) { const int c = n * 8 + g; boff[n] = ((c >> 2) * RBout + halo + t) * 4 + (c & 3); }
+        for (int p = 0; p < NP; ++p) { const int c = 16 * p + 2 * g; boff[p] = ((c >> 2) * RBout + halo + t) * 4 + (c & 3); }
+        { const int c = 8 * (NT8 - 1) + g; boff[NP] = ((c >> 2) * RBout + halo + t) * 4 + (c & 3); }
 #pragma unroll 4
         for (int r0 = r_begin; r0 < r_end; r0 += 8) {
             uint32_t b[NT8][2];
 #pragma unroll
-            for (int n = 0; n < NT8; ++n) {
-                b[n][0] = __float_as_uint(dout[boff[n] + r0 * 4]);
-                b[n][1] = __float_as_uint(dout[boff[n] + r0 * 4 + 16]);
+            for (int p = 0; p < NP; ++p) {
+                const float2 lo = *reinterpret_cast<const float2*>(dout + boff[p] + r0 * 4);
+                const float2 hi = *reinterpret_cast<const float2*>(dout + boff[p] + r0 * 4 + 16);
+                b[2 * p][0] = __float_as_uint(lo.x); b[2 * p + 1][0] = __float_as_uint(lo.y);
+                b[2 * p][1] = __float_as_uint(hi.x); b[2 * p + 1][1] = __float_as_uint(hi.y);
+            }
+            if constexpr (NT8 % 2 == 1) {
+                b[NT8 - 1][0] = __float_as_uint(dout[boff[NP] + r0 * 4]);
+                b[NT8 - 1][1] = __float_as_uint(dout[boff[NP] + r0 * 4 + 16]);
             }
 #pragma unroll
             for (int i = 0; i < MTW; ++i) {
                 if (wrp + 4 * i >= MT) continue;
-                uint32_t a[4];
-                a[0] = __float_as_uint(in[aoff[i][0] + r0 * 4]);
-                a[1] = __float_as_uint(in[aoff[i][1] + r0 * 4]);
-                a[2] = __float_as_uint(in[aoff[i][0] + r0 * 4 + 16]);
-                a[3] = __float_as_uint(in[aoff[i][1] + r0 * 4 + 16]);
+                const float2 lo = *reinterpret_cast<const float2*>(in + aoff[i] + r0 * 4);
+                const float2 hi = *reinterpret_cast<const float2*>(in + aoff[i] + r0 * 4 + 16);
+                const uint32_t a[4] = {__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(hi.x), __float_as_uint(hi.y)};
 #pragma unroll
                 for (int n = 0; n < NT8; ++n) mma_sync_tf32(acc[i][n], a, b[n]);
             }
         }
     }
-    // flush with an optional read-modify-write (second partial sum of a K-split tile)
+    __device__ __forceinline__ void accumulate(const float* __restrict__ in, int RBin, const float* __restrict__ dout, int RBout,
+                                               int halo, int W, int rows, int wrp, int lane) {
+        accumulate_range(in, RBin, dout, RBout, halo, W, 0, rows, wrp, lane);
+    }
+    // each tile has exactly one owner: write straight into the PyTorch weight layout (CO, CI, KT);
+    // dst2 (optional) receives the centre tap as (CO, CI, 1) -- the folded 1x1 skip; `add` = read-modify-write
+    // (second partial sum of a K-split tile)
     __device__ __forceinline__ void flush_acc(float* dst, float* dst2, int CIN, int COUT, int wrp, int lane, bool add) {
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -145,7 +123,8 @@ struct WgradMma {
             for (int n = 0; n < NT8; ++n)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int j = (wrp + 4 * i) * 16 + g + 8 * (e >> 1), co = n * 8 + 2 * t + (e & 1);
+                    const int j = (wrp + 4 * i) * 16 + 2 * g + (e >> 1), col = 2 * t + (e & 1);
+                    const int co = n < 2 * NP ? 16 * (n >> 1) + 2 * col + (n & 1) : 8 * n + col;
                     if (j >= J) continue;
                     const int tap = j / CIP, ci = j - tap * CIP;
                     if (ci < CIN && co < COUT) {
@@ -157,26 +136,8 @@ struct WgradMma {
                 }
         }
     }
-    // each tile has exactly one owner: write straight into the PyTorch weight layout (CO, CI, KT);
-    // dst2 (optional) receives the centre tap as (CO, CI, 1) -- the folded 1x1 skip
     __device__ __forceinline__ void flush(float* dst, float* dst2, int CIN, int COUT, int wrp, int lane) {
-        const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-        for (int i = 0; i < MTW; ++i) {
-            if (wrp + 4 * i >= MT) continue;
-#pragma unroll
-            for (int n = 0; n < NT8; ++n)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = (wrp + 4 * i) * 16 + g + 8 * (e >> 1), co = n * 8 + 2 * t + (e & 1);
-                    if (j >= J) continue;
-                    const int tap = j / CIP, ci = j - tap * CIP;
-                    if (ci < CIN && co < COUT) {
-                        dst[(co * CIN + ci) * KT + tap] = acc[i][n][e];
-                        if (dst2 && tap == KT / 2) dst2[co * CIN + ci] = acc[i][n][e];
-                    }
-                }
-        }
+        flush_acc(dst, dst2, CIN, COUT, wrp, lane, false);
     }
 };
 
