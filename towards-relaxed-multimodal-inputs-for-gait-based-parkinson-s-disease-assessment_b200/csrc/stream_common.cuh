@@ -183,6 +183,7 @@ struct HeadCtx {
     const float *hws, *hbs, *hngs, *hnbs, *inws; float* DPs;
     const float* Ps;      // optional pre-pooled features [W][NF] (already divided by the bin size)
     const int* ys;        // optional labels of the tile's windows, prefetched to shared memory
+    float inv_bin;        // > 0: every pooling bin has 1 / inv_bin frames (a power of two: the product is exact)
 };
 
 template <int NFL, int SC>
@@ -202,6 +203,8 @@ struct HeadState {
         for (int i = 0; i < NFL; ++i) { g_hng[i] = 0.f; g_hnb[i] = 0.f; }
     }
 
+    // FAST: MUFU exp / log in the loss (tensor-core path; the fp32 path keeps libdevice's expf / logf)
+    template <bool FAST = false>
     __device__ __forceinline__ void run(const StreamArgs& A, const HeadCtx& c, int w_, int lane, int win0, bool train, float inv_denom) {
             const int wi = win0 + w_; const int K = A.K, NF = A.NF;
             float f[NFL], xn[NFL], xh[NFL];
@@ -274,8 +277,8 @@ struct HeadState {
                         }
                         float se = 0.f;
 #pragma unroll
-                        for (int k = 0; k < KMAX; ++k) if (k < K) se += expf(zz[k] - mx);
-                        const float lse = mx + logf(se);
+                        for (int k = 0; k < KMAX; ++k) if (k < K) se += FAST ? __expf(zz[k] - mx) : expf(zz[k] - mx);
+                        const float lse = mx + (FAST ? __logf(se) : logf(se));
                         float zy = 0.f, wy = 0.f;
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) if (k < K && k == y) { zy = zz[k]; wy = A.cls_w[k]; }
@@ -283,7 +286,7 @@ struct HeadState {
                         acc_correct += (am == y) ? 1.f : 0.f;
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) if (k < K)
-                            dl[k] = A.scale * wy * inv_denom * (expf(zz[k] - lse) - (k == y ? 1.f : 0.f));
+                            dl[k] = A.scale * wy * inv_denom * ((FAST ? __expf(zz[k] - lse) : expf(zz[k] - lse)) - (k == y ? 1.f : 0.f));
                     } else {
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) if (k < K) dl[k] = A.dlogits_ext[(size_t)wi * K + k];
@@ -348,7 +351,7 @@ struct HeadState {
 #pragma unroll
                 for (int i = 0; i < NFL; ++i) {
                     const int j = lane + 32 * i, b = j / SC;
-                    c.DPs[w_ * NF + j] = df[i] / (float)(c.bin_e[b] - c.bin_s[b]);
+                    c.DPs[w_ * NF + j] = c.inv_bin > 0.f ? df[i] * c.inv_bin : df[i] / (float)(c.bin_e[b] - c.bin_s[b]);
                 }
             }
             }

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     float g_b1[O1], g_b2[ENC == ENC_INSOLE ? CP : 4], g_lng[CP], g_lnb[CP], g_bb[S];
     HeadState<NFL, S> head; head.zero();
     HeadCtx hc; hc.Zs = Zs; hc.RB = RB; hc.halo = halo; hc.W = W; hc.S = S; hc.bin_s = bins; hc.bin_e = bins + bdim;
-    hc.hws = hws; hc.hbs = hbs; hc.hngs = hngs; hc.hnbs = hnbs; hc.inws = inws; hc.DPs = DPs; hc.Ps = nullptr; hc.ys = nullptr;
+    hc.hws = hws; hc.hbs = hbs; hc.hngs = hngs; hc.hnbs = hnbs; hc.inws = inws; hc.DPs = DPs; hc.Ps = nullptr; hc.ys = nullptr; hc.inv_bin = 0.f;
     if (train) {
         g_w1.zero(); g_w2.zero(); g_wb.zero(); g_wp.zero();
 #pragma unroll

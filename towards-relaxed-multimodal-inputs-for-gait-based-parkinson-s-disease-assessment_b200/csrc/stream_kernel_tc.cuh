@@ -48,15 +48,19 @@ __device__ __forceinline__ void mma_sync_tf32(float (&d)[4], const uint32_t (&a)
 //   MMA col n of N-tile 2p + q  <->  co = 16 p + 2 n + q                    (b of tiles 2p, 2p+1 = channels co, co + 1)
 //   a last unpaired N-tile i    <->  co = 8 i + n
 // Half-warp wavefronts of these loads touch 32 distinct banks for RB = 4 (mod 8).
-template <int KT, int CIP, int NOUT>
+// Work split over the four warps of a row tile: KS = false -> M-tile mt belongs to warp mt % 4 (all rows);
+// KS = true -> every warp holds ALL M-tiles for its quarter of the rows (balanced when MT is not a multiple of 4, and
+// the B fragments are shared by all M-tiles), the four partial sums being added in warp order at the final flush.
+template <int KT, int CIP, int NOUT, bool KS = false>
 struct WgradMma {
     static_assert(CIP % 4 == 0 && NOUT % 8 == 0, "");
     static constexpr int J = KT * CIP;
     static constexpr int MT = (J + 15) / 16;
     static constexpr int NT8 = NOUT / 8;
     static constexpr int NP = NT8 / 2;                // paired N-tiles
-    static constexpr int MTW = (MT + 3) / 4;
+    static constexpr int MTW = KS ? MT : (MT + 3) / 4;
     float acc[MTW][NT8][4];
+    __device__ __forceinline__ static int tile_of(int i, int wrp) { return KS ? i : wrp + 4 * i; }
 
     __device__ __forceinline__ void zero() {
 #pragma unroll
@@ -73,7 +77,7 @@ struct WgradMma {
         int aoff[MTW];
 #pragma unroll
         for (int i = 0; i < MTW; ++i) {
-            int j = (wrp + 4 * i) * 16 + 2 * g;
+            int j = tile_of(i, wrp) * 16 + 2 * g;
             if (j >= J) j = 0;                                   // padding rows of the last tile: results ignored
             const int tap = j / CIP, ci = j - tap * CIP;
             aoff[i] = ((ci >> 2) * RBin + halo + (tap - KT / 2) * W + t) * 4 + (ci & 3);
@@ -98,7 +102,7 @@ struct WgradMma {
             }
 #pragma unroll
             for (int i = 0; i < MTW; ++i) {
-                if (wrp + 4 * i >= MT) continue;
+                if (tile_of(i, wrp) >= MT) continue;
                 const float2 lo = *reinterpret_cast<const float2*>(in + aoff[i] + r0 * 4);
                 const float2 hi = *reinterpret_cast<const float2*>(in + aoff[i] + r0 * 4 + 16);
                 const uint32_t a[4] = {__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(hi.x), __float_as_uint(hi.y)};
@@ -109,7 +113,8 @@ struct WgradMma {
     }
     __device__ __forceinline__ void accumulate(const float* __restrict__ in, int RBin, const float* __restrict__ dout, int RBout,
                                                int halo, int W, int rows, int wrp, int lane) {
-        accumulate_range(in, RBin, dout, RBout, halo, W, 0, rows, wrp, lane);
+        if constexpr (KS) accumulate_range(in, RBin, dout, RBout, halo, W, wrp * (rows / 4), (wrp + 1) * (rows / 4), wrp, lane);
+        else accumulate_range(in, RBin, dout, RBout, halo, W, 0, rows, wrp, lane);
     }
     // each tile has exactly one owner: write straight into the PyTorch weight layout (CO, CI, KT);
     // dst2 (optional) receives the centre tap as (CO, CI, 1) -- the folded 1x1 skip; `add` = read-modify-write
@@ -118,12 +123,12 @@ struct WgradMma {
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
         for (int i = 0; i < MTW; ++i) {
-            if (wrp + 4 * i >= MT) continue;
+            if (tile_of(i, wrp) >= MT) continue;
 #pragma unroll
             for (int n = 0; n < NT8; ++n)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int j = (wrp + 4 * i) * 16 + 2 * g + (e >> 1), col = 2 * t + (e & 1);
+                    const int j = tile_of(i, wrp) * 16 + 2 * g + (e >> 1), col = 2 * t + (e & 1);
                     const int co = n < 2 * NP ? 16 * (n >> 1) + 2 * col + (n & 1) : 8 * n + col;
                     if (j >= J) continue;
                     const int tap = j / CIP, ci = j - tap * CIP;
@@ -136,8 +141,16 @@ struct WgradMma {
                 }
         }
     }
+    // called by all threads of the CTA (KS: four ordered passes separated by CTA barriers)
     __device__ __forceinline__ void flush(float* dst, float* dst2, int CIN, int COUT, int wrp, int lane) {
-        flush_acc(dst, dst2, CIN, COUT, wrp, lane, false);
+        if constexpr (KS) {
+            for (int pass = 0; pass < 4; ++pass) {
+                if (wrp == pass) flush_acc(dst, dst2, CIN, COUT, wrp, lane, pass > 0);
+                __syncthreads();
+            }
+        } else {
+            flush_acc(dst, dst2, CIN, COUT, wrp, lane, false);
+        }
     }
 };
 
@@ -318,9 +331,11 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     __syncthreads();
 
     // ---- persistent accumulators
-    WgradMma<KT1, CI4 * 4, (O1 + 7) / 8 * 8> g_w1;
+    // row-split (balanced) weight gradients where the register budget allows it
+    constexpr bool KS_W1 = (ENC != ENC_INSOLE) && CIN <= 4, KS_WB = KS_W1;       // walkway only: the IMU stream is at its register cap
+    WgradMma<KT1, CI4 * 4, (O1 + 7) / 8 * 8, KS_W1> g_w1;
     WgradMma<3, (ENC == ENC_INSOLE ? H4 * 4 : 4), (ENC == ENC_INSOLE ? NC : 8)> g_w2;
-    WgradMma<3, CP, NS> g_wb;
+    WgradMma<3, CP, NS, KS_WB> g_wb;
     float g_b1[O1], g_b2[ENC == ENC_INSOLE ? CP : 4], g_lng[CP], g_lnb[CP], g_bb[S];
     HeadState<NFL, S> head; head.zero();
     HeadCtx hc; hc.Zs = Zs; hc.RB = RB; hc.halo = halo; hc.W = W; hc.S = S; hc.bin_s = bin_s; hc.bin_e = bin_e;
@@ -331,6 +346,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     float* Ps = sm + SP.P;
     hc.Ps = pool_shfl ? Ps : nullptr;
     hc.ys = nullptr;
+    hc.inv_bin = (binsz > 0 && (binsz & (binsz - 1)) == 0) ? 1.0f / (float)binsz : 0.f;
     const int logW = FX ? 1 : 31 - __clz(W);             // W is a power of two (planner)
     g_w1.zero(); g_w2.zero(); g_wb.zero();
 #pragma unroll
@@ -491,7 +507,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         __syncthreads();
         PH(9);
         // ================= pool + head + loss (warp per window)
-        if (wrp < W) head.run(A, hc, wrp, lane, win0, train, inv_denom);
+        if (wrp < W) head.template run<true>(A, hc, wrp, lane, win0, train, inv_denom);
         if (!train) { if (has_next) prefetch(tile + (int)gridDim.x); __syncthreads(); continue; }
         PH(10);
         __syncthreads();

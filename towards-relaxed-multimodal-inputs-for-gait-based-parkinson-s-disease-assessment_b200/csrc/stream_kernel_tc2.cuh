@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NT2, Tc2MinBlocks<Cfg>::value) stream_kernel_t
     HeadState<NFL, S> head; head.zero();
     HeadCtx hc; hc.Zs = Zs; hc.RB = RB; hc.halo = halo; hc.W = W; hc.S = S; hc.bin_s = bin_s; hc.bin_e = bin_e;
     hc.hws = hws; hc.hbs = hbs; hc.hngs = hngs; hc.hnbs = hnbs; hc.inws = inws; hc.DPs = DPs;
-    hc.Ps = Ps; hc.ys = nullptr;
+    hc.Ps = Ps; hc.ys = nullptr; hc.inv_bin = 0.f;
     g_w1.zero(); g_w2.zero(); g_wb.zero();
 #pragma unroll
     for (int i = 0; i < ((ENC == ENC_INSOLE) ? MH::NH : MC::NH); ++i) g_b1[i] = 0.f;
