@@ -218,7 +218,7 @@ def run_gpu(args):
     dtype_id = gaitk.DTYPE_TF32 if wl["dtype"] == "tf32" else gaitk.DTYPE_F32
     step = gaitk.FusedTrainStep(model, crit, cagrad_c=wl["cagrad_c"], max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
                                 private_mult=wl["private_mult"], process_group=None if world > 1 else False, dtype=dtype_id,
-                                use_graph=bool(args.graph) and world == 1)
+                                use_graph=bool(args.graph))
     NBUF = len(host)
     devb = [([x.to(dev) for x in xs], [y.to(dev) for y in ys]) for xs, ys in host]
     # global label vectors (all ranks' labels; cheap) fix the weighted-mean denominators
@@ -338,11 +338,24 @@ def run_gpu(args):
         alg = B * (dims[s_][0] * dims[s_][1] * 4 + 8)
         ach = alg / (per_stream[dom] * 1e-3) / 1e9
         kname = "stream_kernel_tc" if wl["dtype"] == "tf32" else "stream_kernel"
+        # DRAM traffic / tensor-pipe utilisation of the same kernel from the committed `ncu --set full` capture
+        # (profiles/r1_ncu_full_final.json, made by scratch/ncu_summary.py); per launch, scaled to this batch
+        traffic = tensor_pct = None; traffic_src = None
+        sig = {"walkway": "StreamCfg<0, 2,", "insole": "StreamCfg<1, 13,", "imu": "StreamCfg<0, 24,"}.get(dom)
+        prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_final.json")
+        if sig and wl["dtype"] == "tf32" and os.path.exists(prof):
+            for nm, rec in json.load(open(prof)).items():
+                if kname + "<" in nm and sig in nm and rec.get("dram_bytes_read") is not None:
+                    traffic = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * B / rec["batch"]
+                    tensor_pct = rec.get("tensor_pipe_pct_of_peak"); traffic_src = "profiles/r1_ncu_full_final.json (ncu --set full, B=%d)" % rec["batch"]
         roof = {"bound": "hbm", "kernel": f"{kname}<{dom}> (fused fwd+loss+bwd)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "tensor_pipe_pct_of_peak": tensor_pct, "peak_source": peak_src,
                 "ms_per_launch": per_stream[dom], "algorithmic_bytes_per_launch": alg,
-                "note": "issue/latency-bound, not HBM-bound (DESIGN.md 3.1); the timed launch also contains the small reduce "
-                        "kernel and the single-CTA update kernel; ncu: DRAM read == algorithmic bytes (profiles/)",
+                "note": "issue/latency-bound, not HBM-bound (DESIGN.md 3.1): DRAM traffic equals the algorithmic bytes (inputs are "
+                        "read once), what limits the kernel is the thread-local epilogue / weight-gradient work between the "
+                        "MMAs at 8-12 warps per SM; the timed launch also contains the small reduce kernel and the "
+                        "single-CTA update kernel",
                 "per_stream_ms": per_stream,
                 "step_hbm_gbs": B * bytes_per_unit / (ms_max / args.steps * 1e-3) / 1e9}
 
@@ -361,7 +374,7 @@ def run_gpu(args):
             "config": {"workload": workload_name(B, args.workload), "parallelism": f"dp{world}", "global_batch": world * B,
                        "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
                        "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks",
-                       "cuda_graph": bool(args.graph) and world == 1},
+                       "cuda_graph": bool(args.graph)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host batch of (B,64,2)+(B,64,13)+(B,64,24) fp32 + labels copied every step (copy of batch i+1 "
                             "overlaps step i), result (loss[3], correct[3]) read back every step"},
@@ -387,7 +400,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="replay the step as one CUDA graph (single-GPU)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step (kernels + the NCCL all-reduce when data-parallel) as one CUDA graph")
     ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog"],
                     help="default = BASELINE.json configs[1]; the others are extra report lines")
     ap.add_argument("--dtype", default="tf32", choices=["f32", "tf32"], help="contraction arithmetic of the stream kernels")

@@ -76,7 +76,7 @@ class FusedTrainStep:
     def _step_impl(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], *, enabled: Sequence[bool] = None,
              tasks: Sequence[bool] = None, ys_global: Optional[Sequence[torch.Tensor]] = None,
              win_start: Optional[Sequence[torch.Tensor]] = None, logits_out: Optional[Sequence] = None,
-             update: bool = True, grads_out: Optional[torch.Tensor] = None):
+             update: bool = True, grads_out: Optional[torch.Tensor] = None, part: Optional[str] = None):
         """xs[s]: (B, T_s, D_s) CUDA fp32 (or frame stores with win_start[s] int64[B]); ys[s]: int64[B].
         ys_global: label vectors of the WHOLE data-parallel batch (defaults to ys) -- they fix the
         weighted-mean denominators so that shards add up to the single-GPU step."""
@@ -110,8 +110,14 @@ class FusedTrainStep:
                                      task_mask, self.private_mult, self.consistency_lambda,
                                      None if logits_out is None else ptr_array([0 if l is None else l.data_ptr() for l in logits_out]),
                                      gbuf.data_ptr(), ws.data_ptr(), ws.numel(), self.dtype, st), "gaitk_step_grads")
+        if part == "grads":
+            return None
         if self._distributed():
             torch.distributed.all_reduce(gbuf, group=self.pg if self.pg not in (None, False) else None)
+        self._update_part(plan, flat, gbuf, mom, diag, task_mask, update, grads_out, st)
+        return self.stats()
+
+    def _update_part(self, plan, flat, gbuf, mom, diag, task_mask, update, grads_out, st):
         check(lib().gaitk_step_update(plan.handle, flat.data_ptr() if update else None, mom.data_ptr() if update else None,
                                       gbuf.data_ptr(), task_mask, self.cagrad_c, self.max_norm, self.lr, self.momentum,
                                       self.weight_decay, None if grads_out is None else grads_out.data_ptr(),
@@ -120,31 +126,50 @@ class FusedTrainStep:
 
     def step(self, xs, ys, **kw):
         """One fused training step.  With use_graph=True the launch sequence (denominators, stream kernels, reduces,
-        update) is captured once per distinct set of buffer addresses / options and replayed as ONE CUDA graph."""
-        if not self.use_graph or self._distributed() or kw.get("grads_out") is not None or kw.get("logits_out") is not None:
+        update) is captured once per distinct set of buffer addresses / options and replayed as ONE CUDA graph; when
+        data-parallel, as TWO graphs (gradient half, update half) around the eager NCCL all-reduce of gbuf."""
+        if not self.use_graph or kw.get("grads_out") is not None or kw.get("logits_out") is not None:
             return self._step_impl(xs, ys, **kw)
         ws = kw.get("win_start")
         if hasattr(self.model, "set_window") and (ws is None or ws[0] is None):
             self.model.set_window(xs[0].shape[1])
         def ptrs(seq):
             return None if seq is None else tuple(0 if t is None else t.data_ptr() for t in seq)
+        dist_mode = self._distributed()
         key = (ptrs(xs), ptrs(ys), ptrs(kw.get("ys_global")), ptrs(kw.get("win_start")), tuple(kw.get("enabled") or ()),
                tuple(kw.get("tasks") or ()), kw.get("update", True), xs[0].shape[0] if kw.get("win_start") is None else kw["win_start"][0].numel(),
                tuple(id(c.weight) if getattr(c, "weight", None) is not None else 0 for c in self.criterions),
-               self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c)
+               self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c, dist_mode)
         g = self._graphs.get(key)
         if g is None:
             self._step_impl(xs, ys, **kw)                      # this call's step, eagerly (also allocates buffers / workspace)
             torch.cuda.synchronize()
             # capture records the launch sequence without executing it; later calls replay it
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_impl(xs, ys, **kw)
             if len(self._graphs) > 64:
                 self._graphs.clear()
-            self._graphs[key] = g
+            if not dist_mode:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._step_impl(xs, ys, **kw)
+                self._graphs[key] = (g1, None)
+            else:
+                plan = self.model.plan(); flat = self.model.flat_params()
+                gbuf, denom, diag, mom = self._buffers(plan)
+                n = len(xs); tasks = kw.get("tasks")
+                task_mask = ((1 << n) - 1) if tasks is None else sum(1 << i for i, e in enumerate(tasks) if e)
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._step_impl(xs, ys, part="grads", **kw)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    self._update_part(plan, flat, gbuf, mom, diag, task_mask, kw.get("update", True), None, stream_handle())
+                self._graphs[key] = (g1, g2)
             return self.stats()
-        g.replay()
+        g1, g2 = g
+        g1.replay()
+        if g2 is not None:
+            torch.distributed.all_reduce(self._gbuf, group=self.pg if self.pg not in (None, False) else None)
+            g2.replay()
         return self.stats()
 
     # ------------------------------------------------------------------ end-to-end (host batch) entries
