@@ -476,6 +476,38 @@ def test_tf32_path_large_batch_vs_fp32_path(gk):
     assert relerr(b[3], a[3]) < 4e-3, relerr(b[3], a[3])          # all final gradients (private ones dominate)
 
 
+@pytest.mark.parametrize("T", [32, 128])
+def test_tf32_path_other_window_lengths(gk, T):
+    """Window lengths other than the default use the runtime-geometry instantiation of the tensor-core kernel
+    (T = 32 -> 4 windows per 128-row tile, T = 128 -> 1): same properties as the default geometry."""
+    import gait_oracle as O
+    torch.manual_seed(6)
+    m = gk.WearGaitThreeModal().cuda()
+    B = 1031
+    xs, y = O.synth_weargait_batch(B, T=T, seed=12)
+    xs = [dev(x) for x in xs]; y = dev(y)
+    crit = [gk.GCLLoss(cls_num_list=[400, 600], m=0.2, s=25, noise_mul=0.0) for _ in range(3)]
+    plan = m.set_window(T).plan()
+    res = {}
+    for dt in (gk.DTYPE_F32, gk.DTYPE_TF32):
+        st = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, dtype=dt, process_group=False)
+        gout = torch.zeros(plan.NP, device="cuda")
+        loss, correct = st.step(xs, [y, y, y], grads_out=gout, update=False)
+        res[dt] = (loss.cpu().numpy(), correct.cpu().numpy(), st._gbuf[:3 * plan.P].cpu().numpy(), gout.cpu().numpy())
+    a, b = res[gk.DTYPE_F32], res[gk.DTYPE_TF32]
+    assert relerr(b[0], a[0]) < 1e-3
+    assert np.abs(b[1] - a[1]).max() <= 0.004 * B + 1
+    assert relerr(b[2], a[2]) < 2e-3, relerr(b[2], a[2])
+    assert relerr(b[3], a[3]) < 8e-3, relerr(b[3], a[3])
+    # and the fp32 path itself against the CPU oracle at this window length
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items() if not k.startswith("_shared") and not k.startswith("head_i") and not k.startswith("head_m")}
+    lg = O.weargait_forward(O._HeadAlias(p), *[x.cpu() for x in xs])
+    with torch.no_grad():
+        out = m(*xs)
+    for u, v in zip(out, lg):
+        close(u.cpu().numpy(), v.detach().numpy(), 2e-5, f"logits T={T}")
+
+
 def test_end_to_end_training_matches_oracle(gk):
     """30 training steps + evaluation under the 7 modality masks: fused CUDA path vs the CPU oracle on the same
     data / seeds.  north_star: end-to-end metrics within 0.5 points."""
