@@ -56,8 +56,9 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread (a 20-step
-    timed region lasts ~25 ms, too short for nvidia-smi's own loop), nvidia-smi -lms as the fallback."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~10 ms from a thread on rank 0 (a
+    20-step timed region lasts ~25 ms, too short for nvidia-smi's own loop; a faster poll on every rank competes with the
+    launching threads for the host cores), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
@@ -86,7 +87,7 @@ class ClockSampler:
                 self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.01)
 
     def start(self):
         try:
@@ -254,7 +255,7 @@ def run_gpu(args):
     dtype_id = gaitk.DTYPE_TF32 if wl["dtype"] == "tf32" else gaitk.DTYPE_F32
     step = gaitk.FusedTrainStep(model, crit, cagrad_c=wl["cagrad_c"], max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
                                 private_mult=wl["private_mult"], process_group=None if world > 1 else False, dtype=dtype_id,
-                                use_graph=bool(args.graph))
+                                use_graph=bool(args.graph), p2p=bool(args.p2p) and world > 1)
     NBUF = len(host)
     devb = [([x.to(dev) for x in xs], [y.to(dev) for y in ys]) for xs, ys in host]
     # global label vectors (all ranks' labels; cheap) fix the weighted-mean denominators
@@ -286,7 +287,9 @@ def run_gpu(args):
     for i in range(args.warmup):
         one_step(i)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
@@ -296,7 +299,7 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1)
     if l2_flush is not None:                           # subtract nothing: the flush is part of the timed loop; report it
         pass
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     loss, correct = step.stats(); loss = loss.cpu().tolist()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -410,7 +413,8 @@ def run_gpu(args):
             "config": {"workload": workload_name(B, args.workload), "parallelism": f"dp{world}", "global_batch": world * B,
                        "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
                        "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks",
-                       "cuda_graph": bool(args.graph)},
+                       "cuda_graph": bool(args.graph),
+                       "exchange": "none (1 GPU)" if world == 1 else ("gaitk_p2p_allreduce over NVLink peer memory, fused into the step graph" if args.p2p else "NCCL all_reduce of gbuf")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host batch of (B,64,2)+(B,64,13)+(B,64,24) fp32 + labels copied every step (copy of batch i+1 "
                             "overlaps step i), result (loss[3], correct[3]) read back every step"},
@@ -436,6 +440,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2p", type=int, default=1, help="data-parallel exchange by the peer-memory all-reduce kernel (0 = NCCL all_reduce)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step (kernels + the NCCL all-reduce when data-parallel) as one CUDA graph")
     ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog"],
                     help="default = BASELINE.json configs[1]; the others are extra report lines")

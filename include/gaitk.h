@@ -165,6 +165,17 @@ int64_t gaitk_gbuf_floats(const gaitk_plan* plan);
 int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_streams,
                             const gaitk_loss_desc* loss, float* denom, void* stream);
 
+/* Data-parallel exchange over NVLink peer memory, between gaitk_step_grads and gaitk_step_update (replaces the
+ * gradient all-reduce a DistributedDataParallel wrapper of the reference trainers would issue).
+ * peer_gbuf_dev / peer_flag_dev: DEVICE arrays [world] of peer-mapped pointers (e.g. from a torch symmetric-memory
+ * rendezvous): every rank's gbuf of this step's parity (gbuf is double-buffered by step parity) and every rank's flag
+ * word.  counter: local device word counting completed exchanges (zero at start; the call increments it on the
+ * stream).  The kernel publishes this rank's step number, waits for all peers, and sums the gbufs in rank order into
+ * the local gsum (gaitk_gbuf_floats floats), which gaitk_step_update then consumes.  Bit-identical on every rank.
+ * If a peer does not arrive within ~4 s the step is flagged (diag[15] = -1) instead of hanging the device. */
+int gaitk_p2p_allreduce(gaitk_plan* plan, const float* const* peer_gbuf_dev, uint32_t* const* peer_flag_dev,
+                        uint32_t* counter, int rank, int world, float* gsum, float* diag, void* stream);
+
 /* Fused training step, phase 2 (replaces CAGrad.cagrad + overwrite_grad +
  * clip_grad_norm_ multitask_weighting.py:694-729,748-759,775 and
  * torch.optim.SGD.step weargait_train.py:248,560): on-device Gram matrix, simplex

@@ -23,7 +23,7 @@ EXPORTS = [
     "gaitk_version", "gaitk_last_error", "gaitk_plan_create", "gaitk_plan_destroy", "gaitk_param_count",
     "gaitk_param_info", "gaitk_param_total", "gaitk_shared_total", "gaitk_num_streams", "gaitk_stream_in_dim",
     "gaitk_stream_in_len", "gaitk_stream_geometry", "gaitk_workspace_bytes", "gaitk_forward", "gaitk_loss", "gaitk_backward",
-    "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_cagrad", "gaitk_cagrad_solve_host",
+    "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_p2p_allreduce", "gaitk_cagrad", "gaitk_cagrad_solve_host",
     "gaitk_sgd", "gaitk_window_indices", "gaitk_stats_accumulate", "gaitk_stats_finalize",
     "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_mask_eval", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
     "gaitk_umma_selftest",
@@ -85,6 +85,7 @@ def lib():
     L.gaitk_loss_denominators.restype = i32
     L.gaitk_step_update.argtypes = [vp, vp, vp, vp, u32, f32, f32, f32, f32, f32, vp, vp, i32, vp]
     L.gaitk_step_update.restype = i32
+    L.gaitk_p2p_allreduce.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]; L.gaitk_p2p_allreduce.restype = i32
     L.gaitk_cagrad.argtypes = [vp, i32, i32, f32, f32, vp, vp, i32, vp]; L.gaitk_cagrad.restype = i32
     L.gaitk_cagrad_solve_host.argtypes = [C.POINTER(C.c_float), i32, f32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.gaitk_cagrad_solve_host.restype = i32

@@ -567,6 +567,20 @@ extern "C" int gaitk_step_update(gaitk_plan* pl, float* params, float* momentum,
     return 0;
 }
 
+extern "C" int gaitk_p2p_allreduce(gaitk_plan* pl, const float* const* peer_gbuf_dev, uint32_t* const* peer_flag_dev,
+                                   uint32_t* counter, int rank, int world, float* gsum, float* diag, void* stream) {
+    if (!pl || !peer_gbuf_dev || !peer_flag_dev || !counter || !gsum) return fail(GAITK_E_BADARG, "null argument");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(GAITK_E_BADARG, "bad rank / world size");
+    P2PArgs Q; Q.peer_gbuf = peer_gbuf_dev; Q.peer_flag = (unsigned* const*)peer_flag_dev; Q.counter = counter;
+    Q.gsum = gsum; Q.n = (int)gaitk_gbuf_floats(pl); Q.rank = rank; Q.world = world; Q.diag = diag;
+    const int grid = std::max(1, std::min(16, (Q.n + P2P_THREADS * 4 - 1) / (P2P_THREADS * 4)));
+    p2p_allreduce_kernel<<<grid, P2P_THREADS, 0, (cudaStream_t)stream>>>(Q);
+    LAUNCH_CHECK();
+    bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int gaitk_cagrad(const float* G, int P, int n_tasks, float c, float max_norm, float* shared_grad, float* diag, int solver,
                             void* stream) {
     if (!G || !shared_grad || P <= 0 || n_tasks < 1 || n_tasks > MAXT) return fail(GAITK_E_BADARG, "bad argument");

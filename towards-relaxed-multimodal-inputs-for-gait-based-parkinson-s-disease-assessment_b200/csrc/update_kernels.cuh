@@ -189,4 +189,55 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Data-parallel exchange fused with the update: one-shot all-reduce of gbuf over NVLink peer memory.
+// Every rank's gbuf lives in a symmetric allocation (the same buffer is mapped by all ranks of the node).  After its
+// reduce kernels, a rank publishes `step` in its own flag word (release, system scope); every CTA of this kernel
+// waits until all peers have published (acquire), then sums the N buffers IN RANK ORDER into the local `gsum` -- the
+// same order on every rank, so replicas stay bit-identical -- and the ordinary single-CTA update runs on gsum.  No NCCL
+// call, no host involvement; the whole step stays one CUDA graph.  gbuf is double-buffered by step parity: a rank can
+// start writing buffer (k+2)&1 only after its step-(k+1) exchange, which completes only after every peer published
+// step k+1, i.e. after every peer finished reading buffer k&1.
+struct P2PArgs {
+    const float* const* peer_gbuf;     // device array [world]: gbuf of this step's parity on every rank (peer-mapped)
+    unsigned* const* peer_flag;        // device array [world]: flag word of every rank
+    const unsigned* counter;           // local: number of completed exchanges (step = counter + 1)
+    float* gsum; int n; int rank, world; float* diag;
+};
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v;
+}
+constexpr int P2P_THREADS = 256;
+__global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_kernel(const P2PArgs Q) {
+    __shared__ int ok_s;
+    const unsigned step = *Q.counter + 1u;
+    if (threadIdx.x == 0) ok_s = 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); st_release_sys(Q.peer_flag[Q.rank], step); }
+    __syncthreads();
+    if ((int)threadIdx.x < Q.world) {
+        const unsigned* f = Q.peer_flag[threadIdx.x];
+        const long long t0 = clock64();
+        // step numbers only grow; the comparison is wrap-safe.  A peer that never arrives (crashed rank) must not hang
+        // the GPU: give up after ~4 s of SM clocks and flag the step as failed (diag[15] = -1).
+        while ((int)(ld_acquire_sys(f) - step) < 0) {
+            if (clock64() - t0 > (8ll << 30)) { ok_s = 0; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (!ok_s && Q.diag && blockIdx.x == 0 && threadIdx.x == 0) Q.diag[15] = -1.0f;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Q.n; e += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < Q.world; ++r) s += ld_relaxed_sys(Q.peer_gbuf[r] + e);
+        Q.gsum[e] = s;
+    }
+}
+__global__ void bump_counter_kernel(unsigned* counter) { *counter += 1u; }
+
 }  // namespace gaitk

@@ -27,7 +27,7 @@ class FusedTrainStep:
     def __init__(self, model: FlatParamModule, criterions: Sequence, *, cagrad_c: float, max_norm: float = 1.0,
                  lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, private_mult: float = 2.0,
                  process_group=None, consistency_lambda: float = 0.0, solver: int = _lib.SOLVER_SLSQP,
-                 dtype: int = None, use_graph: bool = False):
+                 dtype: int = None, use_graph: bool = False, p2p: bool = False):
         self.model = model; self.criterions = list(criterions)
         self.cagrad_c = float(cagrad_c); self.max_norm = float(max_norm)
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
@@ -38,6 +38,8 @@ class FusedTrainStep:
         self._pinned = {}; self._dev_in = {}
         self._copy_stream = None; self._staged = {}; self._slot_free = {}
         self.use_graph = bool(use_graph); self._graphs = {}
+        # p2p: data-parallel exchange by gaitk_p2p_allreduce over symmetric (peer-mapped) memory instead of NCCL
+        self.p2p = bool(p2p); self._p2p = None; self._red = None
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, plan):
@@ -48,7 +50,44 @@ class FusedTrainStep:
             self._diag = torch.zeros(16, dtype=torch.float32, device=dev)
         if self._mom is None or self._mom.numel() != plan.NP or self._mom.device != dev:
             self._mom = torch.zeros(plan.NP, dtype=torch.float32, device=dev)
+        if self._red is None or self._p2p is None:
+            self._red = self._gbuf
         return self._gbuf, self._denom, self._diag, self._mom
+
+    def _p2p_state(self, plan):
+        """Symmetric allocation [gbuf parity 0 | gbuf parity 1 | flag word] mapped by every rank of the group (torch
+        symmetric memory does the handle exchange), device arrays of the peers' pointers, the local exchange counter and
+        the local reduced buffer.  Collective: every rank must reach it at the same step."""
+        if self._p2p is not None:
+            return self._p2p
+        try:
+            return self._p2p_setup(plan)
+        except Exception as e:                       # no symmetric memory on this system: every rank falls back to NCCL
+            import warnings
+            warnings.warn(f"gaitk: peer-memory exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce")
+            self.p2p = False
+            return None
+
+    def _p2p_setup(self, plan):
+        import torch.distributed._symmetric_memory as symm
+        dist = torch.distributed
+        group = dist.group.WORLD if self.pg in (None, False) else self.pg
+        dev = plan.device
+        n = plan.gbuf_floats; n_pad = (n + 63) // 64 * 64
+        buf = symm.empty(2 * n_pad + 64, dtype=torch.float32, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        ptrs = [int(q) for q in hdl.buffer_ptrs]
+        st = dict(buf=buf, hdl=hdl, rank=int(hdl.rank), world=int(hdl.world_size), steps=0,
+                  gbufs=[buf[0:n], buf[n_pad:n_pad + n]],
+                  peer_gbuf=[torch.tensor([q + par * n_pad * 4 for q in ptrs], dtype=torch.int64, device=dev) for par in (0, 1)],
+                  peer_flag=torch.tensor([q + 2 * n_pad * 4 for q in ptrs], dtype=torch.int64, device=dev),
+                  counter=torch.zeros(1, dtype=torch.int32, device=dev),
+                  gsum=torch.zeros(n, dtype=torch.float32, device=dev))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                     # every rank's buffer is zeroed before anyone publishes a flag
+        self._p2p = st; self._red = st["gsum"]
+        return st
 
     def _distributed(self) -> bool:
         """process_group=False: never; a group: always; None: whenever a default group with >1 ranks exists."""
@@ -66,7 +105,7 @@ class FusedTrainStep:
     def stats(self):
         """(losses[n_streams], correct[n_streams]) device tensors of the last step."""
         plan = self.model.plan()
-        st = self._gbuf[3 * plan.P + plan.NP:]
+        st = (self._red if self._red is not None else self._gbuf)[3 * plan.P + plan.NP:]
         return st[0:plan.n_streams], st[4:4 + plan.n_streams]
 
     def diag(self):
@@ -76,7 +115,8 @@ class FusedTrainStep:
     def _step_impl(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], *, enabled: Sequence[bool] = None,
              tasks: Sequence[bool] = None, ys_global: Optional[Sequence[torch.Tensor]] = None,
              win_start: Optional[Sequence[torch.Tensor]] = None, logits_out: Optional[Sequence] = None,
-             update: bool = True, grads_out: Optional[torch.Tensor] = None, part: Optional[str] = None):
+             update: bool = True, grads_out: Optional[torch.Tensor] = None, part: Optional[str] = None,
+             par: Optional[int] = None, count: bool = True):
         """xs[s]: (B, T_s, D_s) CUDA fp32 (or frame stores with win_start[s] int64[B]); ys[s]: int64[B].
         ys_global: label vectors of the WHOLE data-parallel batch (defaults to ys) -- they fix the
         weighted-mean denominators so that shards add up to the single-GPU step."""
@@ -86,6 +126,14 @@ class FusedTrainStep:
             model.set_window(xs[0].shape[1])
         plan = model.plan(); flat = model.flat_params()
         gbuf, denom, diag, mom = self._buffers(plan)
+        p2p = self.p2p and self._distributed()
+        if p2p:
+            ps = self._p2p_state(plan)
+            p2p = ps is not None
+        if p2p:
+            par = (ps["steps"] & 1) if par is None else par
+            gbuf = ps["gbufs"][par]                     # this step's half of the symmetric buffer
+        self._red = ps["gsum"] if p2p else gbuf
         K = plan.K
         descs = (LossDesc * _lib.MAX_STREAMS)()
         offs = []
@@ -112,7 +160,14 @@ class FusedTrainStep:
                                      gbuf.data_ptr(), ws.data_ptr(), ws.numel(), self.dtype, st), "gaitk_step_grads")
         if part == "grads":
             return None
-        if self._distributed():
+        if p2p:
+            check(lib().gaitk_p2p_allreduce(plan.handle, ps["peer_gbuf"][par].data_ptr(), ps["peer_flag"].data_ptr(),
+                                            ps["counter"].data_ptr(), ps["rank"], ps["world"], ps["gsum"].data_ptr(),
+                                            diag.data_ptr(), st), "gaitk_p2p_allreduce")
+            if count:
+                ps["steps"] += 1
+            gbuf = ps["gsum"]
+        elif self._distributed():
             torch.distributed.all_reduce(gbuf, group=self.pg if self.pg not in (None, False) else None)
         self._update_part(plan, flat, gbuf, mom, diag, task_mask, update, grads_out, st)
         return self.stats()
@@ -136,10 +191,12 @@ class FusedTrainStep:
         def ptrs(seq):
             return None if seq is None else tuple(0 if t is None else t.data_ptr() for t in seq)
         dist_mode = self._distributed()
+        p2p = self.p2p and dist_mode and self._p2p_state(self.model.plan()) is not None
+        par = (self._p2p["steps"] & 1) if p2p else 0
         key = (ptrs(xs), ptrs(ys), ptrs(kw.get("ys_global")), ptrs(kw.get("win_start")), tuple(kw.get("enabled") or ()),
                tuple(kw.get("tasks") or ()), kw.get("update", True), xs[0].shape[0] if kw.get("win_start") is None else kw["win_start"][0].numel(),
                tuple(id(c.weight) if getattr(c, "weight", None) is not None else 0 for c in self.criterions),
-               self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c, dist_mode)
+               self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c, dist_mode, p2p, par)
         g = self._graphs.get(key)
         if g is None:
             self._step_impl(xs, ys, **kw)                      # this call's step, eagerly (also allocates buffers / workspace)
@@ -147,10 +204,12 @@ class FusedTrainStep:
             # capture records the launch sequence without executing it; later calls replay it
             if len(self._graphs) > 64:
                 self._graphs.clear()
-            if not dist_mode:
+            if not dist_mode or p2p:
+                # (p2p: the eager call above advanced the parity; the graph is captured for the parity of the key and
+                # will be replayed whenever that parity comes round again)
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
-                    self._step_impl(xs, ys, **kw)
+                    self._step_impl(xs, ys, par=par, count=False, **kw)
                 self._graphs[key] = (g1, None)
             else:
                 plan = self.model.plan(); flat = self.model.flat_params()
@@ -167,6 +226,8 @@ class FusedTrainStep:
             return self.stats()
         g1, g2 = g
         g1.replay()
+        if p2p:
+            self._p2p["steps"] += 1
         if g2 is not None:
             torch.distributed.all_reduce(self._gbuf, group=self.pg if self.pg not in (None, False) else None)
             g2.replay()
