@@ -40,6 +40,7 @@ extern "C" {
 #define GAITK_FAMILY_FOG      1   /* train/feature_encoder.py:149-265 MultiModalMultiTaskModel   */
 
 #define GAITK_MAX_STREAMS 3
+#define GAITK_DENOM_FLOATS 32   /* size of the `denom` device buffer: [0..3] results, the rest scratch of gaitk_loss_denominators */
 #define GAITK_MAX_CLASSES 4
 #define GAITK_MAX_PASSES  6
 
@@ -161,7 +162,8 @@ int gaitk_step_grads(gaitk_plan* plan, const float* params, const float* const* 
                      float* gbuf, void* workspace, size_t workspace_bytes, int dtype, void* stream);
 int64_t gaitk_gbuf_floats(const gaitk_plan* plan);
 
-/* sum_b w[y_b] per stream from (global) label vectors -> denom[n_streams] (device). */
+/* sum_b w[y_b] per stream from (global) label vectors -> denom[0 .. n_streams) (device).  `denom` must hold
+ * GAITK_DENOM_FLOATS floats: the tail is scratch (class histograms, tickets) zeroed by the call. */
 int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_streams,
                             const gaitk_loss_desc* loss, float* denom, void* stream);
 

@@ -18,6 +18,7 @@ MAX_STREAMS, MAX_CLASSES = 3, 4
 FAMILY_WEARGAIT, FAMILY_FOG = 0, 1
 DTYPE_F32, DTYPE_TF32 = 0, 1
 SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN = 0, 1, 2
+DENOM_FLOATS = 32           # GAITK_DENOM_FLOATS
 
 EXPORTS = [
     "gaitk_version", "gaitk_last_error", "gaitk_plan_create", "gaitk_plan_destroy", "gaitk_param_count",

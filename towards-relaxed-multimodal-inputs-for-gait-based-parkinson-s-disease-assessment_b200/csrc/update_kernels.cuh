@@ -232,9 +232,16 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_kernel(const P2PArg
     }
     __syncthreads();
     if (!ok_s && Q.diag && blockIdx.x == 0 && threadIdx.x == 0) Q.diag[15] = -1.0f;
+    // all remote loads of an element are issued before the first one is consumed (rank order is kept in the sum)
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Q.n; e += gridDim.x * blockDim.x) {
         float s = 0.f;
-        for (int r = 0; r < Q.world; ++r) s += ld_relaxed_sys(Q.peer_gbuf[r] + e);
+        for (int r0 = 0; r0 < Q.world; r0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = r0 + i < Q.world ? ld_relaxed_sys(Q.peer_gbuf[r0 + i] + e) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v[i];
+        }
         Q.gsum[e] = s;
     }
 }

@@ -46,7 +46,7 @@ class FusedTrainStep:
         dev = plan.device
         if self._gbuf is None or self._gbuf.numel() != plan.gbuf_floats or self._gbuf.device != dev:
             self._gbuf = torch.zeros(plan.gbuf_floats, dtype=torch.float32, device=dev)
-            self._denom = torch.ones(4, dtype=torch.float32, device=dev)
+            self._denom = torch.ones(_lib.DENOM_FLOATS, dtype=torch.float32, device=dev)
             self._diag = torch.zeros(16, dtype=torch.float32, device=dev)
         if self._mom is None or self._mom.numel() != plan.NP or self._mom.device != dev:
             self._mom = torch.zeros(plan.NP, dtype=torch.float32, device=dev)
