@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     constexpr int NC = ((C + 15) / 16) * 16, NS = ((S + 15) / 16) * 16, NH = ((H + 15) / 16) * 16;
     constexpr int O1 = (ENC == ENC_INSOLE) ? H4 * 4 : CP;
     static_assert(N1 <= 32 && NC <= 32 && NS <= 32 && (H == 0 || NH <= 32), "accumulator fits 32 TMEM columns");
+    static_assert(S <= 32, "ReLU mask is one 32-bit word");
     constexpr int FX_HALO = (KT1 / 2 > 1 ? KT1 / 2 : 1) * 2;
     const int W = FX ? 2 : A.W, halo = FX ? FX_HALO : A.halo, RB = FX ? tc_round_rb(128, FX_HALO) : A.RB;
     const int rows = FX ? 128 : A.rows, T = FX ? 64 : A.T;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
     const bool train = A.mode != MODE_FWD;
 
     float* Xs = sm + SP.X; float* HAs = sm + SP.HA; float* D1s = sm + SP.D1; float* XHs = sm + SP.XH;
-    float* Ds = sm + SP.D; float* Fs = sm + SP.F; float* RSTDs = sm + SP.RSTD; float* Zs = sm + SP.Z;
+    float* Ds = sm + SP.D; float* Fs = sm + SP.F; float* Zs = sm + SP.Z;
     float* w1b = sm + SP.W1B; float* b1s = sm + SP.B1; float* w2b = sm + SP.W2B; float* b2s = sm + SP.B2; float* w2d = sm + SP.W2D;
     float* lngs = sm + SP.LNG; float* lnbs = sm + SP.LNB; float* wbb = sm + SP.WBB; float* bbs = sm + SP.BB; float* wbd = sm + SP.WBD;
     float* hws = sm + SP.HW; float* hbs = sm + SP.HB; float* hngs = sm + SP.HNG; float* hnbs = sm + SP.HNB; float* inws = sm + SP.INW;
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         }
         GAITK_MMA_WAIT();
         PH(5);
+        float rstd_row = 0.f;                            // LayerNorm 1/sigma of this row, kept for the backward
         {
             float a[NC], g[CP], d[CP], xh[CP], f[CP]; float rstd;
             tmem_row<NC>(trow, a);
@@ -473,20 +475,22 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
 #pragma unroll
             for (int c = 0; c < CP; ++c) f[c] = c < C ? fmaf(xh[c], lngs[c], lnbs[c]) : 0.f;
             store_row_tf32<CP>(Fs, RB, halo, r, f);
-            if (train) { store_row<CP>(Ds, RB, halo, r, d); store_row<CP>(XHs, RB, halo, r, xh); RSTDs[r] = rstd; }
+            if (train) { store_row<CP>(Ds, RB, halo, r, d); store_row<CP>(XHs, RB, halo, r, xh); rstd_row = rstd; }
         }
         PH(6);
         // ================= shared backbone forward
         GAITK_MMA_PHASE((issue_conv_tab<3, KC, NS>(tmem, dtab[2])));
         GAITK_MMA_WAIT();
         PH(7);
+        uint32_t zmask = 0;                              // ReLU mask of this row's S backbone channels
         {
             float z[NS];
             tmem_row<NS>(trow, z);
             float zz[S];
 #pragma unroll
-            for (int s = 0; s < S; ++s) zz[s] = fmaxf(z[s] + bbs[s], 0.f);
-            store_row<S>(Zs, RB, halo, r, zz);
+            for (int s = 0; s < S; ++s) { zz[s] = fmaxf(z[s] + bbs[s], 0.f); zmask |= (zz[s] > 0.f ? 1u : 0u) << s; }
+            // with shuffle pooling nothing reads Z itself again: the backward needs only the ReLU mask (a register)
+            if (!pool_shfl) store_row<S>(Zs, RB, halo, r, zz);
             if (pool_shfl) {
                 // rows of one (window, bin) are the lanes r, r+W, ..., r+(binsz-1)W of this warp
                 for (int o = W; o < binsz * W; o <<= 1)
@@ -515,8 +519,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         // ================= dz through pool + ReLU, in place over Z (tf32: it is an MMA operand now)
         {
             const int t = r >> logW, w = r & (W - 1);
-            float z[S], dz[S];
-            load_row<S>(Zs, RB, halo, r, z);
+            float dz[S];
             const int lo = t_lo[t], hi = t_hi[t];
             if (lo == hi) {
                 const float4* dp = reinterpret_cast<const float4*>(DPs + w * NF + lo * S);
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
                 }
             }
 #pragma unroll
-            for (int s = 0; s < S; ++s) { dz[s] = z[s] > 0.f ? dz[s] : 0.f; g_bb[s] += dz[s]; }
+            for (int s = 0; s < S; ++s) { dz[s] = ((zmask >> s) & 1u) ? dz[s] : 0.f; g_bb[s] += dz[s]; }
             store_row_tf32<S>(Zs, RB, halo, r, dz);
         }
         PH(12);
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             tmem_row<NC>(trow, df);
             load_row<CP>(XHs, RB, halo, r, xh);
             load_row<CP>(Ds, RB, halo, r, d);
-            const float rstd = RSTDs[r];
+            const float rstd = rstd_row;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
                 const float dfc = c < C ? df[c] : 0.f;
