@@ -874,3 +874,16 @@ def test_eval_one_epoch_on_resident_loader_matches_dense_torch(gk):
     np.testing.assert_allclose(loss, ls / n, rtol=2e-6)
     np.testing.assert_allclose(acc, ac / n, rtol=1e-12)
     assert abs(ens - 100.0 * corr / tot) < 1e-9
+
+
+def test_peer_memory_exchange_matches_nccl_on_two_gpus(gk):
+    """gaitk_p2p_allreduce (the data-parallel exchange as a kernel over NVLink peer memory) against the NCCL path:
+    launched through torchrun when two devices are visible (tests/dist_p2p_check.py), skipped on a single-GPU box."""
+    import subprocess, sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", str(ROOT / "tests" / "dist_p2p_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "P2P_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -465,6 +465,9 @@ static int launch_reduce(const gaitk_plan* pl, int s, const float* partial, int 
     return 0;
 }
 
+__global__ void zero_floats_kernel(float* p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.f;
+}
 extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float* const* x, const int64_t* const* win_start,
                                 const int64_t* const* y, int B, const gaitk_loss_desc* loss, const float* const* logit_off,
                                 const float* denom, uint32_t enabled_mask, uint32_t task_mask, float private_mult,
@@ -476,7 +479,10 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         return fail(GAITK_E_BADARG, "consistency term couples the streams: use gaitk_forward + gaitk_backward per task");
     if (workspace_bytes < gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(gbuf, 0, (size_t)gaitk_gbuf_floats(pl) * sizeof(float), st));
+    // a kernel, not cudaMemsetAsync: gbuf may live in a peer-mapped symmetric allocation (gaitk_p2p_allreduce), where a
+    // memset node inside a CUDA graph is not a plain device-local fill
+    zero_floats_kernel<<<8, 256, 0, st>>>(gbuf, (int)gaitk_gbuf_floats(pl));
+    LAUNCH_CHECK();
     if (B <= 0) return 0;
     for (int s = 0; s < pl->n_streams; ++s) {
         if (!(task_mask & (1u << s))) continue;
