@@ -633,13 +633,34 @@ def fog_train_step(p: Params, bufs, x_skel, x_sens, ys, yt, *, sensor_length, sy
 # evaluation under masks                         weargait_train.py:391-433
 # --------------------------------------------------------------------------
 
+def cheap_xattn(a, b):
+    """CheapCrossAttention weargait_encoders.py:324-337: softmax(A B^T / sqrt(d)) B, no parameters."""
+    sim = (a @ b.transpose(1, 2)) * (a.shape[-1] ** -0.5)
+    return torch.softmax(sim, dim=-1) @ b
+
+
 def baseline_forward(p: Params, xs, kind: str, synchronized: bool, bdim: int = 8):
-    """Fusion baselines weargait_encoders.py:247-322 (``kind`` = "late_fusion" | "shared_latent").
-    late_fusion sync: shared head on the MEAN latent (:271-277); async: per-stream heads on per-stream latents.
-    shared_latent: encoder -> Linear(enc_out_ch->proj_ch) per stream -> shared backbone -> head(s) (:310-322)."""
+    """Fusion baselines weargait_encoders.py:209-387 (``kind`` = "early_fusion" | "late_fusion" | "shared_latent" |
+    "cheap_xattn").
+    early_fusion (:209-245): ONE backbone over the channel concat of the three encoder outputs; sync: one shared head,
+        async: three heads on the SAME fused representation.
+    late_fusion  (:247-282): sync: shared head on the MEAN latent; async: per-stream heads on per-stream latents.
+    shared_latent(:284-322): encoder -> Linear(enc_out_ch->proj_ch) per stream -> shared backbone -> head(s).
+    cheap_xattn  (:339-387): six pairwise zero-parameter cross-attentions, X* = mean of X attended to the other two,
+        shared backbone, per-branch heads (shared module in sync)."""
     view = _HeadAlias(p) if synchronized else p
     feats = [enc_walkway(p, xs[0]), enc_insole(p, xs[1]), enc_imu(p, xs[2])]
-    if kind == "shared_latent":
+    if kind == "early_fusion":
+        rep = backbone(p, torch.cat(feats, dim=-1), bdim)
+        if synchronized:
+            lg = task_head(view, rep, "head_w.")
+            return lg, lg, lg
+        return tuple(task_head(view, rep, h) for h in WG_HEADS)
+    if kind == "cheap_xattn":
+        W, I, M = feats
+        feats = [(cheap_xattn(W, I) + cheap_xattn(W, M)) * 0.5, (cheap_xattn(I, W) + cheap_xattn(I, M)) * 0.5,
+                 (cheap_xattn(M, W) + cheap_xattn(M, I)) * 0.5]
+    elif kind == "shared_latent":
         feats = [f @ p[f"proj_{m}.weight"].t() + p[f"proj_{m}.bias"] for f, m in zip(feats, "wim")]
     elif kind != "late_fusion":
         raise ValueError(kind)
@@ -660,6 +681,47 @@ def baseline_train_step(p: Params, bufs, xs, ys, *, kind, synchronized, lr=1e-3,
     grads = {k: g for k, g in zip(keys, gs)}
     sgd_update(p, grads, bufs, lr, momentum, wd)
     return dict(logits=[l.detach() for l in logits], losses=[float(l.detach()) for l in losses], grads=grads)
+
+
+def fog_baseline_forward(p: Params, x_skel, x_sens, kind: str, *, sensor_length: int, synchronized: bool, bdim: int = 8,
+                         out_len: int = 101):
+    """2-stream fusion baselines feature_encoder.py:346-596 behind baselines/fusion_train.py (``kind`` = "early" | "late" |
+    "share_latent" | "cheap_xattn").  Returns one logits tensor (sync, except share_latent) or (logits_skel, logits_sens).
+    early  (:347-394): backbone over the channel concat of the two encoder outputs; head / head_skel + head_sens
+    late   (:397-444): shared backbone per stream, head(s) on the CONCAT of the two latents (2 * feature_dim inputs)
+    share_latent (:447-491): Linear(enc -> S) per stream, shared backbone, ONE head applied to each latent
+    cheap_xattn  (:494-596): symmetric zero-parameter cross-attention, fused = mean of the two attended sequences"""
+    h = x_skel @ p["skel_enc.fc1.weight"].t() + p["skel_enc.fc1.bias"]
+    sk = torch.relu(layer_norm(h, p["skel_enc.ln1.weight"], p["skel_enc.ln1.bias"]))
+    se = conv_time(x_sens, p["sens_enc.conv1d.weight"], p["sens_enc.conv1d.bias"])
+    if se.shape[1] == sensor_length:
+        se = adaptive_avg_pool_time(se, out_len)
+    bb = lambda f: backbone(p, f, bdim, "backbone.conv1d.weight", "backbone.conv1d.bias")
+    lin = lambda x, pre: x @ p[pre + "weight"].t() + p[pre + "bias"]
+    if kind == "share_latent":
+        rs = bb(lin(sk, "proj_skel.")); rt = bb(lin(se, "proj_sens."))
+        return lin(rs, "head."), lin(rt, "head.")
+    if kind == "early":
+        rep = bb(torch.cat([sk, se], dim=-1))
+    elif kind == "late":
+        rep = torch.cat([bb(sk), bb(se)], dim=1)
+    elif kind == "cheap_xattn":
+        sim = (sk @ se.transpose(1, 2)) * (sk.shape[-1] ** -0.5)
+        s_star = torch.softmax(sim, dim=-1) @ se
+        g_star = torch.softmax(sim.transpose(1, 2), dim=-1) @ sk
+        rep = bb((s_star + g_star) * 0.5)
+    else:
+        raise ValueError(kind)
+    if synchronized:
+        return lin(rep, "head.")
+    return lin(rep, "head_skel."), lin(rep, "head_sens.")
+
+
+def fog_baseline_loss(out, ys, yt, kind: str, synchronized: bool):
+    """fusion_train.py:234-242: CE on the skeleton label (single-output models), else the mean of the two CE losses."""
+    if synchronized and kind != "share_latent":
+        return weighted_ce(out, ys)
+    return 0.5 * (weighted_ce(out[0], ys) + weighted_ce(out[1], yt))
 
 
 def eval_mask_sync(p: Params, xs, y, mask, bdim=8) -> Tuple[int, int]:

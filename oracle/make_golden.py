@@ -275,6 +275,41 @@ def baseline_case(name, baseline, synchronized, B=8, steps=2, seed=43):
     print(f"  wrote {name}.npz ({(OUT / (name + '.npz')).stat().st_size / 1024:.0f} KiB, {len(flat)} arrays)")
 
 
+# ------------------------------------------------------------------ 2-stream fusion baselines (baselines/fusion_train.py)
+def fog_baseline_case(name, kind, synchronized, B=6, seed=43):
+    FT.set_random_seed(seed)
+    common = dict(skeleton_input_dim=21, skeleton_output_dim=6, sensor_in_channels=6, sensor_out_channels=6, sensor_length=426,
+                  shared_out_channels=16, backbone_dim=8, num_classes=3, synchronized_loading=synchronized)
+    if kind == "early":
+        model = FE.EarlyFusionModel(**common)
+    elif kind == "late":
+        model = FE.LateFusionModel(**common)
+    elif kind == "share_latent":
+        model = FE.ShareLatentModel(**common, taskhead_input_dim=8 * 16)
+    else:
+        model = FE.CheapXAttnModel(**common)
+    sk, se, y = synth_fog_batch(B, seed=seed)
+    r = np.random.default_rng(seed + 1)
+    yt = y if synchronized else r.permutation(y)
+    out = model(torch.from_numpy(sk), torch.from_numpy(se))
+    ce = torch.nn.CrossEntropyLoss()
+    if synchronized and kind != "share_latent":                     # fusion_train.py:234-242
+        loss = ce(out, torch.from_numpy(y)); logits = [_np(out)]
+    else:
+        loss = 0.5 * (ce(out[0], torch.from_numpy(y)) + ce(out[1], torch.from_numpy(yt))); logits = [_np(out[0]), _np(out[1])]
+    model.zero_grad(); loss.backward()
+    flat = {f"state0/{k}": v for k, v in _state(model).items()}
+    for k, v in _grads(model).items():
+        if v is not None:
+            flat[f"grad:{k}"] = v
+    flat.update(x_skel=sk, x_sens=se, ys=y, yt=yt, loss=np.array(float(loss.detach())))
+    for i, l in enumerate(logits):
+        flat[f"logits{i}"] = l
+    flat["meta"] = json.dumps(dict(kind=kind, synchronized=synchronized, B=B, sensor_length=426))
+    np.savez_compressed(OUT / f"{name}.npz", **flat)
+    print(f"  wrote {name}.npz ({(OUT / (name + '.npz')).stat().st_size / 1024:.0f} KiB, {len(flat)} arrays)")
+
+
 # ------------------------------------------------------------------ single-modality paths
 def single_modality_case(name, seed=5, B=6):
     FT.set_random_seed(seed)
@@ -508,6 +543,12 @@ def main():
         "bl_late_async": lambda: baseline_case("bl_late_async", "late_fusion", False),
         "bl_shared_latent_sync": lambda: baseline_case("bl_shared_latent_sync", "shared_latent", True),
         "bl_shared_latent_async": lambda: baseline_case("bl_shared_latent_async", "shared_latent", False),
+        **{f"fogbl_{k}_{'sync' if sy else 'async'}": (lambda k=k, sy=sy: fog_baseline_case(f"fogbl_{k}_{'sync' if sy else 'async'}", k, sy))
+           for k in ("early", "late", "share_latent", "cheap_xattn") for sy in (True, False)},
+        "bl_early_sync": lambda: baseline_case("bl_early_sync", "early_fusion", True),
+        "bl_early_async": lambda: baseline_case("bl_early_async", "early_fusion", False),
+        "bl_xattn_sync": lambda: baseline_case("bl_xattn_sync", "cheap_xattn", True),
+        "bl_xattn_async": lambda: baseline_case("bl_xattn_async", "cheap_xattn", False),
         "cagrad_corpus": lambda: cagrad_corpus("cagrad_corpus"),
         "data_path": lambda: data_case("data_path"),
     }

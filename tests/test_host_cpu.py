@@ -124,3 +124,23 @@ def test_exact_solver_never_worse_than_slsqp():
         assert abs(w.sum() - 1) < 1e-12 and (w >= 0).all()
         f_ours = O.cagrad_objective(A, w, float(alpha)); f_ref = O.cagrad_objective(A, wref[:n], float(alpha))
         assert f_ours <= f_ref + 1e-9 * max(1.0, abs(f_ref))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a tiny sample: one JSON line
+    with the contract's keys; under a multi-rank launch only rank 0 prints."""
+    import json, os, subprocess, sys
+    env = dict(os.environ); env.pop("RANK", None)
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-batch", "128"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "windows/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    env["RANK"] = "1"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -183,9 +183,11 @@ def test_single_modality_paths_match_reference():
                 _close(p[k].grad.numpy(), v, rtol=2e-4, atol=2e-6)
 
 
-@pytest.mark.parametrize("name", ["bl_late_sync", "bl_late_async", "bl_shared_latent_sync", "bl_shared_latent_async"])
+@pytest.mark.parametrize("name", ["bl_late_sync", "bl_late_async", "bl_shared_latent_sync", "bl_shared_latent_async",
+                                  "bl_early_sync", "bl_early_async", "bl_xattn_sync", "bl_xattn_async"])
 def test_fusion_baselines_match_reference(name):
-    """LateFusion3 / SharedLatent3 trained the way ``--baseline`` trains them (plain mean of the CE losses)."""
+    """The four 3-stream fusion baselines trained the way ``--baseline`` trains them (plain mean of the CE losses).
+    EarlyFusion3 / CheapXAttn3 have no CUDA path yet: the oracle and its goldens are the parity infrastructure for it."""
     z = load_golden(name)
     meta = z["meta"]
     sync = meta["synchronized"]
@@ -208,3 +210,29 @@ def test_fusion_baselines_match_reference(name):
                 _close(g.numpy(), z[gk])
         for k, v in p.items():
             _close(v.detach().numpy(), z[f"s{st}/param:{k}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["early", "late", "share_latent", "cheap_xattn"])
+@pytest.mark.parametrize("sync", [True, False])
+def test_two_stream_fusion_baselines_match_reference(kind, sync):
+    """The 2-stream twins behind baselines/fusion_train.py (feature_encoder.py:346-596): logits, loss and every
+    gradient of the oracle restatement against the reference classes.  No CUDA path yet: this
+    pins the oracle it will be checked against."""
+    z = load_golden(f"fogbl_{kind}_{'sync' if sync else 'async'}")
+    p = {k: torch.tensor(v, dtype=torch.float32).requires_grad_(True) for k, v in sub(z, "state0").items()}
+    out = O.fog_baseline_forward(p, torch.from_numpy(z["x_skel"]), torch.from_numpy(z["x_sens"]), kind,
+                                 sensor_length=z["meta"]["sensor_length"], synchronized=sync)
+    outs = [out] if torch.is_tensor(out) else list(out)
+    for i, l in enumerate(outs):
+        _close(l.detach().numpy(), z[f"logits{i}"])
+    loss = O.fog_baseline_loss(out, torch.from_numpy(z["ys"]), torch.from_numpy(z["yt"]), kind, sync)
+    _close(np.array(float(loss.detach())), z["loss"])
+    keys = list(p)
+    gs = torch.autograd.grad(loss, [p[k] for k in keys], allow_unused=True)
+    n = 0
+    for k, g in zip(keys, gs):
+        if g is None:
+            assert f"grad:{k}" not in z, k
+        else:
+            _close(g.numpy(), z[f"grad:{k}"]); n += 1
+    assert n >= 8
