@@ -133,9 +133,45 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+# ---------------------------------------------------------------------------------------------- synthetic inputs
+# Generators of WearGait- / FoG-shaped data.  They live here so that the GPU arm never imports oracle/
+# (only the cpu_baseline / reference leg does); same distributions as the generators the tests use.
+def synth_weargait_labels(B: int, seed: int = 0, p_pd: float = 0.6):
+    rng = np.random.default_rng(seed)
+    y = (rng.random(B) < p_pd).astype(np.int64)
+    if B > 1:
+        y[0], y[1] = 0, 1
+    return y
+
+
+def synth_weargait_batch(B: int, T_: int = 64, seed: int = 0, p_pd: float = 0.6):
+    """walkway U[0,1), insole N(0,1), IMU N(0, sigma^2) with sigma = 2 for PD and 1 for HC; p(PD) = 0.6"""
+    rng = np.random.default_rng(seed)
+    y = (rng.random(B) < p_pd).astype(np.int64)
+    if B > 1:
+        y[0], y[1] = 0, 1
+    xw = rng.random((B, T_, 2), dtype=np.float32)
+    xi = rng.standard_normal((B, T_, 13), dtype=np.float32)
+    sig = np.where(y == 1, 2.0, 1.0).astype(np.float32)[:, None, None]
+    xm = rng.standard_normal((B, T_, 24), dtype=np.float32) * sig
+    return [xw, xi, xm], y
+
+
+def synth_fog_batch(B: int, seed: int = 0, pose_len=101, sens_len=426, joints=7, sens_ch=6):
+    """skeleton U[0,1) and sensor N(0,1) clips zero-padded at the end from random true lengths; 3 classes p=(.5,.3,.2)"""
+    rng = np.random.default_rng(seed)
+    y = rng.choice(3, size=B, p=[0.5, 0.3, 0.2]).astype(np.int64)
+    sk = rng.random((B, pose_len, joints * 3), dtype=np.float32)
+    se = rng.standard_normal((B, sens_len, sens_ch), dtype=np.float32)
+    Ls = rng.integers(min(40, pose_len // 3), pose_len + 1, size=B)
+    Lt = rng.integers(min(140, sens_len // 3), sens_len + 1, size=B)
+    for b in range(B):
+        sk[b, Ls[b]:] = 0.0; se[b, Lt[b]:] = 0.0
+    return sk, se, y
+
+
 def synth(B, seed):
-    import gait_oracle as O
-    return O.synth_weargait_batch(B, T=T, seed=seed)
+    return synth_weargait_batch(B, T_=T, seed=seed)
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -199,7 +235,6 @@ MASK_CYCLE = [(True, False, False), (False, True, False), (False, False, True), 
 
 def build_workload(args, gaitk, dev, rank):
     """-> dict(model, crit, step_kw(i), host batches, stream names, dims, units)"""
-    import gait_oracle as O
     kind = args.workload; B = args.batch
     if kind == "fog":
         model = gaitk.MultiModalMultiTaskModel(21, 6, 6, 6, 426, 16, 8, 128, 3, synchronized_loading=False).to(dev)
@@ -207,7 +242,7 @@ def build_workload(args, gaitk, dev, rank):
         crit = [gaitk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in counts]
         host = []
         for i in range(2):
-            sk, se, y = O.synth_fog_batch(B, seed=1000 * rank + i)
+            sk, se, y = synth_fog_batch(B, seed=1000 * rank + i)
             y2 = np.random.default_rng(7 + i).permutation(y)
             host.append(([torch.from_numpy(sk).pin_memory(), torch.from_numpy(se).pin_memory()],
                          [torch.from_numpy(y).pin_memory(), torch.from_numpy(y2).pin_memory()]))
@@ -264,8 +299,7 @@ def run_gpu(args):
             return None
         if args.workload != "weargait":
             raise SystemExit("multi-GPU bench is wired for the default workload")
-        import gait_oracle as O
-        g = torch.cat([torch.from_numpy(O.synth_weargait_labels(B, seed=1000 * r + i)).to(dev) for r in range(world)])
+        g = torch.cat([torch.from_numpy(synth_weargait_labels(B, seed=1000 * r + i)).to(dev) for r in range(world)])
         return [g, g, g]
     yglob = [global_labels(i) for i in range(NBUF)]
     l2_flush = None
