@@ -464,7 +464,7 @@ def run_gpu(args):
                 "value": res_value, "unit": UNIT, "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": d2h,
                 "note": "frame stores resident in HBM (uploaded once per fold); per step the host sends int64 window-start "
                         "indices + labels, the stream kernels gather the windows (win_start path); result read back every step"},
-            "gpu_launches": (3 + 2 * ns) * args.steps,      # denominators, zero-fill, ns x (stream kernel + reduce), update
+            "gpu_launches": (4 + ns) * args.steps,          # denominators, zero-fill, ns stream kernels, one reduce, update
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "final_losses": loss,
         }

@@ -399,9 +399,9 @@ static size_t stream_ws_floats(const gaitk_plan* pl, const StreamPlan& sp, int B
 }
 extern "C" size_t gaitk_workspace_bytes(const gaitk_plan* pl, int B) {
     if (!pl) return 0;
-    size_t mx = 0;
-    for (int s = 0; s < pl->n_streams; ++s) mx = std::max(mx, stream_ws_floats(pl, pl->st[s], B));
-    return mx * sizeof(float) + 256;
+    size_t sum = 0;                                      // every stream keeps its own partial rows until the single reduce launch
+    for (int s = 0; s < pl->n_streams; ++s) sum += (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64;
+    return sum * sizeof(float) + 256;
 }
 
 static const float* pp(const float* params, const gaitk_plan* pl, int idx) { return idx < 0 ? nullptr : params + pl->params[idx].off; }
@@ -452,13 +452,17 @@ static void set_loss(StreamArgs& a, const gaitk_loss_desc& L, int K) {
     for (int k = 0; k < KMAX; ++k) { a.margin[k] = k < K ? L.margin[k] : 0.f; a.cls_w[k] = k < K ? L.cls_weight[k] : 0.f; }
 }
 
-static int launch_reduce(const gaitk_plan* pl, int s, const float* partial, int grid, float* gbuf, int task, float mult,
-                         int stat_slot, cudaStream_t st) {
+static void fill_reduce(const gaitk_plan* pl, int s, const float* partial, int grid, float* gbuf, int task, float mult,
+                        int stat_slot, ReduceArgs& R) {
     const StreamPlan& sp = pl->st[s];
-    ReduceArgs R; memset(&R, 0, sizeof(R));
+    memset(&R, 0, sizeof(R));
     R.partial = partial; R.grid = grid; R.NGP = sp.NGP; R.NG = sp.go.total; R.nseg = sp.nseg;
     for (int i = 0; i < sp.nseg; ++i) R.seg[i] = sp.seg[i];
     R.gbuf = gbuf; R.P = pl->P; R.NP = pl->NP; R.task = task; R.private_mult = mult; R.stat_slot = stat_slot;
+}
+static int launch_reduce(const gaitk_plan* pl, int s, const float* partial, int grid, float* gbuf, int task, float mult,
+                         int stat_slot, cudaStream_t st) {
+    ReduceArgs R; fill_reduce(pl, s, partial, grid, gbuf, task, mult, stat_slot, R);
     const int n = R.NG + 2;
     reduce_partials_kernel<<<(n + 127) / 128, dim3(128, 8), 0, st>>>(R);
     LAUNCH_CHECK();
@@ -484,18 +488,29 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
     zero_floats_kernel<<<8, 256, 0, st>>>(gbuf, (int)gaitk_gbuf_floats(pl));
     LAUNCH_CHECK();
     if (B <= 0) return 0;
+    ReduceArgsMulti M; memset(&M, 0, sizeof(M));
+    int n_active = 0, max_ng = 0;
+    float* part = (float*)workspace;
     for (int s = 0; s < pl->n_streams; ++s) {
+        const size_t ws_floats = (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64;
+        float* my_part = part; part += ws_floats;
         if (!(task_mask & (1u << s))) continue;
         StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_FUSED, !(enabled_mask & (1u << s)), a);
         set_loss(a, loss[s], pl->d.num_classes);
         a.y = (const long long*)y[s]; a.denom = denom + s;
         a.logit_off = logit_off ? logit_off[s] : nullptr;
         a.logits = logits ? logits[s] : nullptr;
-        a.partial = (float*)workspace;
+        a.partial = my_part;
         const int grid = stream_grid(pl, pl->st[s], B, dtype);
         int rc = launch_stream(pl, s, a, grid, st, dtype);
         if (rc) return rc;
-        if ((rc = launch_reduce(pl, s, (const float*)workspace, grid, gbuf, s, private_mult, s, st))) return rc;
+        fill_reduce(pl, s, my_part, grid, gbuf, s, private_mult, s, M.r[n_active]);
+        max_ng = std::max(max_ng, M.r[n_active].NG + 2);
+        ++n_active;
+    }
+    if (n_active) {
+        reduce_partials_multi_kernel<<<dim3((max_ng + 127) / 128, n_active), dim3(128, 8), 0, st>>>(M);
+        LAUNCH_CHECK();
     }
     return 0;
 }

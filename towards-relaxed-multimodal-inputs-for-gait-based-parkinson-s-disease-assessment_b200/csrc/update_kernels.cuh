@@ -28,7 +28,7 @@ struct ReduceArgs {
 
 // sum the per-CTA partial rows in fixed order (8 row slices per output, combined in slice order), then add
 // into gbuf (passes run in launch order).  blockDim = (128, 8).
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const ReduceArgs R) {
+__device__ __forceinline__ void reduce_partials_body(const ReduceArgs& R) {
     __shared__ float sh[8][128];
     const int e = blockIdx.x * 128 + threadIdx.x, sl = threadIdx.y;
     float s0 = 0.f, s1 = 0.f;
@@ -58,6 +58,15 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const ReduceArgs 
             return;
         }
     }
+}
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const ReduceArgs R) { reduce_partials_body(R); }
+// all streams of a fused step in ONE launch (blockIdx.y = stream): every output element of gbuf receives exactly one
+// contribution there (task column = stream, private segments and stat slots are disjoint), so the order is immaterial
+struct ReduceArgsMulti { ReduceArgs r[MAXT]; };
+__global__ void __launch_bounds__(1024) reduce_partials_multi_kernel(const ReduceArgsMulti M) {
+    const ReduceArgs& R = M.r[blockIdx.y];
+    if ((int)blockIdx.x * 128 >= R.NG + 2) return;
+    reduce_partials_body(R);
 }
 
 struct ParamSeg { long long off; int numel; int shared_off; int has_grad; };
