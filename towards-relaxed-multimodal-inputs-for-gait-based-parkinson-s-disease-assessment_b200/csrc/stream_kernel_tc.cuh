@@ -491,7 +491,32 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
             for (int s = 0; s < S; ++s) { zz[s] = fmaxf(z[s] + bbs[s], 0.f); zmask |= (zz[s] > 0.f ? 1u : 0u) << s; }
             // with shuffle pooling nothing reads Z itself again: the backward needs only the ReLU mask (a register)
             if (!pool_shfl) store_row<S>(Zs, RB, halo, r, zz);
-            if (pool_shfl) {
+            if constexpr (FX && S == 16) {
+                // W = 2, 8 frames per bin: the 8 rows of one (window, bin) are the lanes with equal (lane & 1, lane >> 4).
+                // Reduce-scatter butterfly over lane bits 3, 2, 1: at every stage a lane keeps half of its channels and
+                // hands the other half to its partner (14 shuffles instead of the 48 of an all-reduce); afterwards
+                // lane l holds the sums of channels 2 * ((l >> 1) & 7) and + 1 of its (window, bin).
+                float a8[8], a4[4], a2[2];
+                const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float keep = h8 ? zz[8 + i] : zz[i], send = h8 ? zz[i] : zz[8 + i];
+                    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float keep = h4 ? a8[4 + i] : a8[i], send = h4 ? a8[i] : a8[4 + i];
+                    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float keep = h2 ? a4[2 + i] : a4[i], send = h2 ? a4[i] : a4[2 + i];
+                    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+                const int ch = (h8 ? 8 : 0) + (h4 ? 4 : 0) + (h2 ? 2 : 0);
+                const int w = r & 1, bin = r >> 4;                        // r = 32 wrp + lane: 16 rows per bin
+                *reinterpret_cast<float2*>(Ps + w * NF + bin * S + ch) = make_float2(a2[0] * 0.125f, a2[1] * 0.125f);
+            } else if (pool_shfl) {
                 // rows of one (window, bin) are the lanes r, r+W, ..., r+(binsz-1)W of this warp
                 for (int o = W; o < binsz * W; o <<= 1)
 #pragma unroll
