@@ -129,3 +129,41 @@ def test_loader_order_equals_a_real_torch_dataloader(dl):
     for _ in range(3):
         assert [b.tolist() for b in ref] == [ib.index.tolist() for ib in mine.index_batches()]
         assert [b.tolist() for b in ref_te] == [ib.index.tolist() for ib in mine_te.index_batches()]
+
+
+@pytest.mark.parametrize("n,bs,seed", [(1, 4, 0), (5, 5, 1), (64, 7, 2), (129, 64, 3)])
+def test_loader_order_equals_torch_dataloader_for_other_sizes(dl, n, bs, seed):
+    class DS(torch.utils.data.Dataset):
+        def __len__(self): return n
+        def __getitem__(self, i): return i
+    st = dl.WindowStore("walkway", torch.zeros(n * 64, 2), 64, [f"s|walkway|{i}" for i in range(n)], np.arange(n) * 64)
+    ds = dl.WearGaitSyncDataset((st,), [(f"s|walkway|{i}",) for i in range(n)], {"s": 0})
+    g1 = torch.Generator().manual_seed(seed); g2 = torch.Generator().manual_seed(seed)
+    ref = torch.utils.data.DataLoader(DS(), batch_size=bs, shuffle=True, num_workers=0, generator=g1)
+    mine = dl.DeviceLoader(ds, bs, True, g2)
+    assert len(mine) == len(ref)
+    for _ in range(2):
+        a = [b.tolist() for b in ref]; b = [ib.index.tolist() for ib in mine.index_batches()]
+        assert a == b
+        assert sorted(i for x in b for i in x) == list(range(n))          # every window exactly once per epoch
+
+
+def test_mask_table_arithmetic_matches_the_reference_formulas():
+    """evaluation.py turns per-batch hit counts into the numbers eval_with_mask / eval_one_epoch return
+    (weargait_train.py:322-433): sync = micro accuracy over windows, async = mean over batches of the per-batch
+    accuracy ((pred == y).float().mean().item() * 100), macro over the enabled streams."""
+    import gaitk
+    ev = gaitk.evaluation
+    counts = np.array([[3, 2, 1, 3, 2, 1, 3, 2, 1, 3], [1, 1, 1, 1, 1, 1, 1, 0, 2, 1]], dtype=np.int32)   # two batches
+    sizes = np.array([4, 3], dtype=np.int64)
+    for i, (name, mask) in enumerate(ev.MASK_COMBOS.items()):
+        got = ev._mask_result(counts, sizes, False, i, mask)
+        assert got == 100.0 * float(counts[:, i].sum()) / 7.0
+        res = ev._mask_result(counts, sizes, True, i, mask)
+        want = {}
+        for s, nm in enumerate(("walkway", "insole", "imu")):
+            if mask[s]:
+                accs = [torch.tensor([1.0] * int(c) + [0.0] * int(n - c)).mean().item() * 100 for c, n in zip(counts[:, 7 + s], sizes)]
+                want[nm] = sum(accs) / 2
+        want["macro_enabled"] = sum(want.values()) / len(want)
+        assert res == want, (name, res, want)
