@@ -204,9 +204,11 @@ struct HeadState {
     }
 
     // FAST: MUFU exp / log in the loss (tensor-core path; the fp32 path keeps libdevice's expf / logf)
-    template <bool FAST = false>
+    // KT: compile-time number of classes (0 = read A.K): with K known the KMAX-wide loops lose their dead iterations
+    // and, NF = 32 NFL being a constant, every weight address is an immediate offset
+    template <bool FAST = false, int KT = 0>
     __device__ __forceinline__ void run(const StreamArgs& A, const HeadCtx& c, int w_, int lane, int win0, bool train, float inv_denom) {
-            const int wi = win0 + w_; const int K = A.K, NF = A.NF;
+            const int wi = win0 + w_; const int K = KT ? KT : A.K; constexpr int NF = NFL * 32;
             float f[NFL], xn[NFL], xh[NFL];
             float rstd_h = 1.f;
 #pragma unroll

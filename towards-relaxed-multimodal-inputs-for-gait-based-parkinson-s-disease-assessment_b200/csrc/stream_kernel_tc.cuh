@@ -536,7 +536,11 @@ __global__ void __launch_bounds__(NT, TcMinBlocks<Cfg>::value) stream_kernel_tc(
         __syncthreads();
         PH(9);
         // ================= pool + head + loss (warp per window)
-        if (wrp < W) head.template run<true>(A, hc, wrp, lane, win0, train, inv_denom);
+        if (wrp < W) {
+            if (K == 2) head.template run<true, 2>(A, hc, wrp, lane, win0, train, inv_denom);
+            else if (K == 3) head.template run<true, 3>(A, hc, wrp, lane, win0, train, inv_denom);
+            else head.template run<true, 0>(A, hc, wrp, lane, win0, train, inv_denom);
+        }
         if (!train) { if (has_next) prefetch(tile + (int)gridDim.x); __syncthreads(); continue; }
         PH(10);
         __syncthreads();
