@@ -170,14 +170,31 @@ def synth_fog_batch(B: int, seed: int = 0, pose_len=101, sens_len=426, joints=7,
     return sk, se, y
 
 
+def synth_fog_labels(B: int, seed: int = 0):
+    return np.random.default_rng(seed).choice(3, size=B, p=[0.5, 0.3, 0.2]).astype(np.int64)
+
+
 def synth(B, seed):
     return synth_weargait_batch(B, T_=T, seed=seed)
 
 
+def stream_labels(kind: str, B: int, rank: int, i: int):
+    """Label vectors (one per stream) of host batch i on `rank` -- regenerated from the seeds alone, so that every rank can
+    form the label vectors of the GLOBAL batch (the weighted-mean denominators) without an exchange."""
+    if kind == "fog":
+        y = synth_fog_labels(B, seed=1000 * rank + i)
+        return [y, np.random.default_rng(7 + i).permutation(y)]
+    y = synth_weargait_labels(B, seed=1000 * rank + i)
+    if kind == "weargait_async":
+        r = np.random.default_rng(50 + i)
+        return [y, r.permutation(y), r.permutation(y)]
+    return [y, y, y]
+
+
 # ---------------------------------------------------------------------------------------------- CPU arm
 def cpu_port_step_time(B: int, steps: int, warmup: int, threads: int):
-    """One reference training step (forward_batch + 3 criteria + step_cagrad_three + SGD,
-    weargait_train.py:163-248,305-311) restated by the oracle with the same torch-CPU / SciPy calls."""
+    """Fallback when no staged reference exists: one reference training step (forward_batch + 3 criteria +
+    step_cagrad_three + SGD, weargait_train.py:163-248,305-311) restated by the oracle with the same torch-CPU / SciPy calls."""
     import gait_oracle as O
     torch.set_num_threads(threads)
     torch.manual_seed(0)
@@ -196,21 +213,45 @@ def cpu_port_step_time(B: int, steps: int, warmup: int, threads: int):
     return times
 
 
+def reference_step_times(B: int, steps: int, warmup: int, device: str, threads: int):
+    """The UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py): forward_batch + make_criteria's three GCL
+    losses + step_cagrad_three + SGD (train/weargait_train.py:163-248,300-311), driven by oracle/ref_harness.py on
+    `device` ("cpu": all host threads; "cuda": stock torch-CUDA fp32 on the B200).  -> (seconds per step, kind)"""
+    import ref_harness as H
+    if H.load_reference() is None:
+        if device != "cpu":
+            return None, "unavailable"
+        return cpu_port_step_time(B, steps, warmup, threads), "port"
+    st = H.RefWearGaitStep(device, threads=threads)
+    batches = []
+    for i in range(2):
+        xs, y = synth(B, 1 + i)
+        batches.append(([torch.from_numpy(x).to(device) for x in xs], torch.from_numpy(y).to(device)))
+    return st.time_steps(batches, steps, warmup), "reference"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = args.cpu_batch
-    times = cpu_port_step_time(B, args.steps, max(args.warmup, 1), threads)
+    B = args.batch if args.cpu_batch <= 0 else args.cpu_batch
+    # bounded: the whole run must end within a few minutes -> probe one step, then shrink the per-step sample if needed
+    probe, kind = reference_step_times(min(B, 4096), 1, 1, "cpu", threads)
+    est = probe[0] * B / min(B, 4096) * (args.steps + max(args.warmup, 1))
+    while est > 240 and B > 4096:
+        B //= 2; est /= 2
+    times, kind = reference_step_times(B, args.steps, max(args.warmup, 1), "cpu", threads)
     total = sum(times); val = B * len(times) / total
+    sample = (f"{len(times)} steps of B={B} windows" + (" (the GPU arm's per-GPU batch)" if B == args.batch else f" (bounded sample of B={args.batch})")
+              + f", {'unmodified reference from oracle/_ref' if kind == 'reference' else 'oracle port'}, torch {torch.__version__} CPU, {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch, getattr(args, "workload", "weargait")), "cpu_sample_batch": B, "timing": "time.perf_counter around each step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(times)} steps of B={B} windows (bounded sample of the per-GPU batch), torch {torch.__version__} CPU"},
+        "config": {"workload": workload_name(args.batch, getattr(args, "workload", "weargait")), "cpu_sample_batch": B,
+                   "same_config": B == args.batch, "timing": "time.perf_counter around each step (incl. the three loss .item() reads)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -243,9 +284,10 @@ def build_workload(args, gaitk, dev, rank):
         host = []
         for i in range(2):
             sk, se, y = synth_fog_batch(B, seed=1000 * rank + i)
-            y2 = np.random.default_rng(7 + i).permutation(y)
+            ys = stream_labels(kind, B, rank, i)
+            assert np.array_equal(ys[0], y)
             host.append(([torch.from_numpy(sk).pin_memory(), torch.from_numpy(se).pin_memory()],
-                         [torch.from_numpy(y).pin_memory(), torch.from_numpy(y2).pin_memory()]))
+                         [torch.from_numpy(v).pin_memory() for v in ys]))
         return dict(model=model, crit=crit, host=host, names=("skeleton", "sensor"), dims=((101, 21), (426, 6)),
                     cagrad_c=0.1, private_mult=1.0, dtype="f32", kw=lambda i: {})
     sync = kind != "weargait_async"
@@ -254,12 +296,12 @@ def build_workload(args, gaitk, dev, rank):
     host = []
     for i in range(2):
         xs, y = synth(B, 1000 * rank + i)
-        yt = torch.from_numpy(y).pin_memory()
+        yl = stream_labels(kind, B, rank, i)
+        assert np.array_equal(yl[0], y)
         if sync:
-            ys = [yt, yt, yt]
+            yt = torch.from_numpy(y).pin_memory(); ys = [yt, yt, yt]
         else:
-            r = np.random.default_rng(50 + i)
-            ys = [yt, torch.from_numpy(r.permutation(y)).pin_memory(), torch.from_numpy(r.permutation(y)).pin_memory()]
+            ys = [torch.from_numpy(v).pin_memory() for v in yl]
         host.append(([torch.from_numpy(x).pin_memory() for x in xs], ys))
     kw = (lambda i: dict(enabled=MASK_CYCLE[i % 7], tasks=MASK_CYCLE[i % 7])) if kind == "weargait_relaxed" else (lambda i: {})
     return dict(model=model, crit=crit, host=host, names=("walkway", "insole", "imu"), dims=((T, 2), (T, 13), (T, 24)),
@@ -297,10 +339,11 @@ def run_gpu(args):
     def global_labels(i):
         if world == 1:
             return None
-        if args.workload != "weargait":
-            raise SystemExit("multi-GPU bench is wired for the default workload")
-        g = torch.cat([torch.from_numpy(synth_weargait_labels(B, seed=1000 * r + i)).to(dev) for r in range(world)])
-        return [g, g, g]
+        per_rank = [stream_labels(args.workload, B, r, i) for r in range(world)]
+        out = [torch.from_numpy(np.concatenate([pr[s_] for pr in per_rank])).to(dev) for s_ in range(ns)]
+        if args.workload in ("weargait", "weargait_relaxed"):
+            out = [out[0]] * ns                           # one shared label vector (same device pointer: one histogram)
+        return out
     yglob = [global_labels(i) for i in range(NBUF)]
     l2_flush = None
     if B * bytes_per_unit < 2 * 126e6:                 # small batches: flush L2 between steps instead
@@ -348,6 +391,15 @@ def run_gpu(args):
         rank_ms = [ms / args.steps]
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
+    # replicas must stay bit-identical (every rank ran the same deterministic solve + update on the same reduced buffer)
+    flat = model.flat_params()
+    chk = torch.stack([flat.double().sum(), flat.double().abs().sum(), (flat.view(torch.int32).to(torch.int64)).sum().double()])
+    chks = [chk.cpu().tolist()]
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        chks = [c.cpu().tolist() for c in allc]
+    replicas_identical = all(c == chks[0] for c in chks)
 
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H of (loss, correct), every step.  The H2D copy of
     # batch i+1 is issued on a copy stream before step i is launched (two device slots), so it overlaps compute.
@@ -375,24 +427,36 @@ def run_gpu(args):
     # ---- end-to-end with the dataset resident in HBM (the B200-first data path): the frame stores are uploaded once
     # per fold; every step the host sends only the window-start indices and labels (pinned), the kernels gather.
     res_value = None
-    if world == 1 and args.workload == "weargait":
+    if args.workload == "weargait":
+        # every rank holds ITS shard of the fold's frame stores (sharded by window); the per-step index /
+        # label vectors of all ranks are derived from the seeds, so the global label vector needs no exchange
         stores = [torch.cat([devb[i][0][s].reshape(-1, DIMS[s]) for i in range(NBUF)]) for s in range(3)]
-        ycat = torch.cat([host[i][1][0] for i in range(NBUF)])
-        gen = torch.Generator().manual_seed(1234 + rank)
-        idx_host, y_host = [], []
-        for i in range(4):
+        def res_batch(r_, i):
+            gen = torch.Generator().manual_seed(1234 + r_ + 97 * i)
             perm = torch.randperm(NBUF * B, generator=gen)[:B]
-            idx_host.append((perm * T).to(torch.int64).pin_memory()); y_host.append(ycat[perm].contiguous().pin_memory())
+            yc = np.concatenate([stream_labels("weargait", B, r_, j)[0] for j in range(NBUF)])
+            return perm, torch.from_numpy(yc)[perm].contiguous()
+        idx_host, y_host, yg_res = [], [], []
+        for i in range(4):
+            perm, yy = res_batch(rank, i)
+            idx_host.append((perm * T).to(torch.int64).pin_memory()); y_host.append(yy.pin_memory())
+            if world > 1:
+                g = torch.cat([res_batch(r_, i)[1] for r_ in range(world)]).to(dev); yg_res.append([g, g, g])
+            else:
+                yg_res.append(None)
         model.set_window(T)
         for i in range(3):
-            step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3)
+            step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3, ys_global=yg_res[i % 4])
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
         for i in range(args.steps):
-            step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3)
+            step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3, ys_global=yg_res[i % 4])
         r1.record(); barrier()
-        res_value = B * args.steps / (r0.elapsed_time(r1) * 1e-3)
+        t3 = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        res_value = world * B * args.steps / (float(t3.item()) * 1e-3)
 
     # ---- dominant kernel, timed alone with CUDA events on the launching stream (rank 0)
     roof = None; per_stream = {}
@@ -440,12 +504,51 @@ def run_gpu(args):
                 "per_stream_ms": per_stream,
                 "step_hbm_gbs": B * bytes_per_unit / (ms_max / args.steps * 1e-3) / 1e9}
 
-    cpu = None
+    # ---- batch sweep of the fused step (device-resident, CUDA-graph replay), rank 0, N = 1: the reference trains at B = 64
+    sweep = None
+    if rank == 0 and world == 1 and args.workload == "weargait" and not args.no_sweep:
+        sweep = {}
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        for Bs in (64, 512, 4096, 32768):
+            if Bs > B:
+                continue
+            xs_, ys_ = devb[0]
+            xs_ = [x[:Bs].contiguous() for x in xs_]; y_ = ys_[0][:Bs].contiguous(); ys_ = [y_, y_, y_]
+            for _ in range(3):
+                step.step(xs_, ys_)
+            torch.cuda.synchronize()
+            n_it = 20; tot = 0.0
+            for _ in range(n_it):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); step.step(xs_, ys_); b.record(); torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            sweep[str(Bs)] = {"ms_per_step": tot / n_it, "windows_per_s": Bs / (tot / n_it * 1e-3)}
+        del flush
+
+    cpu = None; cuda_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        times = cpu_port_step_time(args.cpu_batch, 3, 1, threads)
-        cpu = {"value": args.cpu_batch * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{len(times)} steps of B={args.cpu_batch} windows (bounded sample), oracle port, torch {torch.__version__} CPU"}
+        times, kind = reference_step_times(args.cpu_batch, 3, 1, "cpu", threads)
+        cpu = {"value": args.cpu_batch * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{len(times)} steps of B={args.cpu_batch} windows (bounded sample of B={B}), "
+                         f"{'unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port'}, torch {torch.__version__} CPU"}
+        # north_star's denominator: the reference's OWN code on this B200 under stock torch-CUDA (fp32), same workload
+        if args.workload == "weargait":
+            cuda_ref = {}
+            for Bs in (64, 4096, 32768):
+                if Bs > B:
+                    continue
+                tms, kind2 = reference_step_times(Bs, 5, 2, "cuda", threads)
+                if tms is None:
+                    cuda_ref = {"unavailable": "no staged reference (oracle/_ref)"}; break
+                mean = sum(tms) / len(tms)
+                cuda_ref[str(Bs)] = {"ms_per_step": 1e3 * mean, "windows_per_s": Bs / mean,
+                                     "gaitk_speedup": (sweep[str(Bs)]["windows_per_s"] / (Bs / mean)) if sweep and str(Bs) in sweep else None}
+            if "unavailable" not in cuda_ref:
+                cuda_ref["how"] = ("unmodified reference step (forward_batch + GCL x3 + step_cagrad_three + SGD, oracle/_ref via "
+                                   "oracle/ref_harness.py) on this GPU under stock torch-CUDA fp32, host wall clock with "
+                                   "torch.cuda.synchronize on both sides, 2 warm-up + 5 timed steps, incl. the .item() loss reads")
 
     if rank == 0:
         line = {
@@ -462,10 +565,12 @@ def run_gpu(args):
                             "overlaps step i), result (loss[3], correct[3]) read back every step"},
             "e2e_resident": None if res_value is None else {
                 "value": res_value, "unit": UNIT, "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": d2h,
-                "note": "frame stores resident in HBM (uploaded once per fold); per step the host sends int64 window-start "
-                        "indices + labels, the stream kernels gather the windows (win_start path); result read back every step"},
+                "note": "frame stores resident in HBM, sharded by window over the ranks (uploaded once per fold); per step the "
+                        "host sends int64 window-start indices + labels, the stream kernels gather the windows (win_start "
+                        "path); result read back every step; whole-job windows/s, max over ranks"},
             "gpu_launches": (4 + ns) * args.steps,          # denominators, zero-fill, ns stream kernels, one reduce, update
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "cuda_reference": cuda_ref, "batch_sweep": sweep,
+            "replicas_identical": replicas_identical, "param_checksum": chks[0],
             "final_losses": loss,
         }
         print(json.dumps(line), flush=True)
@@ -480,8 +585,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gaitk", choices=["gaitk", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="windows per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded CPU sample of the per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=-1, help="windows per step of the CPU arm (default: the GPU arm's batch for "
+                    "--impl reference, shrunk only if the run would exceed a few minutes; 4096 for the gaitk arm's cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the B = 64 .. 32768 sweep of the fused step")
     ap.add_argument("--p2p", type=int, default=0, help="1 = data-parallel exchange by the peer-memory all-reduce kernel gaitk_p2p_allreduce "
                     "(one graph per step); 0 = NCCL all_reduce between two graphs (default: measured 4%% faster at N=2)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step (kernels + the NCCL all-reduce when data-parallel) as one CUDA graph")
@@ -490,6 +597,8 @@ def main():
     ap.add_argument("--dtype", default="tf32", choices=["f32", "tf32"], help="contraction arithmetic of the stream kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaitk" else args.warmup
+    if args.impl == "gaitk" and args.cpu_batch <= 0:
+        args.cpu_batch = 4096
     if args.impl == "reference":
         run_reference(args)
     else:

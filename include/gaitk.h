@@ -242,6 +242,11 @@ int gaitk_fog_prepare_sensor(const double* sens, const int64_t* clip_start, cons
  * and returns the 128 x ncols fp32 accumulator.  Test infrastructure for the descriptor conventions. */
 int gaitk_umma_selftest(const float* A, int nA, const float* B, int nB, const uint32_t* ops, int nops, int ncols,
                         float* D, void* stream);
+/* Same harness for kind::f16 MMAs on bf16 operands (A, B = raw bf16 bit patterns).  accumulate: bit 0 = accumulate into D,
+ * bits 8..15 = column offset of D in units of 8 TMEM columns.  Pins the K-major / MN-major no-swizzle layouts the
+ * split-bf16 stream kernel (stream_kernel_ws.cuh) addresses. */
+int gaitk_umma_selftest_bf16(const uint16_t* A, int nA, const uint16_t* B, int nB, const uint32_t* ops, int nops, int ncols,
+                             float* D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1012,3 +1012,14 @@ extern "C" int gaitk_umma_selftest(const float* A, int nA, const float* B, int n
     LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int gaitk_umma_selftest_bf16(const uint16_t* A, int nA, const uint16_t* B, int nB, const uint32_t* ops, int nops, int ncols,
+                                        float* D, void* stream) {
+    if (!A || !B || !ops || !D || nops < 1 || (ncols != 32 && ncols != 64 && ncols != 128 && ncols != 256)) return fail(GAITK_E_BADARG, "bad argument");
+    const size_t smem = ((size_t)((nA + 511) / 512) * 512 + nB + 128) * sizeof(uint16_t);
+    if (smem > 200 * 1024) return fail(GAITK_E_SHAPE, "operands too large");
+    CUDA_TRY(cudaFuncSetAttribute((const void*)umma_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, nA, B, nB, (const UmmaOp*)ops, nops, ncols, D);
+    LAUNCH_CHECK();
+    return 0;
+}

@@ -48,4 +48,47 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* A, int 
     if (tid < 32) umma::tmem_dealloc(tbase, (uint32_t)ncols);
 }
 
+// Same harness for kind::f16 / bf16 operands: A and B are raw 16-bit images (already bf16 bit patterns, passed as
+// uint16), copied verbatim; pins the K-major and MN-major no-swizzle conventions of the split-bf16 stream kernel.
+__global__ void __launch_bounds__(128) umma_selftest_bf16_kernel(const uint16_t* A, int nA, const uint16_t* B, int nB, const UmmaOp* ops,
+                                                                 int nops, int ncols, float* D /*128 x ncols*/) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint16_t* As = reinterpret_cast<uint16_t*>(sm); uint16_t* Bs = As + ((nA + 511) / 512) * 512;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < nA; i += 128) As[i] = A[i];
+    for (int i = tid; i < nB; i += 128) Bs[i] = B[i];
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+    if (tid < 32) umma::tmem_alloc(&tmem_slot, (uint32_t)ncols);
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    if (tid == 0) {
+        const uint32_t a0 = umma::smem_u32(As), b0 = umma::smem_u32(Bs);
+        for (int i = 0; i < nops; ++i) {
+            const UmmaOp o = ops[i];
+            // bit 31 of `accumulate` = column offset of D in units of 8 columns (bits 8..15)
+            const uint32_t dcol = (o.accumulate >> 8) & 0xffu;
+            umma::mma_bf16(tbase + dcol * 8u, umma::make_desc(a0 + o.a_off, o.a_lbo, o.a_sbo), umma::make_desc(b0 + o.b_off, o.b_lbo, o.b_sbo),
+                           o.idesc, o.accumulate & 1u);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    const uint32_t lane_base = (uint32_t)(tid & ~31) << 16;
+    for (int c = 0; c < ncols; c += 8) {
+        float v[8];
+        umma::ld_x8(tbase + lane_base + c, v);
+        umma::ld_wait();
+        for (int j = 0; j < 8; ++j) D[(size_t)tid * ncols + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tbase, (uint32_t)ncols);
+}
+
 }  // namespace gaitk

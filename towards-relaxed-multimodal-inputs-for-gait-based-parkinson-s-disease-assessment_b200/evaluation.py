@@ -29,39 +29,76 @@ def _ptr_array(ts: Sequence[torch.Tensor]):
     return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
+def streams_are_independent(model) -> bool:
+    """True when stream s's logits depend on input s alone (WearGaitThreeModal, SharedLatent3, LateFusion3 async): only
+    then do the seven zero-filled passes of the reference collapse into one.  Fusion models whose logits couple the
+    streams (LateFusion3 sync feeds the MEAN latent -- zero-input latents included -- through the shared head,
+    weargait_encoders.py:272-279; EarlyFusion3; CheapXAttn3) declare `fuses_streams = True` and are evaluated with one
+    masked pass per mask, exactly as eval_with_mask does."""
+    return not bool(getattr(model, "fuses_streams", False))
+
+
 def _indexed_forward(model, ib: IndexBatch):
     return model.plan().forward(model.flat_params(), list(ib.frames), win_start=list(ib.win_start))
 
 
-def _batches(model, loader, async_mode: bool):
-    """yield (logits[3], ys[3]) per batch; DeviceLoader batches are read from the resident stores by index"""
+def _dense(ib: IndexBatch, win: int):
+    """materialise the (B, T, D) windows of an index batch (fused models go through model.forward)"""
+    out = []
+    for fr, ws in zip(ib.frames, ib.win_start):
+        idx = ws.view(-1, 1) + torch.arange(win, device=ws.device).view(1, -1)
+        out.append(fr[idx].contiguous())
+    return out
+
+
+def _batches(model, loader, async_mode: bool, mask=None):
+    """yield (logits[3], ys[3]) per batch.  mask = None: all streams enabled (one-pass evaluation of independent
+    streams); mask = 3 booleans: disabled inputs are zero-filled and the batch goes through model.forward
+    (forward_batch_masked :360-382).  DeviceLoader batches are read from the resident stores by index."""
+    independent = streams_are_independent(model)
+
+    def run(xs):
+        if mask is not None:
+            xs = [x if u else torch.zeros_like(x) for x, u in zip(xs, mask)]
+        return model(*xs)
+
     if isinstance(loader, DeviceLoader):
         ds = loader.dataset
         st0 = ds.stores[0] if isinstance(ds.stores, tuple) else ds.stores[ds.modalities[0]]
         if hasattr(model, "set_window"):
             model.set_window(st0.win)
         for ib in loader.index_batches():
-            yield _indexed_forward(model, ib), ib.ys
+            if independent and mask is None:
+                yield _indexed_forward(model, ib), ib.ys
+            else:
+                yield run(_dense(ib, st0.win)), ib.ys
         return
     for b in loader:
         if isinstance(b, IndexBatch):
-            yield _indexed_forward(model, b), b.ys
+            if independent and mask is None:
+                yield _indexed_forward(model, b), b.ys
+            else:
+                win = int(getattr(model, "_T", 0) or 0)
+                if not win:
+                    raise _lib.GaitkError("window length unknown for an index batch: call model.set_window(T) first")
+                yield run(_dense(b, win)), b.ys
         elif async_mode:                                    # forward_batch :163-184
             xs = [b[m].cuda().float() for m in _STREAMS]; ys = [b["y"][m].cuda().long() for m in _STREAMS]
-            yield model(*xs), ys
+            yield run(xs), ys
         else:
             xs = [t.cuda().float() for t in b["xs"]]; y = b["y"].cuda().long()
-            yield model(*xs), [y, y, y]
+            yield run(xs), [y, y, y]
 
 
 @torch.no_grad()
-def mask_counts(model, loader, async_mode: bool, criterions: Optional[Sequence] = None):
+def mask_counts(model, loader, async_mode: bool, criterions: Optional[Sequence] = None, mask=None):
     """One pass over ``loader``: int32 (n_batches, 10) hit counts (see gaitk_mask_eval), batch sizes, and -- when
-    criterions are given -- the (n_batches, 3) per-stream losses.  Single device->host read at the end."""
+    criterions are given -- the (n_batches, 3) per-stream losses.  Single device->host read at the end.
+    mask: see _batches (only the counter of that mask is meaningful then)."""
     was_training = model.training
     model.eval()
     L = _lib.lib(); rows, sizes, losses = [], [], []
-    for lg, ys in _batches(model, loader, async_mode):
+    for lg, ys in _batches(model, loader, async_mode, mask):
         lg = [l.contiguous() for l in lg]; ys = [y.contiguous() for y in ys]
         B, K = lg[0].shape
         cnt = torch.zeros(10, dtype=torch.int32, device=lg[0].device)
@@ -95,8 +132,14 @@ def _mask_result(counts, sizes, async_mode, idx, mask):
 def eval_all_masks(model, loader, async_mode: bool) -> Dict[str, object]:
     """:384-389 -- the whole seven-mask table from one pass (sync: accuracy in %, async: dict per enabled stream +
     ``macro_enabled``), same values as calling the reference's eval_with_mask per mask."""
-    counts, sizes, _ = mask_counts(model, loader, async_mode)
-    return {k: _mask_result(counts, sizes, async_mode, i, m) for i, (k, m) in enumerate(MASK_COMBOS.items())}
+    if streams_are_independent(model):
+        counts, sizes, _ = mask_counts(model, loader, async_mode)
+        return {k: _mask_result(counts, sizes, async_mode, i, m) for i, (k, m) in enumerate(MASK_COMBOS.items())}
+    out = {}
+    for i, (k, m) in enumerate(MASK_COMBOS.items()):         # coupled streams: one zero-filled pass per mask (:384-389)
+        counts, sizes, _ = mask_counts(model, loader, async_mode, mask=m)
+        out[k] = _mask_result(counts, sizes, async_mode, i, m)
+    return out
 
 
 def eval_with_mask(model, loader, async_mode: bool, mask, verbose: bool = False):
@@ -107,7 +150,7 @@ def eval_with_mask(model, loader, async_mode: bool, mask, verbose: bool = False)
     names = [k for k, v in MASK_COMBOS.items() if v == mask]
     if not names:                                            # (False, False, False): nothing enabled
         return 0.0 if not async_mode else {"macro_enabled": 0.0}
-    counts, sizes, _ = mask_counts(model, loader, async_mode)
+    counts, sizes, _ = mask_counts(model, loader, async_mode, mask=None if streams_are_independent(model) else mask)
     return _mask_result(counts, sizes, async_mode, list(MASK_COMBOS).index(names[0]), mask)
 
 

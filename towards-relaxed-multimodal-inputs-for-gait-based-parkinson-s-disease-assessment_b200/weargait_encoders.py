@@ -298,6 +298,12 @@ class LateFusion3(_ThreeStreamBase):
                                   "(weargait_train.py:513-524 passes neither use_norm nor use_cosine)")
         self._build(enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized)
 
+    @property
+    def fuses_streams(self) -> bool:
+        """sync: every returned logit is the shared head on the MEAN latent, so masking one input changes all three
+        (weargait_encoders.py:272-279) -- the one-pass mask evaluation does not apply (evaluation.streams_are_independent)"""
+        return bool(self.synchronized)
+
     def forward(self, xw, xi, xm):
         lw, li, lm = self._streams(xw, xi, xm)
         if self.synchronized:
