@@ -54,6 +54,12 @@ extern "C" {
 #define GAITK_SOLVER_MEAN  2      /* no CAGrad: shared grad = mean of the task rows, i.e. torch.stack(losses).mean()
                                      .backward() of step_cagrad_three's plain path (weargait_train.py:244-248); pass
                                      private_mult = 1/n_tasks and max_norm = 0 (that path does not clip)        */
+/* OR-ed into `solver` of gaitk_step_update: diag has GAITK_DIAG_FLOATS entries and diag[GAITK_DIAG_EXCHANGE] is the sticky
+ * status word of the data-parallel exchange (0 ok, -1 a peer never arrived): when it is negative the update leaves
+ * parameters and momentum untouched, so replicas never apply an incomplete gradient sum. */
+#define GAITK_SOLVER_FLAG_CHECK_EXCHANGE 0x100
+#define GAITK_DIAG_FLOATS   24
+#define GAITK_DIAG_EXCHANGE 16
 
 typedef struct gaitk_model_desc {
     int32_t family;               /* GAITK_FAMILY_*                                                   */
@@ -174,7 +180,9 @@ int gaitk_loss_denominators(const int64_t* const* y, const int* counts, int n_st
  * word.  counter: local device word counting completed exchanges (zero at start; the call increments it on the
  * stream).  The kernel publishes this rank's step number, waits for all peers, and sums the gbufs in rank order into
  * the local gsum (gaitk_gbuf_floats floats), which gaitk_step_update then consumes.  Bit-identical on every rank.
- * If a peer does not arrive within ~4 s the step is flagged (diag[15] = -1) instead of hanging the device. */
+ * If a peer does not arrive within ~4 s of SM clocks (GAITK_P2P_TIMEOUT_CYCLES overrides) the step is flagged in the
+ * STICKY status word diag[GAITK_DIAG_EXCHANGE] = -1 (diag: device float[GAITK_DIAG_FLOATS]) instead of hanging the
+ * device; gaitk_step_update called with GAITK_SOLVER_FLAG_CHECK_EXCHANGE then skips the parameter update. */
 int gaitk_p2p_allreduce(gaitk_plan* plan, const float* const* peer_gbuf_dev, uint32_t* const* peer_flag_dev,
                         uint32_t* counter, int rank, int world, float* gsum, float* diag, void* stream);
 
@@ -183,7 +191,8 @@ int gaitk_p2p_allreduce(gaitk_plan* plan, const float* const* peer_gbuf_dev, uin
  * torch.optim.SGD.step weargait_train.py:248,560): on-device Gram matrix, simplex
  * solve, combine, clip, then SGD(momentum, weight decay) on the flat parameter
  * buffer.  Runs identically on every rank after gbuf has been all-reduced.
- * diag (optional, device float[16]): w[3], GTG[9], pre-clip norm, objective, iters. */
+ * diag (optional, device float[16], or float[GAITK_DIAG_FLOATS] with GAITK_SOLVER_FLAG_CHECK_EXCHANGE): w[3], GTG[9],
+ * pre-clip norm, objective, iters, clip factor. */
 int gaitk_step_update(gaitk_plan* plan, float* params, float* momentum, const float* gbuf,
                       uint32_t task_mask, float cagrad_c, float max_norm, float lr, float mom,
                       float weight_decay, float* grads_out /*optional flat*/, float* diag, int solver, void* stream);

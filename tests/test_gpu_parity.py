@@ -887,3 +887,35 @@ def test_peer_memory_exchange_matches_nccl_on_two_gpus(gk):
            "--master-port", "29571", str(ROOT / "tests" / "dist_p2p_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "P2P_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_peer_exchange_timeout_is_sticky_and_skips_the_update(gk, monkeypatch):
+    """a peer that never publishes its step must (a) not hang the device, (b) leave a STICKY failure status
+    that the update kernel does not overwrite, (c) keep parameters and momentum untouched.  One GPU is enough: the
+    'peer' of this world-2 exchange is a flag word nobody writes (no second kernel waits on anything)."""
+    import ctypes as C
+    L = gk.lib(); lib_ = gk._lib
+    monkeypatch.setenv("GAITK_P2P_TIMEOUT_CYCLES", str(1 << 22))          # ~2 ms of SM clocks
+    m = gk.WearGaitThreeModal().cuda(); m.set_window(64)
+    plan = m.plan(); flat = m.flat_params(); before = flat.clone()
+    n = plan.gbuf_floats
+    gb = [torch.randn(n, device="cuda") * 1e-3 for _ in range(2)]
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    peer_g = torch.tensor([g.data_ptr() for g in gb], dtype=torch.int64, device="cuda")
+    peer_f = torch.tensor([flags.data_ptr(), flags.data_ptr() + 4], dtype=torch.int64, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda"); gsum = torch.zeros(n, device="cuda")
+    diag = torch.zeros(lib_.DIAG_FLOATS, device="cuda"); mom = torch.zeros(plan.NP, device="cuda")
+    st = lib_.stream_handle()
+    lib_.check(L.gaitk_p2p_allreduce(plan.handle, peer_g.data_ptr(), peer_f.data_ptr(), counter.data_ptr(), 0, 2, gsum.data_ptr(),
+                                     diag.data_ptr(), st), "p2p")
+    lib_.check(L.gaitk_step_update(plan.handle, flat.data_ptr(), mom.data_ptr(), gsum.data_ptr(), 0b111, 0.5, 1.0, 1e-3, 0.9, 1e-4,
+                                   None, diag.data_ptr(), lib_.SOLVER_SLSQP | lib_.SOLVER_FLAG_CHECK_EXCHANGE, st), "update")
+    torch.cuda.synchronize()
+    assert float(diag[lib_.DIAG_EXCHANGE]) == -1.0
+    assert torch.equal(flat, before) and float(mom.abs().max()) == 0.0
+    # the same update with a healthy status does move the parameters
+    diag.zero_()
+    lib_.check(L.gaitk_step_update(plan.handle, flat.data_ptr(), mom.data_ptr(), gsum.data_ptr(), 0b111, 0.5, 1.0, 1e-3, 0.9, 1e-4,
+                                   None, diag.data_ptr(), lib_.SOLVER_SLSQP | lib_.SOLVER_FLAG_CHECK_EXCHANGE, st), "update")
+    torch.cuda.synchronize()
+    assert not torch.equal(flat, before)

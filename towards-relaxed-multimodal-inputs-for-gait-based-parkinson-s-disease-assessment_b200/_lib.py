@@ -19,6 +19,7 @@ FAMILY_WEARGAIT, FAMILY_FOG = 0, 1
 DTYPE_F32, DTYPE_TF32 = 0, 1
 SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN = 0, 1, 2
 DENOM_FLOATS = 32           # GAITK_DENOM_FLOATS
+SOLVER_FLAG_CHECK_EXCHANGE, DIAG_FLOATS, DIAG_EXCHANGE = 0x100, 24, 16
 
 EXPORTS = [
     "gaitk_version", "gaitk_last_error", "gaitk_plan_create", "gaitk_plan_destroy", "gaitk_param_count",

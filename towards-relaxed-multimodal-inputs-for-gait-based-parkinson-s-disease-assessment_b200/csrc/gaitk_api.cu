@@ -12,11 +12,9 @@
 #include <vector>
 
 #include "../../include/gaitk.h"
-#include "stream_kernel.cuh"
-#include "stream_kernel_tc.cuh"
-#ifdef GAITK_WITH_TC2        // two-threads-per-row experiment (slower): opt-in build
-#include "stream_kernel_tc2.cuh"
-#endif
+#include "stream_common.cuh"
+#include "stream_tc_plan.h"
+#include "stream_dispatch.h"
 #include "update_kernels.cuh"
 #include "umma_selftest.cuh"
 
@@ -35,8 +33,6 @@ static int fail(int code, const char* fmt, ...) {
 struct ParamInfo {
     std::string name; long long off; int numel; int group; int dims[4]; int shared_off;
 };
-typedef void (*StreamKernelFn)(const StreamArgs, const SmemPlan);
-typedef void (*StreamKernelTcFn)(const StreamArgs, const TcPlan);
 
 struct StreamPlan {
     int enc, CIN, T_in, T, W, rows_in, rows, halo, RBi, RB, pool_sensor;
@@ -67,62 +63,6 @@ static int add_param(gaitk_plan* pl, const std::string& name, int group, int d0,
     pl->params.push_back(p);
     return (int)pl->params.size() - 1;
 }
-
-// kernel instantiations -------------------------------------------------------------------
-template <class Cfg> static StreamKernelFn kfn() { return &stream_kernel<Cfg>; }
-
-struct KernelKey { int enc, CIN, KT1, H, C, S, NFL, PROJ; };
-static StreamKernelFn find_kernel(const KernelKey& k) {
-#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
-    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
-        return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
-#define GK_CASE_P(e_, ci_, kt_, h_, c_, s_, nfl_, p_) \
-    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == p_) \
-        return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_, p_>>();
-    // SharedLatent3 (weargait_encoders.py:284-322): per-stream Linear(12 -> proj_ch=16) before the backbone
-    GK_CASE_P(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4, 16)
-    GK_CASE_P(ENC_INSOLE, 13, 5, 24, 12, 16, 4, 16)
-    GK_CASE_P(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4, 16)
-    // WearGait defaults (weargait_train.py:655-673): C=12, H=24, S=16, bdim=8
-    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
-    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
-    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
-    // FoG (configs.py:17-31) and FBG (:2-16)
-    GK_CASE(ENC_LINEAR_LN_RELU, 21, 1, 0, 6, 16, 4)
-    GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)
-    GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
-    GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
-#undef GK_CASE
-#undef GK_CASE_P
-    return nullptr;
-}
-
-template <class Cfg, bool FX> static StreamKernelTcFn kfn_tc() { return &stream_kernel_tc<Cfg, FX>; }
-static StreamKernelTcFn find_kernel_tc(const KernelKey& k, bool fixed_geometry) {
-#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
-    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
-        return fixed_geometry ? kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>, true>() : kfn_tc<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>, false>();
-    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
-    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
-    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
-#undef GK_CASE
-    return nullptr;
-}
-
-#ifdef GAITK_WITH_TC2
-template <class Cfg> static StreamKernelTcFn kfn_tc2() { return &stream_kernel_tc2<Cfg>; }
-// two-threads-per-row variant: compile-time geometry T = 64, W = 2, bdim = 8
-static StreamKernelTcFn find_kernel_tc2(const KernelKey& k) {
-#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
-    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
-        return kfn_tc2<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
-    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
-    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
-    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
-#undef GK_CASE
-    return nullptr;
-}
-#endif
 
 static int round_rb(int rows, int halo) {          // rows per chunk, == 1 (mod 8): conflict-free chunk planes
     int rb = rows + 2 * halo;
@@ -582,7 +522,8 @@ extern "C" int gaitk_step_update(gaitk_plan* pl, float* params, float* momentum,
     }
     U.params = params; U.momentum = momentum; U.gbuf = gbuf; U.grads_out = grads_out; U.diag = diag;
     U.task_mask = task_mask; U.n_tasks_max = pl->n_streams; U.alpha = cagrad_c; U.max_norm = max_norm;
-    U.lr = lr; U.mom = mom; U.wd = weight_decay; U.do_sgd = do_sgd ? 1 : 0; U.solver = solver;
+    U.lr = lr; U.mom = mom; U.wd = weight_decay; U.do_sgd = do_sgd ? 1 : 0; U.solver = solver & 0xff;
+    U.check_exchange = (solver & GAITK_SOLVER_FLAG_CHECK_EXCHANGE) ? 1 : 0;
     cagrad_update_kernel<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(U);
     LAUNCH_CHECK();
     return 0;
@@ -594,6 +535,8 @@ extern "C" int gaitk_p2p_allreduce(gaitk_plan* pl, const float* const* peer_gbuf
     if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(GAITK_E_BADARG, "bad rank / world size");
     P2PArgs Q; Q.peer_gbuf = peer_gbuf_dev; Q.peer_flag = (unsigned* const*)peer_flag_dev; Q.counter = counter;
     Q.gsum = gsum; Q.n = (int)gaitk_gbuf_floats(pl); Q.rank = rank; Q.world = world; Q.diag = diag;
+    Q.timeout_cycles = 8ll << 30;                              // ~4 s of SM clocks
+    if (const char* e = getenv("GAITK_P2P_TIMEOUT_CYCLES")) { const long long v = atoll(e); if (v > 0) Q.timeout_cycles = v; }
     const int grid = std::max(1, std::min(16, (Q.n + P2P_THREADS * 4 - 1) / (P2P_THREADS * 4)));
     p2p_allreduce_kernel<<<grid, P2P_THREADS, 0, (cudaStream_t)stream>>>(Q);
     LAUNCH_CHECK();

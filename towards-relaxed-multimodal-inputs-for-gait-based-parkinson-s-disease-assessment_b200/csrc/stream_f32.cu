@@ -1,0 +1,34 @@
+// stream_f32.cu -- instantiations of the fp32 (FFMA) stream kernel
+#include "stream_kernel.cuh"
+#include "stream_dispatch.h"
+
+namespace gaitk {
+// kernel instantiations -------------------------------------------------------------------
+template <class Cfg> static StreamKernelFn kfn() { return &stream_kernel<Cfg>; }
+
+StreamKernelFn find_kernel(const KernelKey& k) {
+#define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
+        return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
+#define GK_CASE_P(e_, ci_, kt_, h_, c_, s_, nfl_, p_) \
+    if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == p_) \
+        return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_, p_>>();
+    // SharedLatent3 (weargait_encoders.py:284-322): per-stream Linear(12 -> proj_ch=16) before the backbone
+    GK_CASE_P(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4, 16)
+    GK_CASE_P(ENC_INSOLE, 13, 5, 24, 12, 16, 4, 16)
+    GK_CASE_P(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4, 16)
+    // WearGait defaults (weargait_train.py:655-673): C=12, H=24, S=16, bdim=8
+    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
+    GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
+    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
+    // FoG (configs.py:17-31) and FBG (:2-16)
+    GK_CASE(ENC_LINEAR_LN_RELU, 21, 1, 0, 6, 16, 4)
+    GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)
+    GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
+    GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
+#undef GK_CASE
+#undef GK_CASE_P
+    return nullptr;
+}
+
+}  // namespace gaitk

@@ -20,6 +20,7 @@
 #pragma once
 #include "stream_common.cuh"
 #include "umma.cuh"
+#include "stream_tc_plan.h"
 
 namespace gaitk {
 
@@ -27,12 +28,6 @@ namespace gaitk {
 // (two CTAs at most), the single-conv encoders fit three
 template <class Cfg> struct TcMinBlocks { static constexpr int value = Cfg::ENC == ENC_INSOLE ? 2 : 3; };
 
-struct TcPlan {
-    int X, HA, D1, XH, D, F, RSTD, Z;
-    int W1B, B1, W2B, B2, W2D, LNG, LNB, WBB, BB, WBD, HW, HB, HNG, HNB, INW;
-    int DP, BINS, STAGE, STG, P;
-    int total;
-};
 
 __device__ __forceinline__ void mma_sync_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

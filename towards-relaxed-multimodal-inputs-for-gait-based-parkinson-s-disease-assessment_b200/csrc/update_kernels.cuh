@@ -16,6 +16,11 @@ namespace gaitk {
 constexpr int MAX_SEG = 16;
 constexpr int MAX_PARAMS = 40;
 constexpr int MAXT = 3;
+// diag[16]: STICKY exchange status of the data-parallel step -- 0 = ok, -1 = a peer never arrived.  Written only by the
+// exchange kernel; cagrad_update_kernel reads it and refuses to touch parameters / momentum after a failed exchange
+// (replicas must not silently diverge); the host resets it (FusedTrainStep.reset_exchange_status).
+constexpr int DIAG_EXCHANGE = 16;
+constexpr int DIAG_FLOATS = 24;
 
 // one stream-local gradient segment and where it goes
 struct Seg { int src, len, shared_off, param_off; };     // shared_off >= 0 -> G column; else private
@@ -76,6 +81,7 @@ struct UpdateArgs {
     unsigned task_mask; int n_tasks_max;
     float alpha, max_norm, lr, mom, wd;
     int do_sgd, solver;
+    int check_exchange;                // diag has DIAG_FLOATS entries and diag[DIAG_EXCHANGE] gates the update
 };
 
 // single CTA: Gram -> solve -> combine -> clip -> (optional) SGD over the flat parameter buffer.
@@ -90,6 +96,8 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
     __shared__ int nt_s;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wrp = tid >> 5;
     const float* G = U.gbuf; const float* PG = U.gbuf + (size_t)MAXT * U.P;
+    // a failed data-parallel exchange (a peer never published its gradients) must not be applied: gbuf is incomplete
+    if (U.check_exchange && U.diag && U.diag[DIAG_EXCHANGE] < 0.f) return;
     if (tid == 0) {
         int n = 0;
         for (int t = 0; t < U.n_tasks_max; ++t) if (U.task_mask & (1u << t)) tl[n++] = t;
@@ -212,7 +220,9 @@ struct P2PArgs {
     unsigned* const* peer_flag;        // device array [world]: flag word of every rank
     const unsigned* counter;           // local: number of completed exchanges (step = counter + 1)
     float* gsum; int n; int rank, world; float* diag;
+    long long timeout_cycles;          // give up waiting for a peer after this many SM clocks
 };
+
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
@@ -235,12 +245,12 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_kernel(const P2PArg
         // step numbers only grow; the comparison is wrap-safe.  A peer that never arrives (crashed rank) must not hang
         // the GPU: give up after ~4 s of SM clocks and flag the step as failed (diag[15] = -1).
         while ((int)(ld_acquire_sys(f) - step) < 0) {
-            if (clock64() - t0 > (8ll << 30)) { ok_s = 0; break; }
+            if (clock64() - t0 > Q.timeout_cycles) { ok_s = 0; break; }
             __nanosleep(64);
         }
     }
     __syncthreads();
-    if (!ok_s && Q.diag && blockIdx.x == 0 && threadIdx.x == 0) Q.diag[15] = -1.0f;
+    if (!ok_s && Q.diag && threadIdx.x == 0) Q.diag[DIAG_EXCHANGE] = -1.0f;       // every CTA that saw it (same value)
     // all remote loads of an element are issued before the first one is consumed (rank order is kept in the sum)
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Q.n; e += gridDim.x * blockDim.x) {
         float s = 0.f;

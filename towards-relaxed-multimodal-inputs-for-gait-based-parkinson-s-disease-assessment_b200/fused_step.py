@@ -47,7 +47,7 @@ class FusedTrainStep:
         if self._gbuf is None or self._gbuf.numel() != plan.gbuf_floats or self._gbuf.device != dev:
             self._gbuf = torch.zeros(plan.gbuf_floats, dtype=torch.float32, device=dev)
             self._denom = torch.ones(_lib.DENOM_FLOATS, dtype=torch.float32, device=dev)
-            self._diag = torch.zeros(16, dtype=torch.float32, device=dev)
+            self._diag = torch.zeros(_lib.DIAG_FLOATS, dtype=torch.float32, device=dev)
         if self._mom is None or self._mom.numel() != plan.NP or self._mom.device != dev:
             self._mom = torch.zeros(plan.NP, dtype=torch.float32, device=dev)
         if self._red is None or self._p2p is None:
@@ -111,6 +111,15 @@ class FusedTrainStep:
     def diag(self):
         return self._diag
 
+    def exchange_failed(self) -> bool:
+        """True once a peer failed to arrive in the peer-memory exchange (sticky; the updates since then were skipped).
+        Reads one float from the device."""
+        return self._diag is not None and float(self._diag[_lib.DIAG_EXCHANGE]) < 0.0
+
+    def reset_exchange_status(self):
+        if self._diag is not None:
+            self._diag[_lib.DIAG_EXCHANGE] = 0.0
+
     # ------------------------------------------------------------------ step
     def _step_impl(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], *, enabled: Sequence[bool] = None,
              tasks: Sequence[bool] = None, ys_global: Optional[Sequence[torch.Tensor]] = None,
@@ -146,6 +155,11 @@ class FusedTrainStep:
         B = plan._check_inputs(xs, win_start)
         enabled_mask = 0b111 if enabled is None else sum(1 << s for s, e in enumerate(enabled) if e)
         task_mask = ((1 << n) - 1) if tasks is None else sum(1 << s for s, e in enumerate(tasks) if e)
+        if ys_global is None and self._distributed():
+            # each rank normalising by its LOCAL sum of w[y] would make the all-reduced sum `world` times the global-mean
+            # gradient (and break class-weighted means outright): the global label vectors are part of the contract
+            raise _lib.GaitkError("data-parallel step: pass ys_global (the label vectors of the WHOLE global batch, one per "
+                                  "stream) so that the weighted-mean denominators are global; see FusedTrainStep.step")
         yg = ys if ys_global is None else ys_global
         st = stream_handle()
         counts = (C.c_int * n)(*[int(y.numel()) for y in yg])
@@ -176,7 +190,7 @@ class FusedTrainStep:
         check(lib().gaitk_step_update(plan.handle, flat.data_ptr() if update else None, mom.data_ptr() if update else None,
                                       gbuf.data_ptr(), task_mask, self.cagrad_c, self.max_norm, self.lr, self.momentum,
                                       self.weight_decay, None if grads_out is None else grads_out.data_ptr(),
-                                      diag.data_ptr(), self.solver, st), "gaitk_step_update")
+                                      diag.data_ptr(), self.solver | _lib.SOLVER_FLAG_CHECK_EXCHANGE, st), "gaitk_step_update")
         return self.stats()
 
     def step(self, xs, ys, **kw):
@@ -193,10 +207,14 @@ class FusedTrainStep:
         dist_mode = self._distributed()
         p2p = self.p2p and dist_mode and self._p2p_state(self.model.plan()) is not None
         par = (self._p2p["steps"] & 1) if p2p else 0
+        # everything the captured launches bake in: buffer addresses, batch size, and -- BY VALUE -- the loss descriptors
+        # (class weights after a DRW update, margins, scale, NaN flag) and every scalar option of the step
+        K = self.model.plan().K
+        desc_bytes = b"".join(bytes(criterion_spec(c, K)[0]) for c in self.criterions)
         key = (ptrs(xs), ptrs(ys), ptrs(kw.get("ys_global")), ptrs(kw.get("win_start")), tuple(kw.get("enabled") or ()),
                tuple(kw.get("tasks") or ()), kw.get("update", True), xs[0].shape[0] if kw.get("win_start") is None else kw["win_start"][0].numel(),
-               tuple(id(c.weight) if getattr(c, "weight", None) is not None else 0 for c in self.criterions),
-               self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c, dist_mode, p2p, par)
+               desc_bytes, self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c,
+               self.max_norm, self.private_mult, self.solver, self.consistency_lambda, self.dtype, dist_mode, p2p, par)
         g = self._graphs.get(key)
         if g is None:
             self._step_impl(xs, ys, **kw)                      # this call's step, eagerly (also allocates buffers / workspace)
