@@ -329,7 +329,7 @@ def run_gpu(args):
         c.consume_rng = False
     ns = len(names)
     bytes_per_unit = sum(t * d for t, d in dims) * 4 + 8
-    dtype_id = gaitk.DTYPE_TF32 if wl["dtype"] == "tf32" else gaitk.DTYPE_F32
+    dtype_id = {"tf32": gaitk.DTYPE_TF32, "bf16x3": gaitk.DTYPE_BF16X3}.get(wl["dtype"], gaitk.DTYPE_F32)
     step = gaitk.FusedTrainStep(model, crit, cagrad_c=wl["cagrad_c"], max_norm=1.0, lr=1e-3, momentum=0.9, weight_decay=1e-4,
                                 private_mult=wl["private_mult"], process_group=None if world > 1 else False, dtype=dtype_id,
                                 use_graph=bool(args.graph), p2p=bool(args.p2p) and world > 1)
@@ -482,7 +482,7 @@ def run_gpu(args):
         s_ = names.index(dom)
         alg = B * (dims[s_][0] * dims[s_][1] * 4 + 8)
         ach = alg / (per_stream[dom] * 1e-3) / 1e9
-        kname = "stream_kernel_tc" if wl["dtype"] == "tf32" else "stream_kernel"
+        kname = {"tf32": "stream_kernel_tc", "bf16x3": "stream_kernel_ws"}.get(wl["dtype"], "stream_kernel")
         # DRAM traffic / tensor-pipe utilisation of the same kernel from the committed `ncu --set full` capture
         # (profiles/r1_ncu_full_final.json, made by scratch/ncu_summary.py); per launch, scaled to this batch
         traffic = tensor_pct = None; traffic_src = None
@@ -594,7 +594,9 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="replay the step (kernels + the NCCL all-reduce when data-parallel) as one CUDA graph")
     ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog"],
                     help="default = BASELINE.json configs[1]; the others are extra report lines")
-    ap.add_argument("--dtype", default="tf32", choices=["f32", "tf32"], help="contraction arithmetic of the stream kernels")
+    ap.add_argument("--dtype", default="bf16x3", choices=["f32", "tf32", "bf16x3"],
+                    help="contraction arithmetic of the stream kernels: bf16x3 = split-bf16 operands (hi + lo, three tcgen05 passes, "
+                         "fp32 accumulate; the warp-specialised kernel), tf32 = round-1 tcgen05 + mma.sync kernel, f32 = FFMA")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaitk" else args.warmup
     if args.impl == "gaitk" and args.cpu_batch <= 0:

@@ -47,6 +47,8 @@ extern "C" {
 /* arithmetic of the conv/linear contractions */
 #define GAITK_DTYPE_F32  0        /* fp32 FFMA, parity 1e-5                           */
 #define GAITK_DTYPE_TF32 1        /* tensor-core tf32 inputs, fp32 accumulate, 1e-3   */
+#define GAITK_DTYPE_BF16X3 2      /* split bf16 (hi + lo) operands, three tcgen05 passes, fp32 accumulate: operand error 2^-16;
+                                     warp-specialised kernel, weight gradients on tcgen05 as well (stream_kernel_ws.cuh) */
 
 /* simplex solver inside CAGrad */
 #define GAITK_SOLVER_SLSQP 0      /* restatement of SciPy SLSQP's iteration (reference parity; default) */

@@ -919,3 +919,101 @@ def test_peer_exchange_timeout_is_sticky_and_skips_the_update(gk, monkeypatch):
                                    None, diag.data_ptr(), lib_.SOLVER_SLSQP | lib_.SOLVER_FLAG_CHECK_EXCHANGE, st), "update")
     torch.cuda.synchronize()
     assert not torch.equal(flat, before)
+
+
+# ------------------------------------------------------------------------------------------------ split-bf16 (bf16x3) path
+BF16X3_CASES = ["wg_sync_gcl", "wg_sync_gcl_drw", "wg_async_ce", "wg_async_gcl", "wg_sync_classwt_nc"]
+
+
+@pytest.mark.parametrize("name", BF16X3_CASES)
+def test_weargait_bf16x3_path_matches_reference_goldens(gk, name):
+    """The benched arithmetic (warp-specialised all-tcgen05 kernel, split-bf16 operands) DIRECTLY against the reference
+    goldens at B = 8: north_star's reduced-precision bar, 1e-3 relative (norm-wise), on logits, losses, the per-task shared
+    gradient matrix G, EVERY private gradient and the parameters after each of the three steps."""
+    g = load_golden(name); meta = g["meta"]
+    m = wg_model(gk, g); m.compute_dtype = gk.DTYPE_BF16X3
+    step = gk.FusedTrainStep(m, wg_criteria(gk, meta), cagrad_c=meta["alpha"], private_mult=2.0, dtype=gk.DTYPE_BF16X3)
+    for st in range(meta["steps"]):
+        i = st % 2
+        xs = [dev(g[f"x{i}_{j}"]) for j in range(3)]; ys = [dev(g[f"y{i}_{j}"]) for j in range(3)]
+        plan = m.set_window(xs[0].shape[1]).plan()
+        ref = sub(g, f"s{st}")
+        if st == 0:
+            with torch.no_grad():
+                out = m(*xs)                                  # forward-only mode of the kernel
+            assert relerr(torch.stack(out).cpu().numpy(), ref["logits"]) < 1e-4
+        gout = torch.zeros(plan.NP, device="cuda")
+        lg = [torch.zeros(xs[0].shape[0], plan.K, device="cuda") for _ in range(3)]
+        loss, correct = step.step(xs, ys, grads_out=gout, logits_out=lg)
+        assert relerr(torch.stack(lg).cpu().numpy(), ref["logits"]) < 1e-4, relerr(torch.stack(lg).cpu().numpy(), ref["logits"])
+        assert relerr(loss.cpu().numpy(), ref["losses"]) < 1e-4
+        G = step._gbuf[:3 * plan.P].view(3, plan.P).t().cpu().numpy()
+        assert relerr(G, ref["G"]) < 1e-3, ("G", relerr(G, ref["G"]))
+        got = grads_by_name(plan, gout)
+        for k, v in ref.items():
+            if k.startswith("grad:") and k[5:] in got:
+                grp = next(p.group for p in plan.params if p.name == k[5:])
+                if grp > 0:
+                    assert relerr(got[k[5:]], v) < 1e-3, (st, k, relerr(got[k[5:]], v))
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 2e-5, f"step {st} param {k[6:]}")
+
+
+@pytest.mark.parametrize("B,sync", [(64, True), (4097, True), (333, False)])
+def test_bf16x3_path_vs_oracle_at_reference_and_large_batch(gk, B, sync):
+    """B = 64 is the reference's default batch (weargait_train.py:661); 4097 = ragged last tile over many CTAs and all
+    groups; async = three heads / three label vectors.  Gradients against the CPU oracle, 1e-3 norm-wise per tensor."""
+    import gait_oracle as O
+    torch.manual_seed(3)
+    m = gk.WearGaitThreeModal(synchronized=sync).cuda()
+    state = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    xs, y = O.synth_weargait_batch(B, seed=9)
+    r = np.random.default_rng(1)
+    ys = [y, y, y] if sync else [y, r.permutation(y), r.permutation(y)]
+    counts = [[40, 90], [55, 60], [20, 30]]
+    crit = [gk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in counts]
+    step = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, dtype=gk.DTYPE_BF16X3, process_group=False)
+    plan = m.set_window(64).plan()
+    gout = torch.zeros(plan.NP, device="cuda")
+    loss, correct = step.step([dev(x) for x in xs], [dev(v) for v in ys], grads_out=gout, update=False)
+    p = O.canonical_params(state, sync)
+    ex = O.weargait_train_step(p, {}, [torch.from_numpy(x) for x in xs], [torch.from_numpy(v) for v in ys],
+                               synchronized=sync, wm="gcl", counts=counts, alpha=0.5)
+    assert relerr(loss.cpu().numpy(), ex["losses"]) < 1e-4
+    ref_correct = [int((l.argmax(1) == torch.from_numpy(v)).sum()) for l, v in zip(ex["logits"], ys)]
+    assert np.abs(correct.cpu().numpy().round().astype(int) - np.array(ref_correct)).max() <= 1 + B // 2000
+    G = step._gbuf[:3 * plan.P].view(3, plan.P).t().cpu().numpy()
+    Gref = ex["G"].detach().numpy()
+    assert relerr(G, Gref) < 1e-3, relerr(G, Gref)
+    got = grads_by_name(plan, gout)
+    for k, v in ex["grads"].items():
+        if k in got and v is not None:
+            grp = next(q.group for q in plan.params if q.name == k)
+            if grp > 0:
+                assert relerr(got[k], v.detach().numpy()) < 1e-3, (k, relerr(got[k], v.detach().numpy()))
+
+
+def test_bf16x3_resident_gather_and_masks(gk):
+    """win_start gather (aligned and unaligned windows), masked streams (zero input) and dropped tasks through the
+    warp-specialised kernel equal the fp32 path on the same inputs."""
+    import gait_oracle as O
+    torch.manual_seed(4)
+    m = gk.WearGaitThreeModal().cuda()
+    B = 77
+    xs, y = O.synth_weargait_batch(B + 3, seed=21)
+    stores = [dev(np.ascontiguousarray(x.reshape(-1, x.shape[2]))) for x in xs]
+    starts = dev((np.arange(B) * 64 + np.arange(B) % 3).astype(np.int64))       # odd starts -> unaligned windows
+    yv = dev(y[:B])
+    crit = [gk.GCLLoss(cls_num_list=[40, 60], m=0.2, s=25, noise_mul=0.0) for _ in range(3)]
+    plan = m.set_window(64).plan()
+    res = {}
+    for dt in (gk.DTYPE_F32, gk.DTYPE_BF16X3):
+        st = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, dtype=dt, process_group=False)
+        gout = torch.zeros(plan.NP, device="cuda")
+        loss, _ = st.step(stores, [yv] * 3, win_start=[starts] * 3, enabled=(True, False, True), tasks=(True, False, True),
+                          grads_out=gout, update=False)
+        res[dt] = (loss.cpu().numpy(), gout.cpu().numpy())
+    assert relerr(res[gk.DTYPE_BF16X3][0], res[gk.DTYPE_F32][0]) < 1e-4
+    assert relerr(res[gk.DTYPE_BF16X3][1], res[gk.DTYPE_F32][1]) < 1e-3

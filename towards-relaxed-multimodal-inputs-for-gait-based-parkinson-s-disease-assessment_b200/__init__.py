@@ -1,7 +1,7 @@
 """gaitk -- B200 (sm_100a) implementation of the gait training hot path behind the reference's own
 module API.  See DESIGN.md / INTEGRATION.md at the repository root."""
 from . import _lib
-from ._lib import GaitkError, lib, DTYPE_F32, DTYPE_TF32, SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN
+from ._lib import GaitkError, lib, DTYPE_F32, DTYPE_TF32, DTYPE_BF16X3, SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN
 from .plan import Plan, FlatParamModule
 from .weargait_encoders import WearGaitThreeModal, LateFusion3, SharedLatent3
 from .feature_encoder import MultiModalMultiTaskModel, SensorModalityModel, SkelModalityModel

@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ.get("GAITK_LIB", _HERE / "libgaitk.so"))
 
 MAX_STREAMS, MAX_CLASSES = 3, 4
 FAMILY_WEARGAIT, FAMILY_FOG = 0, 1
-DTYPE_F32, DTYPE_TF32 = 0, 1
+DTYPE_F32, DTYPE_TF32, DTYPE_BF16X3 = 0, 1, 2
 SOLVER_SLSQP, SOLVER_EXACT, SOLVER_MEAN = 0, 1, 2
 DENOM_FLOATS = 32           # GAITK_DENOM_FLOATS
 SOLVER_FLAG_CHECK_EXCHANGE, DIAG_FLOATS, DIAG_EXCHANGE = 0x100, 24, 16

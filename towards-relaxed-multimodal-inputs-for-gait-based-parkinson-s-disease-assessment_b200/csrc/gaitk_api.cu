@@ -41,6 +41,7 @@ struct StreamPlan {
     SmemPlan sp; GradOff go; int NGP; size_t smem_bytes; int ctas_per_sm;
     StreamKernelTcFn fn_tc; TcPlan tp; size_t smem_tc; int ctas_tc;      // tensor-core variant (nullptr when unavailable)
     int tc_threads;                                                    // 128 (one thread per row) or 256 (two per row)
+    WsKernel ws; int has_ws;                                           // warp-specialised split-bf16 kernel (GAITK_DTYPE_BF16X3)
     int p_w1, p_b1, p_w2, p_b2, p_wsk, p_bsk, p_lng, p_lnb, p_hng, p_hnb, p_hw, p_hb, p_wp, p_bp;   // param indices (-1 = none)
     int nseg; Seg seg[MAX_SEG];
 };
@@ -160,6 +161,12 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
         if (f2) { sp.fn_tc = f2; sp.tc_threads = NT2; }
     }
 #endif
+    // ---- warp-specialised split-bf16 variant (all contractions on tcgen05): WearGait default geometry, plain linear head
+    sp.has_ws = 0;
+    if (fixed_geo && !d.use_norm && !d.use_cosine && find_kernel_ws(key, d.num_classes, &sp.ws)) {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)sp.ws.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.ws.smem));
+        sp.has_ws = 1;
+    }
     if (sp.fn_tc) {
         CUDA_TRY(cudaFuncSetAttribute((const void*)sp.fn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_tc));
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate TMEM although
@@ -303,6 +310,13 @@ extern "C" int gaitk_stream_geometry(const gaitk_plan* p, int s, int dtype, int*
     const StreamPlan& sp = p->st[s];
     const bool tc = dtype == GAITK_DTYPE_TF32;
     if (tc && !sp.fn_tc) return fail(GAITK_E_DTYPE, "no tensor-core kernel for this stream");
+    if (dtype == GAITK_DTYPE_BF16X3) {
+        if (!sp.has_ws) return fail(GAITK_E_DTYPE, "no split-bf16 kernel for this stream");
+        if (ctas_per_sm) *ctas_per_sm = 1;
+        if (windows_per_tile) *windows_per_tile = 2 * sp.ws.groups;      // tiles in flight per CTA x windows per tile
+        if (smem_bytes) *smem_bytes = (size_t)sp.ws.smem;
+        return 0;
+    }
     if (ctas_per_sm) *ctas_per_sm = tc ? sp.ctas_tc : sp.ctas_per_sm;
     if (windows_per_tile) *windows_per_tile = sp.W;
     if (smem_bytes) *smem_bytes = tc ? sp.smem_tc : sp.smem_bytes;
@@ -324,11 +338,18 @@ extern "C" int gaitk_param_info(const gaitk_plan* p, int index, char* name, size
 
 static int stream_grid(const gaitk_plan* pl, const StreamPlan& sp, int B, int dtype = GAITK_DTYPE_F32) {
     const int ntiles = (B + sp.W - 1) / sp.W;
+    if (dtype == GAITK_DTYPE_BF16X3)                     // one persistent CTA per SM, `groups` tiles in flight in each
+        return std::max(1, std::min((ntiles + sp.ws.groups - 1) / sp.ws.groups, pl->sm_count));
     const int per_sm = dtype == GAITK_DTYPE_TF32 ? sp.ctas_tc : sp.ctas_per_sm;
     return std::max(1, std::min(ntiles, pl->sm_count * per_sm));
 }
 static int check_dtype(const gaitk_plan* pl, int dtype) {
     if (dtype == GAITK_DTYPE_F32) return 0;
+    if (dtype == GAITK_DTYPE_BF16X3) {
+        for (int s = 0; s < pl->n_streams; ++s)
+            if (!pl->st[s].has_ws) return fail(GAITK_E_DTYPE, "split-bf16 (bf16x3) kernels exist for WearGait C=12/S=16/T=64 with a plain linear head; stream %d has none", s);
+        return 0;
+    }
     if (dtype != GAITK_DTYPE_TF32) return fail(GAITK_E_DTYPE, "unknown dtype %d", dtype);
     for (int s = 0; s < pl->n_streams; ++s)
         if (!pl->st[s].fn_tc) return fail(GAITK_E_DTYPE, "tensor-core (tf32) kernels exist for WearGait C=12/S=16 with 128-row tiles; stream %d has none", s);
@@ -366,7 +387,8 @@ static void fill_args(const gaitk_plan* pl, int s, const float* params, const fl
 
 static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int grid, cudaStream_t st, int dtype = GAITK_DTYPE_F32) {
     const StreamPlan& sp = pl->st[s];
-    if (dtype == GAITK_DTYPE_TF32) sp.fn_tc<<<grid, sp.tc_threads, sp.smem_tc, st>>>(a, sp.tp);
+    if (dtype == GAITK_DTYPE_BF16X3) sp.ws.fn<<<grid, sp.ws.threads, sp.ws.smem, st>>>(a);
+    else if (dtype == GAITK_DTYPE_TF32) sp.fn_tc<<<grid, sp.tc_threads, sp.smem_tc, st>>>(a, sp.tp);
     else sp.fn<<<grid, NT, sp.smem_bytes, st>>>(a, sp.sp);
     LAUNCH_CHECK();
     return 0;
