@@ -259,6 +259,10 @@ int gaitk_umma_selftest(const float* A, int nA, const float* B, int nB, const ui
 int gaitk_umma_selftest_bf16(const uint16_t* A, int nA, const uint16_t* B, int nB, const uint32_t* ops, int nops, int ncols,
                              float* D, void* stream);
 
+/* Cost model probe: issues the op list `reps` times from one thread (kind::f16, all accumulating), returns SM clocks
+ * {first issue -> completion, issue only} in cycles[2] (device int64).  Design evidence for DESIGN.md. */
+int gaitk_umma_bench(const uint32_t* ops, int nops, int reps, int ncols, int smem_bytes, int64_t* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

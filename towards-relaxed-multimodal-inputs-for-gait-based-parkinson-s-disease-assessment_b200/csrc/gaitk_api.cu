@@ -988,3 +988,11 @@ extern "C" int gaitk_umma_selftest_bf16(const uint16_t* A, int nA, const uint16_
     LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int gaitk_umma_bench(const uint32_t* ops, int nops, int reps, int ncols, int smem_bytes, int64_t* cycles, void* stream) {
+    if (!ops || !cycles || nops < 1 || reps < 1 || smem_bytes < 1024 || smem_bytes > 200 * 1024) return fail(GAITK_E_BADARG, "bad argument");
+    CUDA_TRY(cudaFuncSetAttribute((const void*)umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    umma_bench_kernel<<<1, 128, smem_bytes, (cudaStream_t)stream>>>((const UmmaOp*)ops, nops, reps, ncols, smem_bytes, (long long*)cycles);
+    LAUNCH_CHECK();
+    return 0;
+}

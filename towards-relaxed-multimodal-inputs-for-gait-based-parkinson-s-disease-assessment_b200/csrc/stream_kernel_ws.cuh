@@ -1,11 +1,10 @@
 // stream_kernel_ws.cuh -- warp-specialised, all-tcgen05 fused stream kernel ("GAITK_DTYPE_BF16X3"), WearGait encoders.
 //
 // One persistent CTA per SM.  G independent 128-row tiles ("groups", 4 row warps each, thread = row) are in flight at
-// once and share ONE copy of the weights, ONE TMEM allocation and three service warps:
-//
-//   MMA-A   issues the latency-critical MMAs (forward and data-gradient convolutions) for all groups
-//   MMA-B   issues the weight-gradient / bias-gradient MMAs, which nobody waits for until a buffer is reused
-//   LOAD    TMA bulk copies (cp.async.bulk) of the next tile's windows + labels, per group
+// once and share ONE copy of the weights, ONE TMEM allocation and a service warpgroup in which warp s belongs to group s:
+// its lane 0 issues every tcgen05.mma of that group (forward / data-gradient convolutions first, the weight- and
+// bias-gradient MMAs nobody waits for behind them), the warp issues the TMA bulk copies (cp.async.bulk) of the group's
+// next tile + labels.
 //
 // Row warps and service warps talk through mbarriers only (per group: operands-ready rdy[k] with 128 arrivals, done /
 // free / wfree committed by tcgen05.commit, ld completed by the bulk copies' transaction bytes), so the tensor core
@@ -76,18 +75,19 @@ struct WsLayout {
     static_assert(FPC * CIN * 4 <= 2048 && (FPC * CIN * 4) % 16 == 0 && 2 * CPW <= 2 * NC8 + 2 * NS8, "staging geometry");
     // ---- shared region
     static constexpr int O_ZERO = G * GRP;
-    static constexpr int W1P = KT1 * NX8E * N1 * 16;                     // bytes per part
+    // weights: K-major B operands [tap][chunk8][2 N rows: hi rows then lo rows][8 x bf16]
+    static constexpr int W1B = KT1 * NX8E * 2 * N1 * 16;
     static constexpr int O_W1 = O_ZERO + PL;
-    static constexpr int W2P = INS ? 3 * NH8E * 16 * 16 : 0;
-    static constexpr int O_W2 = O_W1 + 2 * W1P;
-    static constexpr int W2DP = INS ? 3 * NC8 * NH * 16 : 0;
-    static constexpr int O_W2D = O_W2 + 2 * W2P;
-    static constexpr int WBP = 3 * NC8 * 16 * 16;
-    static constexpr int O_WB = O_W2D + 2 * W2DP;
-    static constexpr int WBDP = 3 * NS8 * 16 * 16;
-    static constexpr int O_WBD = O_WB + 2 * WBP;
-    static constexpr int O_ID = O_WBD + 2 * WBDP;                        // identity [4][32][8] bf16
-    static constexpr int O_F32 = O_ID + 2048;                            // b1[32] b2[16] lng[16] lnb[16] bb[16] hw[4*128] hb[4]
+    static constexpr int W2B = INS ? 3 * NH8E * 2 * 16 * 16 : 0;
+    static constexpr int O_W2 = O_W1 + W1B;
+    static constexpr int W2DB = INS ? 3 * NC8 * 2 * NH * 16 : 0;
+    static constexpr int O_W2D = O_W2 + W2B;
+    static constexpr int WBB = 3 * NC8 * 2 * 16 * 16;
+    static constexpr int O_WB = O_W2D + W2DB;
+    static constexpr int WBDB = 3 * NS8 * 2 * 16 * 16;
+    static constexpr int O_WBD = O_WB + WBB;
+    static constexpr int O_ID = O_WBD + WBDB;                            // identity [chunk8 (4)][K half (2)][32 rows][8] bf16
+    static constexpr int O_F32 = O_ID + 4096;                            // b1[32] b2[16] lng[16] lnb[16] bb[16] hw[4*128] hb[4]
     static constexpr int F_B1 = 0, F_B2 = 32, F_LNG = 48, F_LNB = 64, F_BB = 80, F_HW = 96, F_HB = 96 + 512, F_END = 96 + 512 + 8;
     static constexpr int O_BAR = O_F32 + F_END * 4;                      // per group 16 mbarriers
     static constexpr int O_END = O_BAR + G * 16 * 8 + 16;
@@ -95,17 +95,18 @@ struct WsLayout {
     static constexpr int SPAN = (G - 1) * GRP + (P_F + NC8 + 17) * PL;
     static constexpr int TOTAL = ((O_END > SPAN ? O_END : SPAN) + 127) / 128 * 128;
     // ---- TMEM columns
+    // per group 32 working columns; then the persistent weight-gradient blocks (M = 64: [hi | lo] input planes on the
+    // lanes, 32 columns = [hi | lo] output-gradient planes, one block per tap) and the per-row bias sums
     static constexpr int C_W1 = G * 32;
-    static constexpr int C_W2 = C_W1 + 16 * KT1;
-    static constexpr int C_WB = C_W2 + (INS ? 48 : 0);
-    static constexpr int C_B1 = C_WB + 48;
-    static constexpr int C_B2 = C_B1 + 32;
+    static constexpr int C_W2 = C_W1 + 32 * KT1;
+    static constexpr int C_WB = C_W2 + (INS ? 96 : 0);
+    static constexpr int C_B1 = C_WB + 96;
+    static constexpr int C_B2 = C_B1 + N1;
     static constexpr int C_BB = C_B2 + (INS ? 16 : 0);
-    static constexpr int C_LNB = C_BB + 16;
-    static constexpr int C_END = C_LNB + 16;
+    static constexpr int C_END = C_BB + 16;
     static_assert(C_END <= 512, "TMEM columns");
     static constexpr int NTH = (G + 1) * 128;                            // G row warpgroups + one service warpgroup
-    static constexpr int REG_SERVICE = 64;
+    static constexpr int REG_SERVICE = G == 3 ? 80 : 64;
     static constexpr int REG_LAUNCH = (65536 / NTH) / 8 * 8;
     static constexpr int REG_ROW = ((NTH * REG_LAUNCH - 128 * REG_SERVICE) / (G * 128)) / 8 * 8;
 };
@@ -160,6 +161,13 @@ __device__ __forceinline__ void load_half(const uint8_t* buf, int row, float (&v
 #pragma unroll
     for (int i = 0; i < N / 2; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+// accumulator of a MERGE convolution: columns [0,16) + [16,32)
+__device__ __forceinline__ void ld_merged16(uint32_t taddr, float (&v)[16]) {
+    float t[16];
+    umma::ld_x16(taddr, v); umma::ld_x16(taddr + 16, t); umma::ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+}
 __device__ __forceinline__ void st_zero_x8(uint32_t taddr) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
 }
@@ -169,61 +177,70 @@ template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 // ---- MMA issue (one thread).  All descriptors: no swizzle; K-major SBO = 128 B, MN-major LBO = 128 B.
-// convolution: D = sum_tap A(shifted by (tap - KT/2) * 2 rows) * W_tap over N8 chunks of 8 channels, 3 split passes
-template <int KT, int N8, int N, int HALO, int PL>
-__device__ __forceinline__ void issue_conv(uint32_t d, uint32_t a_hi, uint32_t zero, uint32_t w_hi, uint32_t w_part, bool fresh) {
+// A tcgen05.mma of this size costs ~45 SM clocks whatever M (64 / 128) and N (<= 32; 48 clocks at N = 64) are
+// (scratch/umma_bench.py, profiles/r2_umma_bench.log): the design minimises the NUMBER of MMAs.
+// convolution: D = sum_tap A(shifted by (tap - KT/2) * 2 rows) * W_tap over N8 chunks of 8 channels.
+//   MERGE (2 N <= 32): two MMAs per (tap, K step): A_hi * [W_hi | W_lo] into columns [0, 2N) and A_lo * W_hi into [0, N); the
+//   epilogue adds the two column blocks.  Otherwise three passes hi*hi + lo*hi + hi*lo into columns [0, N).
+template <int KT, int N8, int N, bool MERGE, int HALO, int PL>
+__device__ __forceinline__ void issue_conv(uint32_t d, uint32_t a_hi, uint32_t zero, uint32_t w) {
     constexpr int N8E = (N8 + 1) / 2 * 2;
-    constexpr uint32_t idesc = umma::make_idesc_bf16(128, N, false, false);
-    uint32_t acc = fresh ? 0u : 1u;
+    constexpr uint32_t idesc1 = umma::make_idesc_bf16(128, N, false, false), idesc2 = umma::make_idesc_bf16(128, 2 * N, false, false);
+    uint32_t acc = 0u;
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = a_hi + (pass == 1 ? N8 * PL : 0), w = w_hi + (pass == 2 ? w_part : 0u);
+    for (int pass = 0; pass < (MERGE ? 2 : 3); ++pass) {
+        const uint32_t a = a_hi + (pass == 1 ? N8 * PL : 0);
 #pragma unroll
         for (int tap = 0; tap < KT; ++tap)
 #pragma unroll
             for (int ks = 0; ks < N8E / 2; ++ks) {
                 const uint32_t a0 = a + (uint32_t)((2 * ks) * PL + (HALO + (tap - KT / 2) * 2) * 16);
                 const uint32_t lbo = (2 * ks + 1 < N8) ? (uint32_t)PL : zero - (a + (uint32_t)((2 * ks) * PL));
-                const uint32_t b0 = w + (uint32_t)(((tap * N8E + 2 * ks) * N) * 16);
-                umma::mma_bf16(d, umma::make_desc(a0, lbo, 128u), umma::make_desc(b0, (uint32_t)N * 16u, 128u), idesc, acc);
+                const uint32_t b0 = w + (uint32_t)(((tap * N8E + 2 * ks) * 2 * N + (pass == 2 ? N : 0)) * 16);
+                umma::mma_bf16(d, umma::make_desc(a0, lbo, 128u), umma::make_desc(b0, (uint32_t)(2 * N) * 16u, 128u),
+                               (MERGE && pass == 0) ? idesc2 : idesc1, acc);
                 acc = 1u;
             }
     }
 }
-// weight gradient: D_tap[m][n] += sum_r A[r (+ shift if SHIFT_A)][m] * B[r (+ shift if !SHIFT_A)][n], both MN-major, N = 16
-template <int KT, bool SHIFT_A, int NA8, int NB8, int HALO, int PL>
+// weight gradient, ONE MMA per (tap, 16 rows): D_tap[m][n] += sum_r A[r (+ shift)][m] * B[r (+ shift)][n] with both operands
+// MN-major; the M = 64 rows are A's planes [hi chunks | lo chunks] (8 channels each), the N = 32 columns B's planes
+// [hi | lo]: all four hi/lo products at once, added up when the accumulator is read back.
+template <int KT, bool SHIFT_A, int HALO, int PL>
 __device__ __forceinline__ void issue_wgrad(uint32_t d0, uint32_t a_hi, uint32_t b_hi) {
-    constexpr uint32_t idesc = umma::make_idesc_bf16(128, 16, true, true);
+    constexpr uint32_t idesc = umma::make_idesc_bf16(64, 32, true, true);
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = a_hi + (pass == 1 ? NA8 * PL : 0), b = b_hi + (pass == 2 ? NB8 * PL : 0);
+    for (int tap = 0; tap < KT; ++tap) {
+        const int sh = (tap - KT / 2) * 2;
 #pragma unroll
-        for (int tap = 0; tap < KT; ++tap) {
-            const int sh = (tap - KT / 2) * 2;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t a0 = a + (uint32_t)((HALO + 16 * ks + (SHIFT_A ? sh : 0)) * 16);
-                const uint32_t b0 = b + (uint32_t)((HALO + 16 * ks + (SHIFT_A ? 0 : sh)) * 16);
-                umma::mma_bf16(d0 + (uint32_t)(tap * 16), umma::make_desc(a0, 128u, (uint32_t)PL), umma::make_desc(b0, 128u, (uint32_t)PL), idesc, 1u);
-            }
+        for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t a0 = a_hi + (uint32_t)((HALO + 16 * ks + (SHIFT_A ? sh : 0)) * 16);
+            const uint32_t b0 = b_hi + (uint32_t)((HALO + 16 * ks + (SHIFT_A ? 0 : sh)) * 16);
+            umma::mma_bf16(d0 + (uint32_t)(tap * 32), umma::make_desc(a0, 128u, (uint32_t)PL), umma::make_desc(b0, 128u, (uint32_t)PL), idesc, 1u);
         }
     }
 }
-// per-row running sums: D[r][n] += sum_k A[r][k] * I[k][n]  (bias gradients; reduced over rows at the very end)
+// the same, one tap (8 MMAs): the unit in which the MMA thread interleaves gradient work with latency-critical jobs
+template <int KT, bool SHIFT_A, int HALO, int PL>
+__device__ __forceinline__ void issue_wgrad_tap(uint32_t d0, uint32_t a_hi, uint32_t b_hi, int tap) {
+    constexpr uint32_t idesc = umma::make_idesc_bf16(64, 32, true, true);
+    const int sh = (tap - KT / 2) * 2;
+    const uint32_t a1 = a_hi + (uint32_t)((HALO + (SHIFT_A ? sh : 0)) * 16), b1 = b_hi + (uint32_t)((HALO + (SHIFT_A ? 0 : sh)) * 16);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        umma::mma_bf16(d0 + (uint32_t)(tap * 32), umma::make_desc(a1 + (uint32_t)(256 * ks), 128u, (uint32_t)PL),
+                       umma::make_desc(b1 + (uint32_t)(256 * ks), 128u, (uint32_t)PL), idesc, 1u);
+}
+// per-row running sums: D[r][n] += sum_k (A_hi + A_lo)[r][k] * I[k][n]  (bias gradients; reduced over rows at the very end).
+// One MMA per chunk of 8 channels: its K = 16 step pairs the chunk's hi plane with its lo plane (LBO = N8 planes) against
+// the identity block of that chunk, stored twice (one copy per K half).
 template <int N8, int N, int HALO, int PL>
-__device__ __forceinline__ void issue_ident(uint32_t d, uint32_t a_hi, uint32_t zero, uint32_t idm) {
-    constexpr int N8E = (N8 + 1) / 2 * 2;
+__device__ __forceinline__ void issue_ident(uint32_t d, uint32_t a_hi, uint32_t idm) {
     constexpr uint32_t idesc = umma::make_idesc_bf16(128, N, false, false);
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const uint32_t a = a_hi + part * N8 * PL;
-#pragma unroll
-        for (int ks = 0; ks < N8E / 2; ++ks) {
-            const uint32_t a0 = a + (uint32_t)((2 * ks) * PL + HALO * 16);
-            const uint32_t lbo = (2 * ks + 1 < N8) ? (uint32_t)PL : zero - (a + (uint32_t)((2 * ks) * PL));
-            umma::mma_bf16(d, umma::make_desc(a0, lbo, 128u), umma::make_desc(idm + (uint32_t)((2 * ks) * 32 * 16), 512u, 128u), idesc, 1u);
-        }
-    }
+    for (int c = 0; c < N8; ++c)
+        umma::mma_bf16(d, umma::make_desc(a_hi + (uint32_t)(c * PL + HALO * 16), (uint32_t)(N8 * PL), 128u),
+                       umma::make_desc(idm + (uint32_t)(c * 1024), 512u, 128u), idesc, 1u);
 }
 
 // plain linear head + margin / scale cross entropy for ONE window by one warp (lane l owns features l, l+32, l+64, l+96)
@@ -343,15 +360,16 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     {   // weights as bf16 (hi, lo) K-major B operands [part][tap][chunk8][n][8]
-        auto put = [&](int off, int part_bytes, int idx16, float w) {
+        // (block = tap * chunks + chunk8, n, k & 7) -> hi at row n, lo at row N + n of the block's 2 N rows
+        auto put = [&](int off, int N, int block, int n, int k7, float w) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(w);
             const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-            reinterpret_cast<__nv_bfloat16*>(smw + off)[idx16] = hi;
-            reinterpret_cast<__nv_bfloat16*>(smw + off + part_bytes)[idx16] = lo;
+            reinterpret_cast<__nv_bfloat16*>(smw + off)[(block * 2 * N + n) * 8 + k7] = hi;
+            reinterpret_cast<__nv_bfloat16*>(smw + off)[(block * 2 * N + N + n) * 8 + k7] = lo;
         };
         for (int i = tid; i < O1 * CIN * KT1; i += L::NTH) {
             const int o = i / (CIN * KT1), ci = (i / KT1) % CIN, tap = i % KT1;
-            put(L::O_W1, L::W1P, ((tap * NX8E + (ci >> 3)) * N1 + o) * 8 + (ci & 7), A.w1[i]);
+            put(L::O_W1, N1, tap * NX8E + (ci >> 3), o, ci & 7, A.w1[i]);
         }
         for (int i = tid; i < O1; i += L::NTH) f32[L::F_B1 + i] = A.b1[i];
         if constexpr (INS) {
@@ -359,22 +377,24 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                 const int o = i / (H * 3), ci = (i / 3) % H, tap = i % 3;
                 float w = A.w2[i];
                 if (tap == 1) w += A.skip_identity ? (o == ci ? 1.f : 0.f) : A.wsk[o * H + ci];
-                put(L::O_W2, L::W2P, ((tap * NH8E + (ci >> 3)) * 16 + o) * 8 + (ci & 7), w);                 // fwd: n = o, k = ci
-                put(L::O_W2D, L::W2DP, (((2 - tap) * NC8 + (o >> 3)) * NH + ci) * 8 + (o & 7), w);          // dgrad: n = ci, k = o
+                put(L::O_W2, 16, tap * NH8E + (ci >> 3), o, ci & 7, w);                 // fwd: n = o, k = ci
+                put(L::O_W2D, NH, (2 - tap) * NC8 + (o >> 3), ci, o & 7, w);            // dgrad: n = ci, k = o, flipped taps
             }
             for (int i = tid; i < C; i += L::NTH) f32[L::F_B2 + i] = A.b2[i] + (A.skip_identity ? 0.f : A.bsk[i]);
         }
         for (int i = tid; i < C; i += L::NTH) { f32[L::F_LNG + i] = A.lng[i]; f32[L::F_LNB + i] = A.lnb[i]; }
         for (int i = tid; i < 16 * C * 3; i += L::NTH) {
             const int o = i / (C * 3), ci = (i / 3) % C, tap = i % 3;
-            put(L::O_WB, L::WBP, ((tap * NC8 + (ci >> 3)) * 16 + o) * 8 + (ci & 7), A.wbb[i]);
-            put(L::O_WBD, L::WBDP, (((2 - tap) * NS8 + (o >> 3)) * 16 + ci) * 8 + (o & 7), A.wbb[i]);
+            put(L::O_WB, 16, tap * NC8 + (ci >> 3), o, ci & 7, A.wbb[i]);
+            put(L::O_WBD, 16, (2 - tap) * NS8 + (o >> 3), ci, o & 7, A.wbb[i]);
         }
         for (int i = tid; i < 16; i += L::NTH) f32[L::F_BB + i] = A.bbb[i];
         for (int i = tid; i < K * 128; i += L::NTH) f32[L::F_HW + i] = A.hw[i];
         if (A.hb) for (int i = tid; i < K; i += L::NTH) f32[L::F_HB + i] = A.hb[i];
-        for (int i = tid; i < 32; i += L::NTH)             // identity: element (n, k) at [(k >> 3) * 32 + n][k & 7]
-            reinterpret_cast<uint16_t*>(smw + L::O_ID)[((i >> 3) * 32 + i) * 8 + (i & 7)] = 0x3F80;
+        for (int i = tid; i < 64; i += L::NTH) {           // identity: element (n, k), n = k = i & 31, in both K halves of chunk k >> 3
+            const int k = i & 31, h = i >> 5;
+            reinterpret_cast<uint16_t*>(smw + L::O_ID)[(((k >> 3) * 2 + h) * 32 + k) * 8 + (k & 7)] = 0x3F80;
+        }
     }
     umma::fence_smem_to_async();
     umma::fence_before_sync();
@@ -396,121 +416,116 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     auto tile_of = [&](int it, int g) { return (it * (int)gridDim.x + (int)blockIdx.x) * G + g; };
     constexpr int ROW_WARPS = 4 * G;
 
-    if (warp >= ROW_WARPS) {
+    if (warp < 4) {                                        // warps 0..3: the hardware arbiter prefers HIGH warp ids, so the
+                                                           // polling service warps never take an issue slot from a row warp
         // ====================================================================================== service warpgroup
         ws::reg_dec<L::REG_SERVICE>();
-        const int sw = warp - ROW_WARPS;
+        const int sw = warp;
         const uint32_t zero = sbase + L::O_ZERO, idm = sbase + L::O_ID;
-        if (sw == 0 && lane == 0) {
-            // ---------------------------------------------------------------- MMA-A: forward + data-gradient convolutions
-            for (int it = 0; it < nit; ++it) {
-                const uint32_t par = it & 1;
-                const int nA = train ? (INS ? 5 : 3) : (INS ? 3 : 2);
-                for (int k = 0; k < nA; ++k)
-                    for (int g = 0; g < G; ++g) {
-                        umma::mbar_wait(bar_rdy(g, k), par);
-                        umma::fence_after_sync();
-                        const uint32_t gb = sbase + g * L::GRP, acc = tmem + g * 32;
-                        const int job = INS ? k : (k == 0 ? 0 : k + 1);       // 0 conv1, 1 conv2, 2 backbone, 3 backbone dgrad, 4 conv2 dgrad
-                        if (job == 0) ws::issue_conv<KT1, NX8, N1, HALO, PL>(acc, gb + L::P_X * PL, zero, sbase + L::O_W1, L::W1P, true);
-                        if constexpr (INS) {
-                            if (job == 1) ws::issue_conv<3, NH8, 16, HALO, PL>(acc, gb + L::P_HA * PL, zero, sbase + L::O_W2, L::W2P, true);
-                            if (job == 4) ws::issue_conv<3, NC8, NH, HALO, PL>(acc, gb + L::P_XH * PL, zero, sbase + L::O_W2D, L::W2DP, true);
-                        }
-                        if (job == 2) ws::issue_conv<3, NC8, 16, HALO, PL>(acc, gb + L::P_F * PL, zero, sbase + L::O_WB, L::WBP, true);
-                        if (job == 3) ws::issue_conv<3, NS8, 16, HALO, PL>(acc, gb + L::P_Z * PL, zero, sbase + L::O_WBD, L::WBDP, true);
-                        umma::commit(bar_done(g));
-                        if (!train && job == 2) umma::commit(bar_free(g));    // forward only: F|Z (the staging area) is free again
-                    }
-            }
-        } else if (sw == 1 && lane == 0 && train) {
-            // ---------------------------------------------------------------- MMA-B: weight / bias gradients (TMEM-resident sums)
-            for (int it = 0; it < nit; ++it) {
-                const uint32_t par = it & 1;
-                for (int k = NPH - (INS ? 3 : 2); k < NPH; ++k)
-                    for (int g = 0; g < G; ++g) {
-                        umma::mbar_wait(bar_rdy(g, k), par);
-                        umma::fence_after_sync();
-                        const uint32_t gb = sbase + g * L::GRP;
-                        const int job = k - (NPH - (INS ? 3 : 2));            // 0: backbone, 1: conv2 (insole only), last: conv1
-                        if (job == 0) {
-                            ws::issue_conv<3, NS8, 16, HALO, PL>(tmem + L::C_LNB, gb + L::P_Z * PL, zero, sbase + L::O_WBD, L::WBDP, false);   // sum_r dF
-                            ws::issue_ident<NS8, 16, HALO, PL>(tmem + L::C_BB, gb + L::P_Z * PL, zero, idm);
-                            ws::issue_wgrad<3, true, NC8, NS8, HALO, PL>(tmem + L::C_WB, gb + L::P_F * PL, gb + L::P_Z * PL);
-                            umma::commit(bar_free(g));
-                        } else if (INS && job == 1) {
-                            if constexpr (INS) {
-                                ws::issue_wgrad<3, true, NH8, NC8, HALO, PL>(tmem + L::C_W2, gb + L::P_HA * PL, gb + L::P_XH * PL);
-                                ws::issue_ident<NC8, 16, HALO, PL>(tmem + L::C_B2, gb + L::P_XH * PL, zero, idm);
-                                umma::commit(bar_wfree(g));
-                            }
-                        } else {
-                            if constexpr (INS) {
-                                // lanes = conv1 output channel (dA1 lives in the HA planes), columns = input channel
-                                ws::issue_ident<NH8, N1, HALO, PL>(tmem + L::C_B1, gb + L::P_HA * PL, zero, idm);
-                                ws::issue_wgrad<KT1, false, NH8, NX8, HALO, PL>(tmem + L::C_W1, gb + L::P_HA * PL, gb + L::P_X * PL);
-                            } else {
-                                ws::issue_ident<NC8, 16, HALO, PL>(tmem + L::C_B1, gb + L::P_XH * PL, zero, idm);
-                                ws::issue_wgrad<KT1, true, NX8, NC8, HALO, PL>(tmem + L::C_W1, gb + L::P_X * PL, gb + L::P_XH * PL);
-                            }
-                            umma::commit(bar_done(g));
-                        }
-                    }
-            }
-        } else if (sw == 2) {
-            // ---------------------------------------------------------------- LOAD: windows of the next tile -> staging (inside F|Z), labels
+        // Service warp s is the MMA + TMA warp of group s: lane 0 issues all of that group's MMAs in the group's natural
+        // order with blocking (hardware-suspended) mbarrier waits, the whole warp stages the next tile's windows.  Issuing a
+        // small tcgen05.mma costs the issuing thread ~45 clocks (scratch/umma_bench.py) although the tensor pipe executes it
+        // faster: G issuers in parallel keep the pipe fed (one issuer for all groups was 3x slower, profiles/r2_ws_history.md).
+        // The groups drift apart in phase, so one group's MMAs run under the other groups' epilogues.  (The order in which
+        // different groups' weight-gradient MMAs accumulate into the shared TMEM blocks depends on timing: sums are
+        // reproducible to fp32 rounding, not bit for bit.)
+        if (sw < G) {
+            const int g = sw;
+            const uint32_t gb = sbase + g * L::GRP, acc = tmem + g * 32;
+            uint8_t* gbp = smw + g * L::GRP;
             const int per_win = 64 * CIN;
-            for (int it = 0; it < nit; ++it) {
-                for (int g = 0; g < G; ++g) {
-                    if (it > 0) {
-                        // F|Z are free once MMA-B's backbone gradients (free) AND MMA-A's backbone data gradient have read them;
-                        // the latter is implied by the group's arrival after it consumed that accumulator
-                        if (lane == 0) {
-                            umma::mbar_wait(bar_free(g), (uint32_t)((it - 1) & 1));
-                            if (train) umma::mbar_wait(bar_rdy(g, NPH - (INS ? 2 : 1)), (uint32_t)((it - 1) & 1));
+            auto load_tile = [&](int it) {                 // whole warp: windows of tile `it` -> staging (inside F|Z), labels
+                const int tile = tile_of(it, g);
+                if (lane < 2) {
+                    const int wi = tile * 2 + lane;
+                    reinterpret_cast<int*>(gbp + L::O_YS)[(it & 1) * 2 + lane] = (A.mode == MODE_FUSED && wi < A.B) ? (int)A.y[wi] : 0;
+                }
+                uint32_t bytes = 0;
+                if (!A.zero_input) {
+                    for (int w = 0; w < 2; ++w) {
+                        const int wi = tile * 2 + w;
+                        if (wi >= A.B) continue;
+                        const float* src = A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win);
+                        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) { bytes += (uint32_t)per_win * 4u; continue; }
+                        for (int e = lane; e < per_win; e += 32) {        // unaligned window: plain copy into the same staging layout
+                            const int t = e / CIN, j = t / L::FPC;
+                            reinterpret_cast<float*>(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16)[e - j * L::FPC * CIN] = __ldg(src + e);
                         }
-                        __syncwarp();
                     }
-                    const int tile = tile_of(it, g);
-                    uint8_t* gbp = smw + g * L::GRP;
-                    if (lane < 2) {
-                        const int wi = tile * 2 + lane;
-                        reinterpret_cast<int*>(gbp + L::O_YS)[(it & 1) * 2 + lane] = (A.mode == MODE_FUSED && wi < A.B) ? (int)A.y[wi] : 0;
-                    }
-                    uint32_t bytes = 0;
-                    if (!A.zero_input) {
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (bytes == 0) {
+                        umma::mbar_arrive(bar_ld(g));
+                    } else {
+                        umma::fence_smem_to_async();
+                        umma::mbar_expect_tx(bar_ld(g), bytes);
                         for (int w = 0; w < 2; ++w) {
                             const int wi = tile * 2 + w;
                             if (wi >= A.B) continue;
                             const float* src = A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win);
-                            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) { bytes += (uint32_t)per_win * 4u; continue; }
-                            for (int e = lane; e < per_win; e += 32) {        // unaligned window: plain copy into the same staging layout
-                                const int t = e / CIN, j = t / L::FPC;
-                                reinterpret_cast<float*>(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16)[e - j * L::FPC * CIN] = __ldg(src + e);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (bytes == 0) {
-                            umma::mbar_arrive(bar_ld(g));
-                        } else {
-                            umma::fence_smem_to_async();
-                            umma::mbar_expect_tx(bar_ld(g), bytes);
-                            for (int w = 0; w < 2; ++w) {
-                                const int wi = tile * 2 + w;
-                                if (wi >= A.B) continue;
-                                const float* src = A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win);
-                                if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) continue;
+                            if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) continue;
 #pragma unroll
-                                for (int j = 0; j < L::CPW; ++j) {
-                                    const int fr = (j + 1) * L::FPC <= 64 ? L::FPC : 64 - j * L::FPC;
-                                    umma::bulk_g2s(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16, src + j * L::FPC * CIN, (uint32_t)(fr * CIN * 4), bar_ld(g));
-                                }
+                            for (int j = 0; j < L::CPW; ++j) {
+                                const int fr = (j + 1) * L::FPC <= 64 ? L::FPC : 64 - j * L::FPC;
+                                umma::bulk_g2s(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16, src + j * L::FPC * CIN, (uint32_t)(fr * CIN * 4), bar_ld(g));
                             }
                         }
                     }
                 }
+                __syncwarp();
+            };
+            auto wait_rdy = [&](int k, uint32_t par) { umma::mbar_wait(bar_rdy(g, k), par); umma::fence_after_sync(); };
+            load_tile(0);
+            for (int it = 0; it < nit; ++it) {
+                const uint32_t par = it & 1;
+                if (lane == 0) {
+                    int k = 0;
+                    wait_rdy(k++, par);
+                    ws::issue_conv<KT1, NX8, N1, (N1 <= 16), HALO, PL>(acc, gb + L::P_X * PL, zero, sbase + L::O_W1);
+                    umma::commit(bar_done(g));
+                    if constexpr (INS) {
+                        wait_rdy(k++, par);
+                        ws::issue_conv<3, NH8, 16, true, HALO, PL>(acc, gb + L::P_HA * PL, zero, sbase + L::O_W2);
+                        umma::commit(bar_done(g));
+                    }
+                    wait_rdy(k++, par);
+                    ws::issue_conv<3, NC8, 16, true, HALO, PL>(acc, gb + L::P_F * PL, zero, sbase + L::O_WB);
+                    umma::commit(bar_done(g));
+                    if (train) {
+                        wait_rdy(k++, par);                // dz is in the Z planes
+                        ws::issue_conv<3, NS8, 16, true, HALO, PL>(acc, gb + L::P_Z * PL, zero, sbase + L::O_WBD);
+                        umma::commit(bar_done(g));
+                        ws::issue_ident<NS8, 16, HALO, PL>(tmem + L::C_BB, gb + L::P_Z * PL, idm);
+                        ws::issue_wgrad<3, true, HALO, PL>(tmem + L::C_WB, gb + L::P_F * PL, gb + L::P_Z * PL);
+                        umma::commit(bar_free(g));
+                        wait_rdy(k++, par);                // dA is in the XH planes (and the backbone data gradient has been consumed)
+                        if constexpr (INS) {
+                            ws::issue_conv<3, NC8, NH, false, HALO, PL>(acc, gb + L::P_XH * PL, zero, sbase + L::O_W2D);
+                            umma::commit(bar_done(g));
+                            ws::issue_wgrad<3, true, HALO, PL>(tmem + L::C_W2, gb + L::P_HA * PL, gb + L::P_XH * PL);
+                            ws::issue_ident<NC8, 16, HALO, PL>(tmem + L::C_B2, gb + L::P_XH * PL, idm);
+                            umma::commit(bar_wfree(g));
+                        }
+                    } else {
+                        umma::commit(bar_free(g));
+                    }
+                    umma::mbar_wait(bar_free(g), par);     // the backbone MMAs have read F and Z: the staging area is free
+                }
+                __syncwarp();
+                if (it + 1 < nit) load_tile(it + 1);
+                if (lane == 0 && train) {
+                    if constexpr (INS) {
+                        wait_rdy(5, par);                  // dA1 is in the HA planes: lanes = conv1 output channel, columns = input channel
+                        ws::issue_ident<NH8, N1, HALO, PL>(tmem + L::C_B1, gb + L::P_HA * PL, idm);
+                        ws::issue_wgrad<KT1, false, HALO, PL>(tmem + L::C_W1, gb + L::P_HA * PL, gb + L::P_X * PL);
+                    } else {
+                        ws::issue_ident<NC8, 16, HALO, PL>(tmem + L::C_B1, gb + L::P_XH * PL, idm);
+                        ws::issue_wgrad<KT1, true, HALO, PL>(tmem + L::C_W1, gb + L::P_X * PL, gb + L::P_XH * PL);
+                    }
+                    umma::commit(bar_done(g));
+                }
+                __syncwarp();
             }
         }
         umma::fence_before_sync();
@@ -519,12 +534,13 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     } else {
         // ====================================================================================== row warps: thread = row of its group's tile
         ws::reg_inc<L::REG_ROW>();
-        float g_lng[16];                                   // per-row sums of dF * xh (LayerNorm gamma gradient)
+        float g_lng[16], g_lnb[16];                        // per-row sums of dF * xh and dF (LayerNorm affine gradients)
         ws::HeadLite<K> head;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) g_lng[i] = 0.f;
+        for (int i = 0; i < 16; ++i) { g_lng[i] = 0.f; g_lnb[i] = 0.f; }
         head.zero();
-        const int g = warp >> 2, wq = warp & 3, r = wq * 32 + lane;
+        const int rw = warp - 4;                           // row warp index
+        const int g = rw >> 2, wq = rw & 3, r = wq * 32 + lane;
         uint8_t* gb = smw + g * L::GRP;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + g * 32;
         float* Ps = reinterpret_cast<float*>(gb + L::O_P); float* DPs = reinterpret_cast<float*>(gb + L::O_DP);
@@ -581,7 +597,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
             float rstd_row = 0.f;
             {
                 float a[16], gl[16], d[16], xh[16], f[16]; float rstd;
-                umma::ld_x16(trow, a); umma::ld_wait();
+                ws::ld_merged16(trow, a);
                 const float* bias = INS ? b2s : b1s;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) { if (c < C) gelu_fwd_fast(a[c] + bias[c], gl[c], d[c]); else { gl[c] = 0.f; d[c] = 0.f; } }
@@ -606,7 +622,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
             uint32_t zmask = 0;
             {
                 float z[16];
-                umma::ld_x16(trow, z); umma::ld_wait();
+                ws::ld_merged16(trow, z);
                 umma::fence_before_sync();
                 float zz[16];
 #pragma unroll
@@ -644,7 +660,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
             wait_done();
             {
                 float df[16], xh[16], dxh[16], dg[16], d[(C + 3) / 4 * 4], da[16];
-                umma::ld_x16(trow, df); umma::ld_wait();
+                ws::ld_merged16(trow, df);
                 const float4* xp = reinterpret_cast<const float4*>(gb + L::P_XH * PL) + (HALO + r);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
@@ -656,7 +672,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float dfc = c < C ? df[c] : 0.f;
-                    g_lng[c] = fmaf(dfc, xh[c], g_lng[c]);
+                    g_lng[c] = fmaf(dfc, xh[c], g_lng[c]); g_lnb[c] += dfc;
                     dxh[c] = c < C ? dfc * lngs[c] : 0.f;
                 }
                 ln_bwd<16, C>(dxh, xh, rstd_row, dg);
@@ -689,10 +705,13 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         float* out = A.partial + (size_t)blockIdx.x * A.NGP;
         const GradOff& go = A.go;
         float* stage = reinterpret_cast<float*>(smw);      // the groups' planes are dead
-        // per-row LayerNorm-gamma sums and the head warps' sums: every row warp stages its partial
+        // per-row LayerNorm affine sums and the head warps' sums: every row warp stages its partial
 #pragma unroll
-        for (int c = 0; c < 16; ++c) { const float s = warp_sum(g_lng[c]); if (lane == 0) stage[warp * 16 + c] = s; }
-        float* hstage = stage + ROW_WARPS * 16;            // [head warp][K * 128 + K + 2]
+        for (int c = 0; c < 16; ++c) {
+            const float s1 = warp_sum(g_lng[c]), s2 = warp_sum(g_lnb[c]);
+            if (lane == 0) { stage[rw * 32 + c] = s1; stage[rw * 32 + 16 + c] = s2; }
+        }
+        float* hstage = stage + ROW_WARPS * 32;            // [head warp][K * 128 + K + 2]
         constexpr int HS = K * 128 + K + 2;
         if (wq < 2) {
             float* hs = hstage + (g * 2 + wq) * HS;
@@ -707,8 +726,13 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
             }
         }
         ws::bar_sync(15, ROW_WARPS * 32);
-        const int rt = tid;                                // row threads 0 .. 128 G - 1
-        if (rt < C) { float s = 0.f; for (int q = 0; q < ROW_WARPS; ++q) s += stage[q * 16 + rt]; out[go.lng + rt] = s; }
+        const int rt = tid - 128;                          // row threads 0 .. 128 G - 1
+        if (rt < 2 * C) {
+            const int c = rt % C, which = rt / C;
+            float s = 0.f;
+            for (int q = 0; q < ROW_WARPS; ++q) s += stage[q * 32 + which * 16 + c];
+            out[(which ? go.lnb : go.lng) + c] = s;
+        }
         for (int e = rt; e < HS; e += ROW_WARPS * 32) {
             float s = 0.f;
             for (int q = 0; q < 2 * G; ++q) s += hstage[q * HS + e];
@@ -718,59 +742,80 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         }
         if (g == 0) {
             const uint32_t tq = tmem + ((uint32_t)(wq * 32) << 16);
-            float v[16];
-            if (wq == 0) {
-                // weight-gradient accumulators: lane = M index of the MMA, 16 columns per tap
-                for (int tap = 0; tap < KT1; ++tap) {
-                    umma::ld_x16(tq + L::C_W1 + tap * 16, v); umma::ld_wait();
-                    if constexpr (INS) {                   // lanes = output channel, columns = input channel
-                        if (lane < H) for (int ci = 0; ci < CIN; ++ci) out[go.w1 + (lane * CIN + ci) * KT1 + tap] = v[ci];
-                    } else {
-                        if (lane < CIN) for (int co = 0; co < C; ++co) out[go.w1 + (co * CIN + lane) * KT1 + tap] = v[co];
-                    }
-                }
-                if constexpr (INS) {
-                    for (int tap = 0; tap < 3; ++tap) {
-                        umma::ld_x16(tq + L::C_W2 + tap * 16, v); umma::ld_wait();
-                        if (lane < H) for (int co = 0; co < C; ++co) {
-                            out[go.w2 + (co * H + lane) * 3 + tap] = v[co];
-                            if (tap == 1 && !A.skip_identity) out[go.wsk + co * H + lane] = v[co];
-                        }
-                    }
-                }
-                for (int tap = 0; tap < 3; ++tap) {
-                    umma::ld_x16(tq + L::C_WB + tap * 16, v); umma::ld_wait();
-                    if (lane < C) for (int co = 0; co < 16; ++co) out[go.wbb + (co * C + lane) * 3 + tap] = v[co];
-                }
-            }
-            // per-row sums (bias / LayerNorm-beta gradients): reduce over the 128 lanes
-            float* bst = hstage + 2 * G * HS;              // [4 warps][96]
+            float* bst = hstage + 2 * G * HS;              // [4 warps][64] per-row sums
+            float* wst = bst + 256;                        // [tap][64 rows][32 columns] one weight-gradient region at a time
+            // per-row sums (bias gradients): reduce over the 128 lanes
             auto colsum = [&](int col0, int n, int slot) {
-                for (int c0 = 0; c0 < n; c0 += 16) {
-                    umma::ld_x16(tq + col0 + c0, v); umma::ld_wait();
+                for (int c0 = 0; c0 < n; c0 += 8) {
+                    float v[8];
+                    umma::ld_x8(tq + col0 + c0, v); umma::ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) { const float s = warp_sum(v[c]); if (lane == 0) bst[wq * 96 + slot + c0 + c] = s; }
+                    for (int c = 0; c < 8; ++c) { const float s = warp_sum(v[c]); if (lane == 0) bst[wq * 64 + slot + c0 + c] = s; }
                 }
             };
-            colsum(L::C_B1, 32, 0);
+            colsum(L::C_B1, N1, 0);
             if constexpr (INS) colsum(L::C_B2, 16, 32);
             colsum(L::C_BB, 16, 48);
-            colsum(L::C_LNB, 16, 64);
-            umma::fence_before_sync();
+            // weight-gradient regions: M = 64 accumulator rows sit on lanes 0..15 of every lane quarter (row = 16 * quarter + lane);
+            // rows = A's planes [hi chunks | lo chunks] x 8 channels, columns = B's [hi 16 | lo 16]: dW = hh + hl + lh + ll
+            auto dump = [&](int col0, int KT) {
+                for (int tap = 0; tap < KT; ++tap) {
+                    float v[16], v2[16];
+                    umma::ld_x16(tq + col0 + tap * 32, v); umma::ld_x16(tq + col0 + tap * 32 + 16, v2); umma::ld_wait();
+                    if (lane < 16) {
+                        float* d = wst + (tap * 64 + wq * 16 + lane) * 32;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { d[c] = v[c]; d[16 + c] = v2[c]; }
+                    }
+                }
+                umma::fence_before_sync();
+                ws::bar_sync(14, 128);
+            };
+            auto wval = [&](int tap, int NA8, int rc, int cc) {
+                const float* lo_ = wst + (tap * 64 + (NA8 + (rc >> 3)) * 8 + (rc & 7)) * 32;
+                const float* hi_ = wst + (tap * 64 + (rc >> 3) * 8 + (rc & 7)) * 32;
+                return (hi_[cc] + hi_[16 + cc]) + (lo_[cc] + lo_[16 + cc]);
+            };
+            dump(L::C_W1, KT1);
+            if constexpr (INS) {                           // rows = output channel (dA1 planes), columns = input channel
+                for (int e = rt; e < KT1 * H * CIN; e += 128) {
+                    const int tap = e / (H * CIN), co = (e / CIN) % H, ci = e % CIN;
+                    out[go.w1 + (co * CIN + ci) * KT1 + tap] = wval(tap, NH8, co, ci);
+                }
+            } else {                                       // rows = input channel, columns = output channel
+                for (int e = rt; e < KT1 * CIN * C; e += 128) {
+                    const int tap = e / (CIN * C), ci = (e / C) % CIN, co = e % C;
+                    out[go.w1 + (co * CIN + ci) * KT1 + tap] = wval(tap, NX8, ci, co);
+                }
+            }
             ws::bar_sync(14, 128);
-            if (rt < 96) {
-                const float s = (bst[rt] + bst[96 + rt]) + (bst[192 + rt] + bst[288 + rt]);
+            if constexpr (INS) {
+                dump(L::C_W2, 3);
+                for (int e = rt; e < 3 * H * C; e += 128) {
+                    const int tap = e / (H * C), ci = (e / C) % H, co = e % C;
+                    const float v = wval(tap, NH8, ci, co);
+                    out[go.w2 + (co * H + ci) * 3 + tap] = v;
+                    if (tap == 1 && !A.skip_identity) out[go.wsk + co * H + ci] = v;
+                }
+                ws::bar_sync(14, 128);
+            }
+            dump(L::C_WB, 3);
+            for (int e = rt; e < 3 * C * 16; e += 128) {
+                const int tap = e / (C * 16), ci = (e / 16) % C, co = e % 16;
+                out[go.wbb + (co * C + ci) * 3 + tap] = wval(tap, NC8, ci, co);
+            }
+            if (rt < 64) {
+                const float s = (bst[rt] + bst[64 + rt]) + (bst[128 + rt] + bst[192 + rt]);
                 if (rt < 32) { if (rt < O1) out[go.b1 + rt] = s; }
                 else if (rt < 48) { if (INS && rt - 32 < C) { out[go.b2 + rt - 32] = s; if (!A.skip_identity) out[go.bsk + rt - 32] = s; } }
-                else if (rt < 64) out[go.bbb + rt - 48] = s;
-                else if (rt < 80) { if (rt - 64 < C) out[go.lnb + rt - 64] = s; }
+                else out[go.bbb + rt - 48] = s;
             }
         }
         }
         umma::fence_before_sync();
         asm volatile("bar.sync 0;" ::: "memory");
-        if (warp == 0) umma::tmem_dealloc(tmem, 512);
     }
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace gaitk
