@@ -27,6 +27,7 @@
 // Reference semantics: see stream_common.cuh.  Geometry: the WearGait default window (T = 64, 2 windows per tile, 8
 // pooling bins); other geometries use stream_kernel_tc / stream_kernel.
 #pragma once
+#include <stdio.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -183,7 +184,7 @@ template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setma
 //   MERGE (2 N <= 32): two MMAs per (tap, K step): A_hi * [W_hi | W_lo] into columns [0, 2N) and A_lo * W_hi into [0, N); the
 //   epilogue adds the two column blocks.  Otherwise three passes hi*hi + lo*hi + hi*lo into columns [0, N).
 template <int KT, int N8, int N, bool MERGE, int HALO, int PL>
-__device__ __forceinline__ void issue_conv(uint32_t d, uint32_t a_hi, uint32_t zero, uint32_t w) {
+__device__ __forceinline__ void issue_conv(bool leader, uint32_t d, uint32_t a_hi, uint32_t zero, uint32_t w) {
     constexpr int N8E = (N8 + 1) / 2 * 2;
     constexpr uint32_t idesc1 = umma::make_idesc_bf16(128, N, false, false), idesc2 = umma::make_idesc_bf16(128, 2 * N, false, false);
     uint32_t acc = 0u;
@@ -197,8 +198,9 @@ __device__ __forceinline__ void issue_conv(uint32_t d, uint32_t a_hi, uint32_t z
                 const uint32_t a0 = a + (uint32_t)((2 * ks) * PL + (HALO + (tap - KT / 2) * 2) * 16);
                 const uint32_t lbo = (2 * ks + 1 < N8) ? (uint32_t)PL : zero - (a + (uint32_t)((2 * ks) * PL));
                 const uint32_t b0 = w + (uint32_t)(((tap * N8E + 2 * ks) * 2 * N + (pass == 2 ? N : 0)) * 16);
-                umma::mma_bf16(d, umma::make_desc(a0, lbo, 128u), umma::make_desc(b0, (uint32_t)(2 * N) * 16u, 128u),
-                               (MERGE && pass == 0) ? idesc2 : idesc1, acc);
+                if (leader)
+                    umma::mma_bf16(d, umma::make_desc(a0, lbo, 128u), umma::make_desc(b0, (uint32_t)(2 * N) * 16u, 128u),
+                                   (MERGE && pass == 0) ? idesc2 : idesc1, acc);
                 acc = 1u;
             }
     }
@@ -207,7 +209,7 @@ __device__ __forceinline__ void issue_conv(uint32_t d, uint32_t a_hi, uint32_t z
 // MN-major; the M = 64 rows are A's planes [hi chunks | lo chunks] (8 channels each), the N = 32 columns B's planes
 // [hi | lo]: all four hi/lo products at once, added up when the accumulator is read back.
 template <int KT, bool SHIFT_A, int HALO, int PL>
-__device__ __forceinline__ void issue_wgrad(uint32_t d0, uint32_t a_hi, uint32_t b_hi) {
+__device__ __forceinline__ void issue_wgrad(bool leader, uint32_t d0, uint32_t a_hi, uint32_t b_hi) {
     constexpr uint32_t idesc = umma::make_idesc_bf16(64, 32, true, true);
 #pragma unroll
     for (int tap = 0; tap < KT; ++tap) {
@@ -216,7 +218,8 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d0, uint32_t a_hi, uint32_t
         for (int ks = 0; ks < 8; ++ks) {
             const uint32_t a0 = a_hi + (uint32_t)((HALO + 16 * ks + (SHIFT_A ? sh : 0)) * 16);
             const uint32_t b0 = b_hi + (uint32_t)((HALO + 16 * ks + (SHIFT_A ? 0 : sh)) * 16);
-            umma::mma_bf16(d0 + (uint32_t)(tap * 32), umma::make_desc(a0, 128u, (uint32_t)PL), umma::make_desc(b0, 128u, (uint32_t)PL), idesc, 1u);
+            if (leader)
+                umma::mma_bf16(d0 + (uint32_t)(tap * 32), umma::make_desc(a0, 128u, (uint32_t)PL), umma::make_desc(b0, 128u, (uint32_t)PL), idesc, 1u);
         }
     }
 }
@@ -235,11 +238,11 @@ __device__ __forceinline__ void issue_wgrad_tap(uint32_t d0, uint32_t a_hi, uint
 // One MMA per chunk of 8 channels: its K = 16 step pairs the chunk's hi plane with its lo plane (LBO = N8 planes) against
 // the identity block of that chunk, stored twice (one copy per K half).
 template <int N8, int N, int HALO, int PL>
-__device__ __forceinline__ void issue_ident(uint32_t d, uint32_t a_hi, uint32_t idm) {
+__device__ __forceinline__ void issue_ident(bool leader, uint32_t d, uint32_t a_hi, uint32_t idm) {
     constexpr uint32_t idesc = umma::make_idesc_bf16(128, N, false, false);
 #pragma unroll
     for (int c = 0; c < N8; ++c)
-        umma::mma_bf16(d, umma::make_desc(a_hi + (uint32_t)(c * PL + HALO * 16), (uint32_t)(N8 * PL), 128u),
+        if (leader) umma::mma_bf16(d, umma::make_desc(a_hi + (uint32_t)(c * PL + HALO * 16), (uint32_t)(N8 * PL), 128u),
                        umma::make_desc(idm + (uint32_t)(c * 1024), 512u, 128u), idesc, 1u);
 }
 
@@ -329,15 +332,27 @@ struct HeadLite {
 };
 }  // namespace ws
 
+#ifdef GAITK_WS_TIMING          // phase clocks of group 0 in CTA 0 (row thread 0 / issuing lane), printed at the end
+#define WT(i) do { if (wt_on) { const long long t_ = clock64(); wt_acc[i] += t_ - wt_last; wt_last = t_; } } while (0)
+#else
+#define WT(i) do { } while (0)
+#endif
+
 template <class Cfg, int G, int K>
 __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(const StreamArgs A) {
+#ifdef GAITK_WS_TIMING
+    long long wt_acc[16], wt_last = 0; bool wt_on = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wt_acc[i] = 0;
+#endif
     using L = WsLayout<Cfg, G>;
     constexpr int CIN = L::CIN, KT1 = L::KT1, H = L::H, C = L::C, HALO = L::HALO, PL = L::PL;
     constexpr bool INS = L::INS;
     constexpr int NX8 = L::NX8, NX8E = L::NX8E, NH8 = L::NH8, NH8E = L::NH8E, NC8 = L::NC8, NS8 = L::NS8, N1 = L::N1, O1 = L::O1, NH = L::NH;
     constexpr int NPH = INS ? 6 : 4;                       // operand-ready points per training tile
     extern __shared__ __align__(1024) uint8_t smw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // warp-uniform for the compiler too (uniform datapath)
     const bool train = A.mode != MODE_FWD;
     float* f32 = reinterpret_cast<float*>(smw + L::O_F32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smw + L::O_BAR);
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     if (warp < 4) {                                        // persistent accumulator columns start at zero
         for (int c = L::C_W1; c < L::C_END; c += 8) ws::st_zero_x8(tmem + ((uint32_t)(warp * 32) << 16) + c);
         ws::st_wait();
@@ -416,11 +431,11 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     auto tile_of = [&](int it, int g) { return (it * (int)gridDim.x + (int)blockIdx.x) * G + g; };
     constexpr int ROW_WARPS = 4 * G;
 
-    if (warp < 4) {                                        // warps 0..3: the hardware arbiter prefers HIGH warp ids, so the
-                                                           // polling service warps never take an issue slot from a row warp
+    if (warp >= ROW_WARPS) {                               // the LAST warpgroup: the hardware arbiter prefers high warp ids, so an
+                                                           // MMA / TMA issue never queues behind the row warps' epilogue instructions
         // ====================================================================================== service warpgroup
         ws::reg_dec<L::REG_SERVICE>();
-        const int sw = warp;
+        const int sw = warp - ROW_WARPS;
         const uint32_t zero = sbase + L::O_ZERO, idm = sbase + L::O_ID;
         // Service warp s is the MMA + TMA warp of group s: lane 0 issues all of that group's MMAs in the group's natural
         // order with blocking (hardware-suspended) mbarrier waits, the whole warp stages the next tile's windows.  Issuing a
@@ -434,99 +449,125 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
             const uint32_t gb = sbase + g * L::GRP, acc = tmem + g * 32;
             uint8_t* gbp = smw + g * L::GRP;
             const int per_win = 64 * CIN;
-            auto load_tile = [&](int it) {                 // whole warp: windows of tile `it` -> staging (inside F|Z), labels
-                const int tile = tile_of(it, g);
+            // window w's source address for the NEXT load_tile call, held by lane w (its win_start entry is read one tile ahead:
+            // no global-load latency on the issuing path)
+            const float* src_next = nullptr;
+            auto prefetch_src = [&](int it) {
                 if (lane < 2) {
-                    const int wi = tile * 2 + lane;
-                    reinterpret_cast<int*>(gbp + L::O_YS)[(it & 1) * 2 + lane] = (A.mode == MODE_FUSED && wi < A.B) ? (int)A.y[wi] : 0;
+                    const int wi = tile_of(it, g) * 2 + lane;
+                    src_next = (it < nit && wi < A.B && !A.zero_input)
+                                   ? A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win) : nullptr;
                 }
+            };
+            auto load_tile = [&](int it) {                 // whole warp: windows of tile `it` -> staging (inside F|Z)
+                const float* src0 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src_next, 0);
+                const float* src1 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src_next, 1);
+                prefetch_src(it + 1);
                 uint32_t bytes = 0;
-                if (!A.zero_input) {
-                    for (int w = 0; w < 2; ++w) {
-                        const int wi = tile * 2 + w;
-                        if (wi >= A.B) continue;
-                        const float* src = A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win);
-                        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) { bytes += (uint32_t)per_win * 4u; continue; }
-                        for (int e = lane; e < per_win; e += 32) {        // unaligned window: plain copy into the same staging layout
-                            const int t = e / CIN, j = t / L::FPC;
-                            reinterpret_cast<float*>(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16)[e - j * L::FPC * CIN] = __ldg(src + e);
-                        }
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const float* src = w ? src1 : src0;
+                    if (!src) continue;
+                    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) { bytes += (uint32_t)per_win * 4u; continue; }
+                    for (int e = lane; e < per_win; e += 32) {            // unaligned window: plain copy into the same staging layout
+                        const int t = e / CIN, j = t / L::FPC;
+                        reinterpret_cast<float*>(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16)[e - j * L::FPC * CIN] = __ldg(src + e);
                     }
                 }
                 __syncwarp();
+                WT(11);
                 if (lane == 0) {
                     if (bytes == 0) {
                         umma::mbar_arrive(bar_ld(g));
                     } else {
-                        umma::fence_smem_to_async();
+                        // (no proxy fence here: the row threads fenced their generic writes to F / Z before the arrivals this
+                        // thread has observed, and the MMAs that read them have completed)
                         umma::mbar_expect_tx(bar_ld(g), bytes);
+                        WT(12);
+#pragma unroll
                         for (int w = 0; w < 2; ++w) {
-                            const int wi = tile * 2 + w;
-                            if (wi >= A.B) continue;
-                            const float* src = A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win);
-                            if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) continue;
+                            const float* src = w ? src1 : src0;
+                            if (!src || (reinterpret_cast<uintptr_t>(src) & 15) != 0) continue;
 #pragma unroll
                             for (int j = 0; j < L::CPW; ++j) {
                                 const int fr = (j + 1) * L::FPC <= 64 ? L::FPC : 64 - j * L::FPC;
                                 umma::bulk_g2s(gbp + (L::P_F + w * L::CPW + j) * PL + HALO * 16, src + j * L::FPC * CIN, (uint32_t)(fr * CIN * 4), bar_ld(g));
                             }
                         }
+                        WT(13);
                     }
                 }
                 __syncwarp();
             };
+            const bool leader = umma::elect_one();
             auto wait_rdy = [&](int k, uint32_t par) { umma::mbar_wait(bar_rdy(g, k), par); umma::fence_after_sync(); };
+            auto commit = [&](uint64_t* bar) { if (leader) umma::commit(bar); };
+            prefetch_src(0);
             load_tile(0);
+#ifdef GAITK_WS_TIMING
+            wt_on = blockIdx.x == 0 && g == 0 && lane == 0; wt_last = clock64();
+#endif
             for (int it = 0; it < nit; ++it) {
                 const uint32_t par = it & 1;
-                if (lane == 0) {
-                    int k = 0;
+                int k = 0;
+                wait_rdy(k++, par);
+                WT(0);
+                ws::issue_conv<KT1, NX8, N1, (N1 <= 16), HALO, PL>(leader, acc, gb + L::P_X * PL, zero, sbase + L::O_W1);
+                commit(bar_done(g));
+                WT(1);
+                if constexpr (INS) {
                     wait_rdy(k++, par);
-                    ws::issue_conv<KT1, NX8, N1, (N1 <= 16), HALO, PL>(acc, gb + L::P_X * PL, zero, sbase + L::O_W1);
-                    umma::commit(bar_done(g));
-                    if constexpr (INS) {
-                        wait_rdy(k++, par);
-                        ws::issue_conv<3, NH8, 16, true, HALO, PL>(acc, gb + L::P_HA * PL, zero, sbase + L::O_W2);
-                        umma::commit(bar_done(g));
-                    }
-                    wait_rdy(k++, par);
-                    ws::issue_conv<3, NC8, 16, true, HALO, PL>(acc, gb + L::P_F * PL, zero, sbase + L::O_WB);
-                    umma::commit(bar_done(g));
-                    if (train) {
-                        wait_rdy(k++, par);                // dz is in the Z planes
-                        ws::issue_conv<3, NS8, 16, true, HALO, PL>(acc, gb + L::P_Z * PL, zero, sbase + L::O_WBD);
-                        umma::commit(bar_done(g));
-                        ws::issue_ident<NS8, 16, HALO, PL>(tmem + L::C_BB, gb + L::P_Z * PL, idm);
-                        ws::issue_wgrad<3, true, HALO, PL>(tmem + L::C_WB, gb + L::P_F * PL, gb + L::P_Z * PL);
-                        umma::commit(bar_free(g));
-                        wait_rdy(k++, par);                // dA is in the XH planes (and the backbone data gradient has been consumed)
-                        if constexpr (INS) {
-                            ws::issue_conv<3, NC8, NH, false, HALO, PL>(acc, gb + L::P_XH * PL, zero, sbase + L::O_W2D);
-                            umma::commit(bar_done(g));
-                            ws::issue_wgrad<3, true, HALO, PL>(tmem + L::C_W2, gb + L::P_HA * PL, gb + L::P_XH * PL);
-                            ws::issue_ident<NC8, 16, HALO, PL>(tmem + L::C_B2, gb + L::P_XH * PL, idm);
-                            umma::commit(bar_wfree(g));
-                        }
-                    } else {
-                        umma::commit(bar_free(g));
-                    }
-                    umma::mbar_wait(bar_free(g), par);     // the backbone MMAs have read F and Z: the staging area is free
+                    ws::issue_conv<3, NH8, 16, true, HALO, PL>(leader, acc, gb + L::P_HA * PL, zero, sbase + L::O_W2);
+                    commit(bar_done(g));
                 }
-                __syncwarp();
+                wait_rdy(k++, par);
+                WT(2);
+                ws::issue_conv<3, NC8, 16, true, HALO, PL>(leader, acc, gb + L::P_F * PL, zero, sbase + L::O_WB);
+                commit(bar_done(g));
+                WT(3);
+                if (train) {
+                    wait_rdy(k++, par);                    // dz is in the Z planes
+                    WT(4);
+                    ws::issue_conv<3, NS8, 16, true, HALO, PL>(leader, acc, gb + L::P_Z * PL, zero, sbase + L::O_WBD);
+                    commit(bar_done(g));
+                    WT(5);
+                    ws::issue_ident<NS8, 16, HALO, PL>(leader, tmem + L::C_BB, gb + L::P_Z * PL, idm);
+                    ws::issue_wgrad<3, true, HALO, PL>(leader, tmem + L::C_WB, gb + L::P_F * PL, gb + L::P_Z * PL);
+                    commit(bar_free(g));
+                    WT(6);
+                } else {
+                    commit(bar_free(g));
+                }
+                // this warp's backbone MMAs (data gradient included) have read F and Z: the staging area inside them is free
+                umma::mbar_wait(bar_free(g), par);
+                WT(7);
                 if (it + 1 < nit) load_tile(it + 1);
-                if (lane == 0 && train) {
+                WT(8);
+                if (train) {
+                    wait_rdy(INS ? 4 : 3, par);            // dA is in the XH planes
+                    WT(9);
                     if constexpr (INS) {
+                        ws::issue_conv<3, NC8, NH, false, HALO, PL>(leader, acc, gb + L::P_XH * PL, zero, sbase + L::O_W2D);
+                        commit(bar_done(g));
+                        ws::issue_wgrad<3, true, HALO, PL>(leader, tmem + L::C_W2, gb + L::P_HA * PL, gb + L::P_XH * PL);
+                        ws::issue_ident<NC8, 16, HALO, PL>(leader, tmem + L::C_B2, gb + L::P_XH * PL, idm);
+                        commit(bar_wfree(g));
                         wait_rdy(5, par);                  // dA1 is in the HA planes: lanes = conv1 output channel, columns = input channel
-                        ws::issue_ident<NH8, N1, HALO, PL>(tmem + L::C_B1, gb + L::P_HA * PL, idm);
-                        ws::issue_wgrad<KT1, false, HALO, PL>(tmem + L::C_W1, gb + L::P_HA * PL, gb + L::P_X * PL);
+                        ws::issue_ident<NH8, N1, HALO, PL>(leader, tmem + L::C_B1, gb + L::P_HA * PL, idm);
+                        ws::issue_wgrad<KT1, false, HALO, PL>(leader, tmem + L::C_W1, gb + L::P_HA * PL, gb + L::P_X * PL);
                     } else {
-                        ws::issue_ident<NC8, 16, HALO, PL>(tmem + L::C_B1, gb + L::P_XH * PL, idm);
-                        ws::issue_wgrad<KT1, true, HALO, PL>(tmem + L::C_W1, gb + L::P_X * PL, gb + L::P_XH * PL);
+                        ws::issue_ident<NC8, 16, HALO, PL>(leader, tmem + L::C_B1, gb + L::P_XH * PL, idm);
+                        ws::issue_wgrad<KT1, true, HALO, PL>(leader, tmem + L::C_W1, gb + L::P_X * PL, gb + L::P_XH * PL);
                     }
-                    umma::commit(bar_done(g));
+                    commit(bar_done(g));
+                    WT(10);
                 }
-                __syncwarp();
             }
+#ifdef GAITK_WS_TIMING
+            if (wt_on) printf("ISSUER CIN%d nit %d: rdy0 %lld conv1 %lld | rdy1 %lld bb %lld | rdyZ %lld dgrad %lld wgradbb %lld | free %lld load %lld rdydA %lld wgrad1(+conv2 bwd) %lld || load: pre %lld expect %lld bulk %lld\n", CIN, nit,
+                              wt_acc[0] / nit, wt_acc[1] / nit, wt_acc[2] / nit, wt_acc[3] / nit, wt_acc[4] / nit, wt_acc[5] / nit, wt_acc[6] / nit, wt_acc[7] / nit, wt_acc[8] / nit, wt_acc[9] / nit, wt_acc[10] / nit,
+                              wt_acc[11] / nit, wt_acc[12] / nit, wt_acc[13] / nit);
+#endif
         }
         umma::fence_before_sync();
         asm volatile("bar.sync 0;" ::: "memory");
@@ -539,12 +580,11 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
 #pragma unroll
         for (int i = 0; i < 16; ++i) { g_lng[i] = 0.f; g_lnb[i] = 0.f; }
         head.zero();
-        const int rw = warp - 4;                           // row warp index
+        const int rw = warp;                               // row warp index
         const int g = rw >> 2, wq = rw & 3, r = wq * 32 + lane;
         uint8_t* gb = smw + g * L::GRP;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + g * 32;
         float* Ps = reinterpret_cast<float*>(gb + L::O_P); float* DPs = reinterpret_cast<float*>(gb + L::O_DP);
-        const int* ys = reinterpret_cast<const int*>(gb + L::O_YS);
         const float inv_denom = (A.mode == MODE_FUSED) ? 1.0f / A.denom[0] : 0.f;
         const float* b1s = f32 + L::F_B1; const float* b2s = f32 + L::F_B2; const float* lngs = f32 + L::F_LNG; const float* lnbs = f32 + L::F_LNB;
         const float* bbs = f32 + L::F_BB;
@@ -552,12 +592,19 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         auto arrive = [&](int k) { umma::fence_smem_to_async(); umma::fence_before_sync(); umma::mbar_arrive(bar_rdy(g, k)); };
         auto wait_done = [&]() { umma::mbar_wait(bar_done(g), dph); dph ^= 1u; umma::fence_after_sync(); };
         const int t = r >> 1, w = r & 1;
+#ifdef GAITK_WS_TIMING
+        wt_on = blockIdx.x == 0 && g == 0 && r == 0; wt_last = clock64();
+#endif
         for (int it = 0; it < nit; ++it) {
             const uint32_t par = it & 1;
             const int tile = tile_of(it, g), win0 = tile * 2;
             int kk = 0;
+            // the head warps fetch their window's label now; it is consumed a few thousand clocks later
+            int ylab = 0;
+            if (wq < 2 && A.mode == MODE_FUSED && win0 + wq < A.B) ylab = (int)A.y[win0 + wq];
             // ------------------------------------------------ staged window bytes -> X planes (hi, lo)
             umma::mbar_wait(bar_ld(g), par);
+            WT(0);
             if (!A.zero_input) {
                 const bool live = win0 + w < A.B;
                 const int j = t / L::FPC;
@@ -580,9 +627,11 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                 ws::store_split<NX8 * 8, PL>(gb + L::P_X * PL, HALO + r, v);
             }
             arrive(kk++);
+            WT(1);
             // ------------------------------------------------ encoder forward
             if constexpr (INS) {
                 wait_done();
+                WT(2);
                 {
                     float a1[N1], ha[NH8 * 8], d1[NH8 * 8];
                     umma::ld_x16(trow, a1); umma::ld_x8(trow + 16, a1 + 16); umma::ld_wait();
@@ -592,8 +641,10 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                     if (train) ws::store_half<NH8 * 8, PL>(gb + L::P_D1 * PL, HALO + r, d1);
                 }
                 arrive(kk++);
+                WT(3);
             }
             wait_done();
+            WT(4);
             float rstd_row = 0.f;
             {
                 float a[16], gl[16], d[16], xh[16], f[16]; float rstd;
@@ -617,8 +668,10 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                 }
             }
             arrive(kk++);
+            WT(5);
             // ------------------------------------------------ shared backbone forward: ReLU + adaptive pooling (8 frames per bin)
             wait_done();
+            WT(6);
             uint32_t zmask = 0;
             {
                 float z[16];
@@ -640,10 +693,13 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                 const int ch = (h8 ? 8 : 0) + (h4 ? 4 : 0) + (h2 ? 2 : 0);
                 *reinterpret_cast<float2*>(Ps + w * 128 + (r >> 4) * 16 + ch) = make_float2(a2[0] * 0.125f, a2[1] * 0.125f);
             }
+            WT(7);
             ws::bar_sync(1 + g, 128);
+            WT(8);
             // ------------------------------------------------ head + loss: warp q < 2 <-> window q of the tile
-            if (wq < 2) head.run(A, Ps + wq * 128, DPs + wq * 128, f32 + L::F_HW, f32 + L::F_HB, lane, win0 + wq, train, inv_denom, ys[par * 2 + wq]);
+            if (wq < 2) head.run(A, Ps + wq * 128, DPs + wq * 128, f32 + L::F_HW, f32 + L::F_HB, lane, win0 + wq, train, inv_denom, ylab);
             ws::bar_sync(1 + g, 128);
+            WT(9);
             if (!train) continue;
             // ------------------------------------------------ dz through pooling + ReLU -> Z planes
             {
@@ -656,8 +712,10 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                 ws::store_split<16, PL>(gb + L::P_Z * PL, HALO + r, dz);
             }
             arrive(kk++);
+            WT(10);
             // ------------------------------------------------ LayerNorm / GELU backward -> dA (over XH)
             wait_done();
+            WT(11);
             {
                 float df[16], xh[16], dxh[16], dg[16], d[(C + 3) / 4 * 4], da[16];
                 ws::ld_merged16(trow, df);
@@ -681,6 +739,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                 ws::store_split<16, PL>(gb + L::P_XH * PL, HALO + r, da);
             }
             arrive(kk++);
+            WT(12);
             if constexpr (INS) {
                 // ------------------------------------------------ conv2 data gradient -> dA1 (over HA, once conv2's weight gradient has read it)
                 wait_done();
@@ -694,9 +753,16 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                     ws::store_split<NH8 * 8, PL>(gb + L::P_HA * PL, HALO + r, da1);
                 }
                 arrive(kk++);
+                WT(13);
             }
             wait_done();                                   // the first-layer weight gradient has read X and dA: the tile's buffers are free
+            WT(14);
         }
+#ifdef GAITK_WS_TIMING
+        if (wt_on) printf("ROW    CIN%d nit %d: ld %lld conv %lld | w1 %lld e1 %lld | w %lld enc %lld | wbb %lld pool %lld bar %lld head %lld | dz %lld | wdg %lld lnb %lld | ins %lld | wfinal %lld\n", CIN, nit,
+                          wt_acc[0] / nit, wt_acc[1] / nit, wt_acc[2] / nit, wt_acc[3] / nit, wt_acc[4] / nit, wt_acc[5] / nit, wt_acc[6] / nit, wt_acc[7] / nit, wt_acc[8] / nit, wt_acc[9] / nit,
+                          wt_acc[10] / nit, wt_acc[11] / nit, wt_acc[12] / nit, wt_acc[13] / nit, wt_acc[14] / nit);
+#endif
         // -------------------------------------------------------------------------------------- teardown + flush
         umma::fence_before_sync();
         asm volatile("bar.sync 0;" ::: "memory");          // every group has seen its last commit: all MMAs are complete
@@ -726,7 +792,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
             }
         }
         ws::bar_sync(15, ROW_WARPS * 32);
-        const int rt = tid - 128;                          // row threads 0 .. 128 G - 1
+        const int rt = tid;                                // row threads 0 .. 128 G - 1
         if (rt < 2 * C) {
             const int c = rt % C, which = rt / C;
             float s = 0.f;
