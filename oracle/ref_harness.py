@@ -162,7 +162,7 @@ def write_synthetic_weargait(root: Path, n_per_class: int = 6, seed: int = 0, fr
         for i in range(n_per_class):
             sid = f"{tag}{i + 1:03d}"
             (d / f"{sid}_SelfPace_matTURN.csv").write_text("x\n")
-            N = int(rng.integers(frames[0], frames[1]))
+            N = int(rng.integers(frames[0], frames[1]) * (1.4 if cls == 1 else 1.0))   # unequal class counts (GCL is NaN for equal ones)
             wk = pd.DataFrame({c: rng.random(N) for c in DW.WALKWAY_FIXED})
             Ni = N - int(rng.integers(0, 70))
             ins = pd.DataFrame({c: rng.standard_normal(Ni) for c in DW.INSOLE_NUMERIC[:7]})

@@ -167,3 +167,33 @@ def test_mask_table_arithmetic_matches_the_reference_formulas():
                 want[nm] = sum(accs) / 2
         want["macro_enabled"] = sum(want.values()) / len(want)
         assert res == want, (name, res, want)
+
+
+def test_pkl_reader_matches_the_reference_loader(tmp_path):
+    """load_subject_frames (the reference's on-disk format: three pickled 30 Hz DataFrames per subject, tuple-packed
+    accelerations) against the reference's own load_subject_streams + expand_* + ensure_cols, when a reference copy exists."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    import ref_harness as H
+    R = H.load_reference()
+    if R is None:
+        pytest.skip("no reference copy (oracle/_ref or /root/reference)")
+    import pandas as pd
+    import gaitk
+    DW = R.DW
+    sids, _ = H.write_synthetic_weargait(tmp_path, n_per_class=2, seed=3, frames=(80, 160))
+    d = tmp_path / "data" / "WearGait" / "WearGait_preproc_SPmT_30Hz"
+    # damage one subject the way real recordings are damaged: a missing IMU site, an all-NaN insole column, a NaN run, no walkway
+    imu = pd.read_pickle(d / f"{sids[1]}_imu.pkl").drop(columns=["R_LatShank_FreeAcc"]); imu.to_pickle(d / f"{sids[1]}_imu.pkl")
+    ins = pd.read_pickle(d / f"{sids[1]}_insole.pkl"); ins["RCoP_Y"] = np.nan; ins.loc[3:9, "LCoP_X"] = np.nan; ins.to_pickle(d / f"{sids[1]}_insole.pkl")
+    (d / f"{sids[2]}_walkway.pkl").unlink()
+    for sid in sids:
+        got = gaitk.dataloader_weargait.load_subject_frames(d, sid)
+        st = DW.load_subject_streams(d, sid)
+        ref_w = DW.ensure_cols(st["walkway"], DW.WALKWAY_FIXED).to_numpy(dtype=float)
+        ref_i = DW.expand_insole(st["insole"]); ref_m = DW.expand_imu(st["imu"])
+        assert got["walkway"].shape == ref_w.shape and np.array_equal(got["walkway"], ref_w)
+        assert np.array_equal(got["insole"], ref_i.to_numpy(dtype=float), equal_nan=True), sid
+        assert np.array_equal(got["imu"], ref_m.to_numpy(dtype=float), equal_nan=True), sid
+    assert list(gaitk.dataloader_weargait.INSOLE_FIXED) == list(DW.INSOLE_FIXED) and list(gaitk.dataloader_weargait.IMU_FIXED) == list(DW.IMU_FIXED)

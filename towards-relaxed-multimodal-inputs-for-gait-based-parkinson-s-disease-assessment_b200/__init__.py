@@ -12,6 +12,7 @@ from . import dataloader_weargait
 from . import evaluation
 from .evaluation import MASK_COMBOS, eval_all_masks, eval_with_mask, eval_one_epoch
 from . import dist
+from . import integration
 
 __all__ = ["GaitkError", "lib", "Plan", "FlatParamModule", "WearGaitThreeModal", "LateFusion3", "SharedLatent3", "MultiModalMultiTaskModel", "SensorModalityModel", "SkelModalityModel",
            "GCLLoss", "LDAMLoss", "CrossEntropyLoss", "make_loss_desc", "criterion_spec", "CAGrad", "FusedTrainStep"]

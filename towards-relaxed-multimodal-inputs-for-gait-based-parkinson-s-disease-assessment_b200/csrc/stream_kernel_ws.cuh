@@ -6,7 +6,7 @@
 // bias-gradient MMAs nobody waits for behind them), the warp issues the TMA bulk copies (cp.async.bulk) of the group's
 // next tile + labels.
 //
-// Row warps and service warps talk through mbarriers only (per group: operands-ready rdy[k] with 128 arrivals, done /
+// Row warps and service warps talk through mbarriers only (per group: operands-ready rdy[k] with one arrival per row warp, done /
 // free / wfree committed by tcgen05.commit, ld completed by the bulk copies' transaction bytes), so the tensor core
 // works on one group's convolution while the other groups run their GELU / LayerNorm / pooling / head epilogues: the
 // barrier -> issue -> spin cycle of stream_kernel_tc.cuh is gone, and so is every CTA-wide barrier in the tile loop.
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     __syncthreads();
     if (tid == 0) {
         for (int g = 0; g < G; ++g) {
-            for (int k = 0; k < WS_NPH; ++k) umma::mbar_init(bar_rdy(g, k), 128);
+            for (int k = 0; k < WS_NPH; ++k) umma::mbar_init(bar_rdy(g, k), 4);      // one arrival per row warp
             umma::mbar_init(bar_done(g), 1); umma::mbar_init(bar_free(g), 1); umma::mbar_init(bar_wfree(g), 1); umma::mbar_init(bar_ld(g), 1);
         }
         umma::fence_mbar_init();
@@ -589,7 +589,13 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         const float* b1s = f32 + L::F_B1; const float* b2s = f32 + L::F_B2; const float* lngs = f32 + L::F_LNG; const float* lnbs = f32 + L::F_LNB;
         const float* bbs = f32 + L::F_BB;
         uint32_t dph = 0;                                  // parity of the group's `done` barrier
-        auto arrive = [&](int k) { umma::fence_smem_to_async(); umma::fence_before_sync(); umma::mbar_arrive(bar_rdy(g, k)); };
+        // every thread orders its operand stores before the async proxy, the warp converges, ONE lane arrives (128 arrivals on one
+        // shared-memory word serialise 32-way per warp instruction: half of all shared-memory wavefronts in the v10 profile)
+        auto arrive = [&](int k) {
+            umma::fence_smem_to_async(); umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(bar_rdy(g, k));
+        };
         auto wait_done = [&]() { umma::mbar_wait(bar_done(g), dph); dph ^= 1u; umma::fence_after_sync(); };
         const int t = r >> 1, w = r & 1;
 #ifdef GAITK_WS_TIMING

@@ -13,9 +13,10 @@ Here a fold is prepared ONCE on the device:
     (:278-299, :311-334), and the batch order comes from torch's own DataLoader sampler machinery driven by the same
     ``torch.Generator`` protocol as the reference loaders (:420-455), so a seed gives the same batches.
 
-Input: instead of a directory of pickled DataFrames (the ETL is out of scope) ``prepare_split`` takes
-``frames[sid][modality]`` = float64 (N_frames, D) in the reference's fixed column order (WALKWAY_FIXED / INSOLE_FIXED /
-IMU_FIXED), NaN where a value or a whole column is missing.
+Input: ``prepare_split(train, test, data_dir=...)`` reads the reference's on-disk format -- per subject three pickled
+DataFrames ``<sid>_{walkway,insole,imu}.pkl`` at 30 Hz with tuple-packed accelerations (``load_subject_frames``, restating
+:141-180) -- or takes ``frames[sid][modality]`` = float64 (N_frames, D) directly, in the reference's fixed column order
+(WALKWAY_FIXED / INSOLE_FIXED / IMU_FIXED), NaN where a value or a whole column is missing.
 """
 from __future__ import annotations
 
@@ -28,7 +29,16 @@ import torch
 
 from . import _lib
 
+from pathlib import Path
+
+DEFAULT_DATA_DIR = Path("data/WearGait/WearGait_preproc_SPmT_30Hz")      # dataloader_weargait.py:27
 DEFAULT_MODALITIES = ("walkway", "insole", "imu")
+# fixed channel order of the three streams (:29-50)
+IMU_SITES = ["L_Ankle", "R_Ankle", "L_DorsalFoot", "R_DorsalFoot", "L_MidLatThigh", "R_MidLatThigh", "L_LatShank", "R_LatShank"]
+WALKWAY_FIXED = ["L Foot Pressure_BW", "R Foot Pressure_BW"]
+INSOLE_FIXED = ["LTotalForce_BW", "RTotalForce_BW", "SumForce_BW", "LCoP_X", "LCoP_Y", "RCoP_X", "RCoP_Y",
+                "Linsole_Acc_X", "Linsole_Acc_Y", "Linsole_Acc_Z", "Rinsole_Acc_X", "Rinsole_Acc_Y", "Rinsole_Acc_Z"]
+IMU_FIXED = [f"{s}_FreeAcc_{ax}" for s in IMU_SITES for ax in ("E", "N", "U")]
 MODALITY_DIM = {"walkway": 2, "insole": 13, "imu": 24}
 NORMALISED = ("insole", "imu")                  # walkway is used as is (build_windows_per_subject :248-253)
 MIN_STD = 1e-6
@@ -119,6 +129,46 @@ class WindowStore(Mapping):
         return out
 
 
+# ---------------------------------------------------------------------------------------------- on-disk format (30 Hz PKLs)
+def _column(df, name: str, n: int) -> np.ndarray:
+    """one fixed column as float64 the way expand_* / ensure_cols leave it (:76-91 without statistics): an absent column and a
+    column without a single finite value are 0.0 (so they DO enter the train statistics as zeros and z-score to (0 - mean) / std,
+    exactly as in the reference); non-numeric cells -> NaN (pd.to_numeric(errors='coerce')); isolated NaNs stay NaN and become the
+    train mean on the device (apply_stats :217)."""
+    import pandas as pd
+    if name not in df.columns:
+        return np.zeros(n, dtype=np.float64)
+    x = pd.to_numeric(df[name], errors="coerce").to_numpy(dtype=float)
+    return x if np.isfinite(x).any() or not n else np.zeros(n, dtype=np.float64)
+
+
+def load_subject_frames(data_dir, sid: str) -> Dict[str, np.ndarray]:
+    """load_subject_streams + expand_insole / expand_imu + ensure_cols (:76-91, :141-180) for one subject:
+    ``<sid.lower()>_{walkway,insole,imu}.pkl`` -> {modality: float64 (N_frames, D)} in the fixed column order.  A missing file
+    gives zero frames; tuple columns (``Linsole_Acc``, ``<site>_FreeAcc``) are unpacked into their three axes; a missing or
+    entirely non-finite column is 0.0 (see _column)."""
+    import pandas as pd
+    out = {}
+    for m, fixed, tuples in (("walkway", WALKWAY_FIXED, ()), ("insole", INSOLE_FIXED, (("Linsole_Acc", ("X", "Y", "Z")), ("Rinsole_Acc", ("X", "Y", "Z")))),
+                             ("imu", IMU_FIXED, tuple((f"{s_}_FreeAcc", ("E", "N", "U")) for s_ in IMU_SITES))):
+        path = Path(data_dir) / f"{sid.lower()}_{m}.pkl"
+        df = pd.read_pickle(path) if path.exists() else pd.DataFrame()
+        n = len(df)
+        if n:
+            df = df.copy()
+            for col, axes in tuples:
+                if col in df.columns:
+                    arr = np.vstack([np.asarray(t, dtype=float) for t in df[col].astype(object)])
+                    for i, ax in enumerate(axes):
+                        df[f"{col}_{ax}"] = arr[:, i]
+                    df = df.drop(columns=[col])
+        X = np.empty((n, len(fixed)), dtype=np.float64)
+        for j, c in enumerate(fixed):
+            X[:, j] = _column(df, c, n)
+        out[m] = X
+    return out
+
+
 def _as_f64(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
 
@@ -189,11 +239,14 @@ def build_sync_pairs(stores: Mapping[str, WindowStore], subjects: Sequence[str],
     return pairs
 
 
-def prepare_split(train_subs: Sequence[str], test_subs: Sequence[str], *, frames, win: int = 64, hop: int = 64,
-                  modalities: Tuple[str, ...] = DEFAULT_MODALITIES, device="cuda") -> Dict[str, Any]:
-    """:388-418: statistics on train only, normalise and window train + test, build the sync index.  Same keys in the
-    returned dict as the reference; the stores are device-resident ``WindowStore`` objects."""
+def prepare_split(train_subs: Sequence[str], test_subs: Sequence[str], *, data_dir=DEFAULT_DATA_DIR, win: int = 64, hop: int = 64,
+                  modalities: Tuple[str, ...] = DEFAULT_MODALITIES, frames=None, device="cuda") -> Dict[str, Any]:
+    """:388-418 (same call signature): statistics on train only, normalise and window train + test, build the sync index.
+    Same keys in the returned dict as the reference; the stores are device-resident ``WindowStore`` objects.  ``frames``
+    (optional) bypasses the PKL directory."""
     train_subs = list(train_subs); test_subs = list(test_subs)
+    if frames is None:
+        frames = {sid: load_subject_frames(data_dir, sid) for sid in dict.fromkeys(train_subs + test_subs)}
     stats = fit_stats_on_train(train_subs, frames, device)
     train_stores = {m: build_store(train_subs, frames, m, stats, win, hop, device) for m in modalities}
     test_stores = {m: build_store(test_subs, frames, m, stats, win, hop, device) for m in modalities}
