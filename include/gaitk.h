@@ -40,6 +40,7 @@ extern "C" {
 #define GAITK_FAMILY_FOG      1   /* train/feature_encoder.py:149-265 MultiModalMultiTaskModel   */
 
 #define GAITK_MAX_STREAMS 3
+#define GAITK_DENOM_COUNT  24   /* denom[GAITK_DENOM_COUNT + s] = number of labels in stream s's GLOBAL label vector (KL batchmean) */
 #define GAITK_DENOM_FLOATS 32   /* size of the `denom` device buffer: [0..3] results, the rest scratch of gaitk_loss_denominators */
 #define GAITK_MAX_CLASSES 4
 #define GAITK_MAX_PASSES  6
@@ -161,7 +162,11 @@ int gaitk_backward(gaitk_plan* plan, const float* params, const float* const* x,
  *            multiplied by private_mult) | loss[n] | correct[n] ]
  * y[s] int64[B]; denom[s] = global sum_b w[y_b] (device float[1] per stream, see
  * gaitk_loss_denominators) so that shards of a data-parallel batch add up.
- * task_mask bit t clear => task t skipped (relaxed-input training with a dropped stream). */
+ * task_mask bit t clear => task t skipped (relaxed-input training with a dropped stream).
+ * consistency_lambda != 0 (two-stream plans; fbg_fog_train.py:81-89,121-124): every loss gains
+ * 0.5 lambda (KL(softmax_1 || softmax_0) + KL(softmax_0 || softmax_1)) ('batchmean' over the GLOBAL batch,
+ * denom[GAITK_DENOM_COUNT]), differentiated through both streams: a logits pass, one coupling kernel, then one
+ * recompute + backward pass per (task, stream). */
 int gaitk_step_grads(gaitk_plan* plan, const float* params, const float* const* x,
                      const int64_t* const* win_start, const int64_t* const* y, int B,
                      const gaitk_loss_desc* loss /*[n_streams]*/, const float* const* logit_off,
@@ -262,6 +267,8 @@ int gaitk_umma_selftest_bf16(const uint16_t* A, int nA, const uint16_t* B, int n
 /* Cost model probe: issues the op list `reps` times from one thread (kind::f16, all accumulating), returns SM clocks
  * {first issue -> completion, issue only} in cycles[2] (device int64).  Design evidence for DESIGN.md. */
 int gaitk_umma_bench(const uint32_t* ops, int nops, int reps, int ncols, int smem_bytes, int64_t* cycles, void* stream);
+/* the same with n_issuers (1..4) warps issuing concurrently into disjoint accumulator columns; cycles[2 w], cycles[2 w + 1] per issuer */
+int gaitk_umma_bench_multi(const uint32_t* ops, int nops, int reps, int ncols, int smem_bytes, int n_issuers, int64_t* cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -504,6 +504,33 @@ def data_case(name):
     _save(name, **flat)
 
 
+
+# ------------------------------------------------------------------ FoG / FBG loaders (A5: pairing, oversampling, order)
+def fog_loader_case(name):
+    """create_fusion_loaders (dataloader_fbg_fog.py:269-494) on synthetic readers (oracle/ref_harness.synthetic_fog_reader):
+    key lists / pairs of both datasets after all the oversampling, and what two epochs of both loaders deliver."""
+    import warnings
+    import ref_harness as H
+    flat = {}
+    for cname, dataset, sync, modality, pad_skel, pad_sens in H.FOG_LOADER_CASES:
+        reader, subs = H.synthetic_fog_reader(dataset, seed=5)
+        tr_s, ev_s = H.fog_loader_split(subs, dataset)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr, ev = DF.create_fusion_loaders(dataset, reader, tr_s, ev_s, batch_size=7, synchronized=sync, seed=43, num_workers=0,
+                                              pad_skel=pad_skel, pad_sens=pad_sens, modality=modality)
+            for nm, ld in (("train", tr), ("eval", ev)):
+                ds = ld.dataset
+                flat[f"{cname}/{nm}_pose_keys"] = np.array(ds.pose_ds.keys); flat[f"{cname}/{nm}_sens_keys"] = np.array(ds.sens_ds.keys)
+                flat[f"{cname}/{nm}_len"] = np.array(len(ds))
+                if sync:
+                    flat[f"{cname}/{nm}_pairs"] = np.array(ds.pairs)
+            for k, v in H.loader_trace(tr, ev).items():
+                flat[f"{cname}/{k}"] = v
+    pm = DF.group_by_subject(["A_x_1", "A_y_2", "B_x_1", "A_x_3"]); sm = DF.group_by_subject(["A_x_1", "A_q_x_1", "B_x_1", "B_z_1", "C_x_1"])
+    flat["pairs_small"] = np.array(DF.build_synced_pairs(pm, sm))
+    _save(name, **flat)
+
 def versions():
     import scipy, sklearn
     v = dict(torch=torch.__version__, numpy=np.__version__, scipy=scipy.__version__, pandas=pd.__version__,
@@ -551,6 +578,7 @@ def main():
         "bl_xattn_async": lambda: baseline_case("bl_xattn_async", "cheap_xattn", False),
         "cagrad_corpus": lambda: cagrad_corpus("cagrad_corpus"),
         "data_path": lambda: data_case("data_path"),
+        "fog_loaders": lambda: fog_loader_case("fog_loaders"),
     }
     for k, fn in jobs.items():
         if a.only and a.only != k:

@@ -173,3 +173,77 @@ def write_synthetic_weargait(root: Path, n_per_class: int = 6, seed: int = 0, fr
             wk.to_pickle(out / f"{sid}_walkway.pkl"); ins.to_pickle(out / f"{sid}_insole.pkl"); imu.to_pickle(out / f"{sid}_imu.pkl")
             sids.append(sid); labels.append(cls)
     return sids, labels
+
+
+# ---------------------------------------------------------------------------------------------- synthetic FoG / FBG readers
+def synthetic_fog_reader(dataset: str = "fog", seed: int = 0, n_subjects: int = 9):
+    """An object with the attributes `create_fusion_loaders` reads (dataloader_fbg_fog.py:291-327), in the key formats the
+    reference's readers produce (preprocess_fog.py:107,146: `<SUB>_<video>_<segment>`; FBG: pose `<SUB>_<on|off>_walk_<i>`,
+    GRF `<SUB>_<on|off>_walk` with a trial axis).  Clip lengths straddle the pad lengths; some sensor segments are missing
+    and some have no pose partner, so the synchronised pairing is a proper intersection.  -> (reader, subjects)"""
+    rng = np.random.default_rng(seed)
+    pose, sens = {}, {}
+    if dataset == "fog":
+        subs = [f"SUB{i + 1:02d}" for i in range(n_subjects)]
+        labels = {}
+        for si, sub in enumerate(subs):
+            labels[sub] = [int(si % 3)] if si % 2 == 0 else int(si % 3)       # list and scalar forms (:314-318)
+            for v in range(2):
+                for seg in range(1, 3 + int(rng.integers(0, 2))):
+                    L = int(rng.integers(40, 150))
+                    pose[f"{sub}_v{v}_{seg}"] = rng.random((L, 7, 3)) * 4.0 - 1.0
+                    if rng.random() < 0.85:
+                        Ls = int(rng.integers(140, 520))
+                        sens[f"{sub}_v{v}_{seg}"] = rng.standard_normal((Ls, 6))
+                if rng.random() < 0.5:                                         # a sensor segment without a pose partner
+                    sens[f"{sub}_v{v}_9"] = rng.standard_normal((int(rng.integers(140, 520)), 6))
+        reader = SimpleNamespace(pose_dict=pose, sensor_dict=sens, labels_dict=labels)
+        return reader, subs
+    subs = []
+    pl, sl = {}, {}
+    for si in range(n_subjects):
+        for state in ("on", "off"):
+            if state == "off" and si % 3 == 2:
+                continue
+            sub = f"SUB{si + 1:02d}_{state}"; subs.append(sub)
+            pl[sub] = int((si + (state == "off")) % 3)
+            n_tr = 2 + int(rng.integers(0, 3))
+            for i in range(n_tr):
+                pose[f"{sub}_walk_{i}"] = rng.random((int(rng.integers(60, 130)), 17, 3)) * 2.0
+            grf = rng.standard_normal((int(rng.integers(50, 90)), n_tr + int(rng.integers(0, 2)), 3))
+            sens[f"{sub}_walk"] = grf; sl[f"{sub}_walk"] = pl[sub]
+    reader = SimpleNamespace(pose_dict=pose, sensor_dict=sens, pose_label_dict=pl, sensor_label_dict=sl)
+    return reader, subs
+
+
+FOG_LOADER_CASES = [   # (name, dataset, synchronized, modality, pad_skel, pad_sens)
+    ("fog_sync", "fog", True, "multimodal", 101, 426),
+    ("fog_async", "fog", False, "multimodal", 101, 426),
+    ("fog_skeleton", "fog", False, "skeleton", 101, 426),
+    ("fog_sensor", "fog", False, "sensor", 101, 426),
+    ("fbg_sync", "fbg", True, "multimodal", 101, 65),
+    ("fbg_async", "fbg", False, "multimodal", 101, 65),
+]
+
+
+def fog_loader_split(subs, dataset):
+    """deterministic train / eval split that keeps every class on both sides"""
+    ev = subs[::3]
+    return [s for s in subs if s not in ev], ev
+
+
+def loader_trace(train_loader, eval_loader, epochs: int = 2):
+    """what a trainer sees: per pass and batch, the labels and an order-sensitive fp64 checksum of every sample"""
+    out = {}
+    for ep in range(epochs):
+        for nm, ld in (("train", train_loader), ("eval", eval_loader)):
+            ys, yt, cs, ct, bs = [], [], [], [], []
+            for b in ld:
+                sk = b["skeleton"].detach().cpu().numpy().astype(np.float64); se = b["sensor"].detach().cpu().numpy().astype(np.float64)
+                n = sk.shape[0]; bs.append(n)
+                w1 = np.cos(np.arange(sk[0].size, dtype=np.float64)); w2 = np.cos(np.arange(se[0].size, dtype=np.float64))
+                cs += [float(np.dot(sk[i].ravel(), w1)) for i in range(n)]; ct += [float(np.dot(se[i].ravel(), w2)) for i in range(n)]
+                ys += b["label_skeleton"].tolist(); yt += b["label_sensor"].tolist()
+            out[f"{nm}_ep{ep}/ys"] = np.array(ys); out[f"{nm}_ep{ep}/yt"] = np.array(yt)
+            out[f"{nm}_ep{ep}/cs"] = np.array(cs); out[f"{nm}_ep{ep}/ct"] = np.array(ct); out[f"{nm}_ep{ep}/bs"] = np.array(bs)
+    return out

@@ -44,3 +44,20 @@ for i in range(64):
     d = np.abs(D[:, :16] - ref[i][None, :]).max(1) / np.abs(ref[i]).max()
     lane_of.append(int(np.argmin(d)) if d.min() < 1e-4 else -1)
 print("M=64 accumulator: row -> TMEM lane", lane_of)
+
+# ---- concurrent issuers: is the ~45-clock cost per issuing thread or per tensor pipe?
+def bench_multi(name, ops, n, reps=256, ncols=512):
+    od = torch.from_numpy(np.asarray(ops, dtype=np.uint32).view(np.int32).ravel().copy()).cuda()
+    cyc = torch.zeros(8, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        gaitk._lib.check(L.gaitk_umma_bench_multi(od.data_ptr(), len(ops), reps, ncols, 160 * 1024, n, cyc.data_ptr(), gaitk._lib.stream_handle()))
+        torch.cuda.synchronize()
+    c = cyc.cpu().numpy().reshape(4, 2)[:n]
+    tot = c[:, 0].max()
+    print(f"{name:44s} issuers {n}: {tot / (reps * len(ops)):7.1f} cyc per MMA per issuer -> {tot / (reps * len(ops) * n):6.1f} cyc per MMA overall", flush=True)
+for n in (1, 2, 3, 4):
+    bench_multi("K-major  M=128 N=32", kmajor(128, 32), n)
+for n in (1, 2, 4):
+    bench_multi("MN-major M=64 N=32", mnmajor(64, 32), n)
+for n in (1, 2, 4):
+    bench_multi("K-major  M=128 N=64", kmajor(128, 64), n)

@@ -197,3 +197,39 @@ def test_pkl_reader_matches_the_reference_loader(tmp_path):
         assert np.array_equal(got["insole"], ref_i.to_numpy(dtype=float), equal_nan=True), sid
         assert np.array_equal(got["imu"], ref_m.to_numpy(dtype=float), equal_nan=True), sid
     assert list(gaitk.dataloader_weargait.INSOLE_FIXED) == list(DW.INSOLE_FIXED) and list(gaitk.dataloader_weargait.IMU_FIXED) == list(DW.IMU_FIXED)
+
+
+def test_fog_pairing_and_oversampling_match_the_reference():
+    """A5: build_synced_pairs / oversample_equally / FusionDataset / create_fusion_loaders key logic (dataloader_fbg_fog.py:53-90,
+    170-257, 269-470) against lists the reference itself produced (fog_loaders golden): key lists of both datasets after all the
+    oversampling, the synchronised pairs, and the (pose, sensor, labels) index tables -- host logic only, no device."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    import ref_harness as H
+    import gaitk
+    DF = gaitk.dataloader_fbg_fog
+    g = load_golden("fog_loaders")
+    pm = DF.group_by_subject(["A_x_1", "A_y_2", "B_x_1", "A_x_3"]); sm = DF.group_by_subject(["A_x_1", "A_q_x_1", "B_x_1", "B_z_1", "C_x_1"])
+    assert np.array_equal(np.array(DF.build_synced_pairs(pm, sm)), g["pairs_small"])
+    for cname, dataset, sync, modality, pad_skel, pad_sens in H.FOG_LOADER_CASES:
+        reader, subs = H.synthetic_fog_reader(dataset, seed=5)
+        tr_s, ev_s = H.fog_loader_split(subs, dataset)
+        tr, ev = DF.create_fusion_loaders(dataset, reader, tr_s, ev_s, batch_size=7, synchronized=sync, seed=43, num_workers=0,
+                                          pad_skel=pad_skel, pad_sens=pad_sens, modality=modality)
+        for nm, ld in (("train", tr), ("eval", ev)):
+            ds = ld.dataset
+            assert list(g[f"{cname}/{nm}_pose_keys"]) == ds.pose_ds.keys, (cname, nm)
+            assert list(g[f"{cname}/{nm}_sens_keys"]) == ds.sens_ds.keys, (cname, nm)
+            assert int(g[f"{cname}/{nm}_len"]) == len(ds)
+            if sync:
+                assert [tuple(p) for p in g[f"{cname}/{nm}_pairs"]] == [tuple(p) for p in ds.pairs], (cname, nm)
+            prow, srow, ys, yt = ds.index_tables()
+            assert len(prow) == len(ds) and prow.max() < len(ds.pose_ds.store) and srow.max() < len(ds.sens_ds.store)
+            # labels of the items in dataset order == the labels the reference's un-shuffled eval loader delivered
+            if nm == "eval":
+                assert np.array_equal(ys, g[f"{cname}/eval_ep0/ys"]) and np.array_equal(yt, g[f"{cname}/eval_ep0/yt"]), cname
+        assert len(tr) == len(g[f"{cname}/train_ep0/bs"]) and len(ev) == len(g[f"{cname}/eval_ep0/bs"])
+    assert np.allclose(DF.compute_class_weights([10, 20, 30]).numpy(), (lambda w: w / w.sum() * 3)(1 / np.array([10, 20, 30.0])), rtol=1e-6)
+    a = np.arange(12.0).reshape(6, 2)
+    assert DF.pad_or_trim(a, 6) is a and DF.pad_or_trim(a, 4).shape == (4, 2) and np.array_equal(DF.pad_or_trim(a, 8)[6:], np.zeros((2, 2)))

@@ -211,6 +211,70 @@ def test_fog_fused_step_matches_reference(gk, name):
                 close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
 
 
+@pytest.mark.parametrize("name", ["fog_sync_gcl", "fog_sync_ce_nc"])
+def test_fog_sync_fused_step_matches_reference(gk, name):
+    """Synchronised FoG in the FUSED step: shared head, and -- for wm = gcl -- the symmetric-KL consistency term
+    (fbg_fog_train.py:81-89,121-124) inside gaitk_step_grads (logits pass, coupling kernel, one recompute + backward pass per
+    (task, stream)): losses, every gradient and the parameters after each step against the reference goldens."""
+    g = load_golden(name); meta = g["meta"]
+    m = fog_model(gk, g)
+    lam = meta["cons_lambda"] if meta["wm"] == "gcl" else 0.0
+    step = gk.FusedTrainStep(m, fog_criteria(gk, meta), cagrad_c=meta["alpha"], private_mult=1.0, consistency_lambda=lam)
+    for st in range(meta["steps"]):
+        i = st % 2
+        xs = [dev(g[f"sk{i}"]), dev(g[f"se{i}"])]; ys = [dev(g[f"ys{i}"]), dev(g[f"yt{i}"])]
+        plan = m.set_window(xs[0].shape[1]).plan()
+        gout = torch.zeros(plan.NP, device="cuda")
+        loss, correct = step.step(xs, ys, grads_out=gout)
+        ref = sub(g, f"s{st}")
+        close(loss.cpu().numpy(), ref["losses"], 2e-5, "losses")
+        assert correct.cpu().numpy().round().astype(int).tolist() == ref["correct"][:2].tolist()
+        got = grads_by_name(plan, gout)
+        for k, v in ref.items():
+            if k.startswith("grad:") and k[5:] in got:
+                nm = k[5:]
+                shared = next(p.group for p in plan.params if p.name == nm) == 0
+                close(got[nm], v, 2e-4 if shared else 5e-5, f"step {st} grad {nm}")
+        sd = m.state_dict()
+        for k, v in ref.items():
+            if k.startswith("param:"):
+                close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
+
+
+def test_fog_sync_consistency_graph_replay_and_shards(gk):
+    """The coupled step at a batch with ragged tiles: CUDA-graph replay equals the eager launch sequence bit for bit, and
+    two half-batch shards with GLOBAL denominators / batch size add up to the whole batch (what the data-parallel
+    all-reduce relies on)."""
+    torch.manual_seed(5)
+    B = 301
+    def make():
+        torch.manual_seed(11)
+        return gk.MultiModalMultiTaskModel(21, 6, 6, 6, 426, 16, 8, 128, 3, synchronized_loading=True).cuda()
+    crit = lambda: [gk.GCLLoss(cls_num_list=c, m=0.2, s=25.0, noise_mul=0.0) for c in ([50, 30, 20], [45, 33, 22])]
+    sk = torch.rand(B, 101, 21, device="cuda"); se = torch.randn(B, 426, 6, device="cuda")
+    y = torch.randint(0, 3, (B,), device="cuda")
+    m0 = make(); s0 = gk.FusedTrainStep(m0, crit(), cagrad_c=0.1, private_mult=1.0, consistency_lambda=1.0)
+    plan = m0.set_window(101).plan()
+    g_all = torch.zeros(plan.NP, device="cuda")
+    loss_all, _ = s0.step([sk, se], [y, y], grads_out=g_all, update=False)
+    loss_all = loss_all.clone()
+    # graph replay
+    m1 = make(); s1 = gk.FusedTrainStep(m1, crit(), cagrad_c=0.1, private_mult=1.0, consistency_lambda=1.0, use_graph=True)
+    m2 = make(); s2 = gk.FusedTrainStep(m2, crit(), cagrad_c=0.1, private_mult=1.0, consistency_lambda=1.0, use_graph=False)
+    for _ in range(3):
+        s1.step([sk, se], [y, y]); s2.step([sk, se], [y, y])
+    assert torch.equal(m1.flat_params(), m2.flat_params())
+    # shards: raw gbuf of the two halves adds up to the whole batch's gbuf
+    h = 150
+    def gbuf_of(lo, hi):
+        m = make(); s = gk.FusedTrainStep(m, crit(), cagrad_c=0.1, private_mult=1.0, consistency_lambda=1.0)
+        s._step_impl([sk[lo:hi].contiguous(), se[lo:hi].contiguous()], [y[lo:hi].contiguous()] * 2, ys_global=[y, y], part="grads")
+        return s._gbuf.clone()
+    whole = gbuf_of(0, B); parts = gbuf_of(0, h) + gbuf_of(h, B)
+    err = float((whole - parts).abs().max() / whole.abs().max())
+    assert err < 2e-6, err
+
+
 @pytest.mark.parametrize("name", ["fog_sync_gcl", "fog_sync_ce_nc", "fog_async_gcl"])
 def test_fog_autograd_path_matches_reference(gk, name):
     """Sync FoG adds the symmetric-KL consistency term (fbg_fog_train.py:81-89,121-124), which couples the two
@@ -1026,3 +1090,53 @@ def test_bf16x3_resident_gather_and_masks(gk):
         res[dt] = (loss.cpu().numpy(), gout.cpu().numpy())
     assert relerr(res[gk.DTYPE_BF16X3][0], res[gk.DTYPE_F32][0]) < 1e-4
     assert relerr(res[gk.DTYPE_BF16X3][1], res[gk.DTYPE_F32][1]) < 1e-3
+
+
+def test_fog_device_loaders_yield_reference_batches(gk):
+    """A5 / f2: create_fusion_loaders on the device (ClipStore prepared by gaitk_fog_prepare_pose / _sensor, batches gathered by
+    gaitk_window_gather) delivers, over two epochs of both loaders, exactly the samples the reference's DataLoaders delivered:
+    labels and an order-sensitive fp64 checksum of every sample (data bit exact => checksums equal to rounding of the dot)."""
+    import ref_harness as H
+    DF = gk.dataloader_fbg_fog
+    g = load_golden("fog_loaders")
+    for cname, dataset, sync, modality, pad_skel, pad_sens in H.FOG_LOADER_CASES:
+        reader, subs = H.synthetic_fog_reader(dataset, seed=5)
+        tr_s, ev_s = H.fog_loader_split(subs, dataset)
+        tr, ev = DF.create_fusion_loaders(dataset, reader, tr_s, ev_s, batch_size=7, synchronized=sync, seed=43, num_workers=0,
+                                          pad_skel=pad_skel, pad_sens=pad_sens, modality=modality)
+        got = H.loader_trace(tr, ev)
+        for k, v in got.items():
+            ref = g[f"{cname}/{k}"]
+            assert v.shape == ref.shape, (cname, k)
+            if k.endswith(("/cs", "/ct")):
+                assert np.allclose(v, ref, rtol=0, atol=1e-9 * max(1.0, float(np.abs(ref).max()))), (cname, k, np.abs(v - ref).max())
+            else:
+                assert np.array_equal(v, ref), (cname, k)
+        b = next(iter(ev))
+        assert b["skeleton"].is_cuda and b["skeleton"].shape[1:] == (pad_skel, 7 if dataset == "fog" else 17, 3)
+        assert b["sensor"].shape[1:] == (pad_sens, 6 if dataset == "fog" else 3) and b["label_sensor"].dtype == torch.int64
+
+
+def test_fog_resident_clip_training_equals_dense_batch_training(gk):
+    """index_batches(): the fused step reads the clips in place from the resident stores (win_start path) and lands on the
+    same parameters as training on the dense batches the loader materialises."""
+    import ref_harness as H
+    DF = gk.dataloader_fbg_fog
+    reader, subs = H.synthetic_fog_reader("fog", seed=5)
+    tr_s, ev_s = H.fog_loader_split(subs, "fog")
+    def run(resident):
+        torch.manual_seed(3)
+        m = gk.MultiModalMultiTaskModel(21, 6, 6, 6, 426, 16, 8, 128, 3, synchronized_loading=False).cuda()
+        crit = [gk.GCLLoss(cls_num_list=c, m=0.2, s=25.0, noise_mul=0.0) for c in ([30, 20, 10], [25, 22, 12])]
+        step = gk.FusedTrainStep(m, crit, cagrad_c=0.1, private_mult=1.0)
+        tr, _ = DF.create_fusion_loaders("fog", reader, tr_s, ev_s, batch_size=16, synchronized=False, seed=43, num_workers=0,
+                                         pad_skel=101, pad_sens=426)
+        if resident:
+            for ib in tr.index_batches():
+                step.step(ib.frames, ib.ys, win_start=ib.win_start)
+        else:
+            for b in tr:
+                step.step([b["skeleton"].flatten(2), b["sensor"]], [b["label_skeleton"], b["label_sensor"]])
+        return m.flat_params().clone()
+    a = run(False); b = run(True)
+    assert torch.equal(a, b)

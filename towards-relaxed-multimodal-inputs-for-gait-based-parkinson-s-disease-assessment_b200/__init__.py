@@ -9,6 +9,7 @@ from .classification_losses import GCLLoss, LDAMLoss, CrossEntropyLoss, make_los
 from .multitask_weighting import CAGrad
 from .fused_step import FusedTrainStep
 from . import dataloader_weargait
+from . import dataloader_fbg_fog
 from . import evaluation
 from .evaluation import MASK_COMBOS, eval_all_masks, eval_with_mask, eval_one_epoch
 from . import dist

@@ -28,7 +28,7 @@ EXPORTS = [
     "gaitk_step_grads", "gaitk_gbuf_floats", "gaitk_loss_denominators", "gaitk_step_update", "gaitk_p2p_allreduce", "gaitk_cagrad", "gaitk_cagrad_solve_host",
     "gaitk_sgd", "gaitk_window_indices", "gaitk_stats_accumulate", "gaitk_stats_finalize",
     "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_mask_eval", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
-    "gaitk_umma_selftest", "gaitk_umma_selftest_bf16", "gaitk_umma_bench",
+    "gaitk_umma_selftest", "gaitk_umma_selftest_bf16", "gaitk_umma_bench", "gaitk_umma_bench_multi",
 ]
 
 
@@ -102,6 +102,7 @@ def lib():
     L.gaitk_fog_prepare_sensor.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]; L.gaitk_fog_prepare_sensor.restype = i32
     L.gaitk_umma_selftest.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp]; L.gaitk_umma_selftest.restype = i32
     L.gaitk_umma_bench.argtypes = [vp, i32, i32, i32, i32, vp, vp]; L.gaitk_umma_bench.restype = i32
+    L.gaitk_umma_bench_multi.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]; L.gaitk_umma_bench_multi.restype = i32
     L.gaitk_umma_selftest_bf16.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp]; L.gaitk_umma_selftest_bf16.restype = i32
     _lib = L
     return L

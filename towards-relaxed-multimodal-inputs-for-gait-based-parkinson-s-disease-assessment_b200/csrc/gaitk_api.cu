@@ -336,6 +336,7 @@ extern "C" int gaitk_param_info(const gaitk_plan* p, int index, char* name, size
     return 0;
 }
 
+constexpr int COUPLE_MAX_CTAS = 1024;          // CTAs (256 samples each) of the consistency-coupling kernel
 static int stream_grid(const gaitk_plan* pl, const StreamPlan& sp, int B, int dtype = GAITK_DTYPE_F32) {
     const int ntiles = (B + sp.W - 1) / sp.W;
     if (dtype == GAITK_DTYPE_BF16X3)                     // one persistent CTA per SM, `groups` tiles in flight in each
@@ -362,6 +363,8 @@ extern "C" size_t gaitk_workspace_bytes(const gaitk_plan* pl, int B) {
     if (!pl) return 0;
     size_t sum = 0;                                      // every stream keeps its own partial rows until the single reduce launch
     for (int s = 0; s < pl->n_streams; ++s) sum += (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64;
+    // consistency-coupled step (2 streams): logits[2] + dlogits[4] of (B, K) + the coupling kernel's per-CTA partials
+    if (pl->n_streams == 2) sum += (size_t)6 * ((size_t)std::max(B, 0) * KMAX + 64) + (size_t)COUPLE_MAX_CTAS * 8;
     return sum * sizeof(float) + 256;
 }
 
@@ -431,6 +434,149 @@ static int launch_reduce(const gaitk_plan* pl, int s, const float* partial, int 
     return 0;
 }
 
+struct LossArgs { float scale; float margin[KMAX]; float cls_w[KMAX]; int nan_degenerate; };
+
+// ------------------------------------------------------------------------------------------ consistency-coupled step
+// fbg_fog_train.py:81-89,121-124 (synchronised FoG, wm = gcl): l_s = criterion_s(logits_s, y_s) + 0.5 lambda (KL(q || p) + KL(p || q)),
+// p = softmax(logits_0), q = softmax(logits_1), both KL terms 'batchmean' over the GLOBAL batch and differentiated through BOTH
+// arguments.  With u = log p - log q:  d KLsym / d logits_0[j] = p_j (u_j - sum_k p_k u_k) + p_j - q_j  (and symmetrically for
+// logits_1), so every task's gradient reaches both streams.  One thread per sample writes, per stream s,
+//   dl[2 s]     = d criterion_s / d logits_s + 0.5 lambda d KLsym / d logits_s     (task s through its own stream)
+//   dl[2 s + 1] =                               0.5 lambda d KLsym / d logits_s     (the OTHER task through stream s)
+// and the per-CTA partial sums of (loss_0, loss_1, correct_0, correct_1); the last CTA adds them in CTA order (deterministic).
+struct CoupleArgs {
+    const float* logits[2]; const long long* y[2]; const float* logit_off[2]; LossArgs L[2];
+    const float* denom; float lambda; int B, K;
+    float* dl[4]; float* partial; unsigned* ticket; float* stats;     // stats = gbuf tail: loss[4] | correct[4]
+};
+__global__ void __launch_bounds__(256) couple_kernel(const CoupleArgs A) {
+    __shared__ float sh[4][8];
+    __shared__ int last;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, K = A.K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b < A.B) {
+        float lp[2][KMAX], pr[2][KMAX];
+        const float inv_B = 1.0f / A.denom[GAITK_DENOM_COUNT];
+        for (int s = 0; s < 2; ++s) {
+            const float* lg = A.logits[s] + (size_t)b * K;
+            float mx = -INFINITY;
+            for (int k = 0; k < K; ++k) mx = fmaxf(mx, lg[k]);
+            float se = 0.f;
+            for (int k = 0; k < K; ++k) se += expf(lg[k] - mx);
+            const float lse = mx + logf(se);
+            for (int k = 0; k < K; ++k) { lp[s][k] = lg[k] - lse; pr[s][k] = expf(lp[s][k]); }
+        }
+        float kl = 0.f, su0 = 0.f, su1 = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float u = lp[0][k] - lp[1][k];
+            kl += (pr[0][k] - pr[1][k]) * u; su0 += pr[0][k] * u; su1 += pr[1][k] * u;
+        }
+        const float hl = 0.5f * A.lambda * inv_B;
+        for (int s = 0; s < 2; ++s) {
+            const LossArgs& L = A.L[s];
+            const float* lg = A.logits[s] + (size_t)b * K;
+            const int yy = (int)A.y[s][b];
+            const float inv_denom = 1.0f / A.denom[s];
+            float zz[KMAX]; float mx = -INFINITY, best = -INFINITY; int am = 0;
+            for (int k = 0; k < K; ++k) {
+                float z = lg[k];
+                if (z > best) { best = z; am = k; }
+                if (A.logit_off[s]) z -= A.logit_off[s][(size_t)b * K + k];
+                if (k == yy) z -= L.margin[k];
+                z *= L.scale;
+                if (L.nan_degenerate) z = __int_as_float(0x7fc00000);
+                zz[k] = z; mx = fmaxf(mx, z);
+            }
+            float se = 0.f;
+            for (int k = 0; k < K; ++k) se += expf(zz[k] - mx);
+            const float lse = mx + logf(se);
+            const float wy = L.cls_w[yy];
+            acc[s] = wy * (lse - zz[yy]) * inv_denom + hl * kl;
+            acc[2 + s] = (am == yy) ? 1.f : 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float u = lp[0][k] - lp[1][k];
+                const float dk = s == 0 ? pr[0][k] * (u - su0) + pr[0][k] - pr[1][k] : pr[1][k] * (su1 - u) + pr[1][k] - pr[0][k];
+                const float dce = L.scale * wy * inv_denom * (expf(zz[k] - lse) - (k == yy ? 1.f : 0.f));
+                A.dl[2 * s][(size_t)b * K + k] = dce + hl * dk;
+                A.dl[2 * s + 1][(size_t)b * K + k] = hl * dk;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int i = 0; i < 4; ++i) {
+        float v = acc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[i][wrp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += sh[threadIdx.x][w];
+        A.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < 4) {
+        __threadfence();
+        float v = 0.f;
+        for (unsigned c = 0; c < gridDim.x; ++c) v += reinterpret_cast<volatile const float*>(A.partial)[(size_t)c * 4 + threadIdx.x];
+        const int i = threadIdx.x;
+        A.stats[(i >> 1) * 4 + (i & 1)] += v;          // loss[s] / correct[s]
+        if (i == 0) *A.ticket = 0u;
+    }
+}
+
+static int step_grads_coupled(gaitk_plan* pl, const float* params, const float* const* x, const int64_t* const* win_start,
+                              const int64_t* const* y, int B, const gaitk_loss_desc* loss, const float* const* logit_off,
+                              const float* denom, uint32_t enabled_mask, float private_mult, float lambda,
+                              float* const* logits, float* gbuf, float* part, int dtype, cudaStream_t st) {
+    const int K = pl->d.num_classes;
+    if (pl->n_streams != 2) return fail(GAITK_E_BADARG, "the consistency term couples exactly two streams");
+    if ((B + 255) / 256 > COUPLE_MAX_CTAS) return fail(GAITK_E_SHAPE, "coupled step: at most %d samples per call", COUPLE_MAX_CTAS * 256);
+    float* my_part[2];
+    for (int s = 0; s < 2; ++s) { my_part[s] = part; part += (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64; }
+    const size_t per = ((size_t)B * KMAX + 63) / 64 * 64;
+    float* lg[2]; float* dl[4];
+    for (int s = 0; s < 2; ++s) { lg[s] = (logits && logits[s]) ? logits[s] : part; part += per; }
+    for (int i = 0; i < 4; ++i) { dl[i] = part; part += per; }
+    float* cpart = part; part += (size_t)COUPLE_MAX_CTAS * 4;
+    unsigned* ticket = reinterpret_cast<unsigned*>(part);
+    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    // pass 1: logits of both streams
+    for (int s = 0; s < 2; ++s) {
+        StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_FWD, !(enabled_mask & (1u << s)), a);
+        a.logits = lg[s];
+        int rc = launch_stream(pl, s, a, stream_grid(pl, pl->st[s], B, dtype), st, dtype);
+        if (rc) return rc;
+    }
+    // pass 2: losses + the four logit-gradient vectors
+    CoupleArgs C; memset(&C, 0, sizeof(C));
+    for (int s = 0; s < 2; ++s) {
+        C.logits[s] = lg[s]; C.y[s] = (const long long*)y[s]; C.logit_off[s] = logit_off ? logit_off[s] : nullptr;
+        C.L[s].scale = loss[s].scale; C.L[s].nan_degenerate = loss[s].nan_if_degenerate;
+        for (int k = 0; k < KMAX; ++k) { C.L[s].margin[k] = k < K ? loss[s].margin[k] : 0.f; C.L[s].cls_w[k] = k < K ? loss[s].cls_weight[k] : 0.f; }
+    }
+    for (int i = 0; i < 4; ++i) C.dl[i] = dl[i];
+    C.denom = denom; C.lambda = lambda; C.B = B; C.K = K; C.partial = cpart; C.ticket = ticket;
+    C.stats = gbuf + (size_t)MAXT * pl->P + pl->NP;
+    couple_kernel<<<(B + 255) / 256, 256, 0, st>>>(C);
+    LAUNCH_CHECK();
+    // pass 3: task t through stream s (recompute + backward with external logit gradients); shared parts -> column t of G,
+    // private parts add up over the tasks (fbg_fog_train.py:146-152: every loss reaches both encoders)
+    for (int t = 0; t < 2; ++t)
+        for (int s = 0; s < 2; ++s) {
+            StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_BWD_EXT, !(enabled_mask & (1u << s)), a);
+            a.dlogits_ext = dl[2 * s + (t == s ? 0 : 1)]; a.partial = my_part[s];
+            const int grid = stream_grid(pl, pl->st[s], B, dtype);
+            int rc = launch_stream(pl, s, a, grid, st, dtype);
+            if (rc) return rc;
+            if ((rc = launch_reduce(pl, s, my_part[s], grid, gbuf, t, private_mult, -1, st))) return rc;
+        }
+    return 0;
+}
+
 __global__ void zero_floats_kernel(float* p, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.f;
 }
@@ -441,8 +587,6 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
                                 size_t workspace_bytes, int dtype, void* stream) {
     if (!pl || !params || !x || !y || !loss || !denom || !gbuf || !workspace) return fail(GAITK_E_BADARG, "null argument");
     { int rc_ = check_dtype(pl, dtype); if (rc_) return rc_; }
-    if (consistency_lambda != 0.f)
-        return fail(GAITK_E_BADARG, "consistency term couples the streams: use gaitk_forward + gaitk_backward per task");
     if (workspace_bytes < gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     // a kernel, not cudaMemsetAsync: gbuf may live in a peer-mapped symmetric allocation (gaitk_p2p_allreduce), where a
@@ -450,6 +594,11 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
     zero_floats_kernel<<<8, 256, 0, st>>>(gbuf, (int)gaitk_gbuf_floats(pl));
     LAUNCH_CHECK();
     if (B <= 0) return 0;
+    if (consistency_lambda != 0.f) {
+        if ((task_mask & 3u) != 3u) return fail(GAITK_E_BADARG, "the consistency term needs both tasks");
+        return step_grads_coupled(pl, params, x, win_start, y, B, loss, logit_off, denom, enabled_mask, private_mult,
+                                  consistency_lambda, logits, gbuf, (float*)workspace, dtype, st);
+    }
     ReduceArgsMulti M; memset(&M, 0, sizeof(M));
     int n_active = 0, max_ng = 0;
     float* part = (float*)workspace;
@@ -614,7 +763,6 @@ extern "C" int gaitk_sgd(gaitk_plan* pl, float* params, const float* grads, floa
 }
 
 // ------------------------------------------------------------------------------------------ losses
-struct LossArgs { float scale; float margin[KMAX]; float cls_w[KMAX]; int nan_degenerate; };
 
 // one CTA; deterministic tree reduction
 __global__ void __launch_bounds__(256) loss_kernel(const float* logits, const long long* y, int B, int K, LossArgs L,
@@ -716,6 +864,7 @@ __global__ void __launch_bounds__(256) denom_kernel(DenomArgs D, float* denom) {
             double acc = 0;
             for (int k = 0; k < KMAX; ++k) acc += (double)h[k] * (double)D.cls_w[t][k];
             denom[t] = (float)acc;
+            denom[GAITK_DENOM_COUNT + t] = (float)(h[0] + h[1] + h[2] + h[3]);   // labels in the GLOBAL batch (KL batchmean)
         }
     }
 }
@@ -728,7 +877,7 @@ extern "C" int gaitk_loss_denominators(const int64_t* const* y, const int* count
         for (int t = 0; t < s; ++t) if (y[t] == y[s] && counts[t] == counts[s]) { D.same_as[s] = D.same_as[t]; break; }
         for (int k = 0; k < KMAX; ++k) D.cls_w[s][k] = loss[s].cls_weight[k];
     }
-    static_assert(4 + GAITK_MAX_STREAMS * KMAX + GAITK_MAX_STREAMS <= GAITK_DENOM_FLOATS, "denominator scratch");
+    static_assert(4 + GAITK_MAX_STREAMS * KMAX + GAITK_MAX_STREAMS <= GAITK_DENOM_COUNT && GAITK_DENOM_COUNT + GAITK_MAX_STREAMS <= GAITK_DENOM_FLOATS, "denominator scratch");
     CUDA_TRY(cudaMemsetAsync(denom + 4, 0, (GAITK_DENOM_FLOATS - 4) * sizeof(float), (cudaStream_t)stream));
     denom_kernel<<<dim3(DENOM_CTAS, n_streams), 256, 0, (cudaStream_t)stream>>>(D, denom);
     LAUNCH_CHECK();
@@ -993,6 +1142,15 @@ extern "C" int gaitk_umma_bench(const uint32_t* ops, int nops, int reps, int nco
     if (!ops || !cycles || nops < 1 || reps < 1 || smem_bytes < 1024 || smem_bytes > 200 * 1024) return fail(GAITK_E_BADARG, "bad argument");
     CUDA_TRY(cudaFuncSetAttribute((const void*)umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     umma_bench_kernel<<<1, 128, smem_bytes, (cudaStream_t)stream>>>((const UmmaOp*)ops, nops, reps, ncols, smem_bytes, (long long*)cycles);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gaitk_umma_bench_multi(const uint32_t* ops, int nops, int reps, int ncols, int smem_bytes, int n_issuers, int64_t* cycles, void* stream) {
+    if (!ops || !cycles || nops < 1 || reps < 1 || smem_bytes < 1024 || smem_bytes > 200 * 1024 || n_issuers < 1 || n_issuers > 4)
+        return fail(GAITK_E_BADARG, "bad argument");
+    CUDA_TRY(cudaFuncSetAttribute((const void*)umma_bench_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    umma_bench_multi_kernel<<<1, 128, smem_bytes, (cudaStream_t)stream>>>((const UmmaOp*)ops, nops, reps, ncols, smem_bytes, n_issuers, (long long*)cycles);
     LAUNCH_CHECK();
     return 0;
 }

@@ -132,4 +132,44 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(const UmmaOp* ops, int 
     if (tid < 32) umma::tmem_dealloc(tbase, (uint32_t)ncols);
 }
 
+// The same with `nissue` warps issuing concurrently (warp w -> its own mbarrier, D columns shifted by 64 w): does the ~45-clock
+// cost of a small tcgen05.mma belong to the issuing THREAD (then n issuers give n times the rate) or to the tensor pipe
+// (then the rate stays)?  cycles[2 w] = issuer w's clocks first issue -> completion, cycles[2 w + 1] = clocks spent issuing.
+__global__ void __launch_bounds__(128) umma_bench_multi_kernel(const UmmaOp* ops, int nops, int reps, int ncols, int smem_bytes, int nissue, long long* cycles) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < smem_bytes / 4; i += 128) sm[i] = 0.f;
+    if (tid == 0) { for (int i = 0; i < 4; ++i) umma::mbar_init(&bar[i], 1); umma::fence_mbar_init(); }
+    if (tid < 32) umma::tmem_alloc(&tmem_slot, (uint32_t)ncols);
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    if ((tid & 31) == 0 && warp < nissue) {
+        const uint32_t a0 = umma::smem_u32(sm);
+        uint64_t da[4], db[4]; uint32_t dd[4], id[4];
+        for (int i = 0; i < 4; ++i) {
+            const UmmaOp o = ops[i % nops];
+            da[i] = umma::make_desc(a0 + o.a_off, o.a_lbo, o.a_sbo); db[i] = umma::make_desc(a0 + o.b_off, o.b_lbo, o.b_sbo);
+            dd[i] = tbase + ((o.accumulate >> 8) & 0xffu) * 8u + 64u * warp; id[i] = o.idesc;
+        }
+        const long long t0 = clock64();
+        for (int r = 0; r < reps * nops; r += 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) umma::mma_bf16(dd[i], da[i], db[i], id[i], 1u);
+        }
+        const long long t1 = clock64();
+        umma::commit(&bar[warp]);
+        umma::mbar_wait(&bar[warp], 0);
+        const long long t2 = clock64();
+        cycles[2 * warp] = t2 - t0; cycles[2 * warp + 1] = t1 - t0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tbase, (uint32_t)ncols);
+}
+
 }  // namespace gaitk

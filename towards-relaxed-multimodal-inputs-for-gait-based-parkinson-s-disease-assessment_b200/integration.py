@@ -15,7 +15,7 @@ from pathlib import Path
 def install_shadow(reference_root, *, data_path: bool = True):
     """reference_root: directory that holds ``train/`` and ``data/WearGait/`` of the reference.  Returns the imported
     (unmodified) ``weargait_train`` module.  data_path=False keeps the reference's own host DataLoaders."""
-    from . import classification_losses, dataloader_weargait, feature_encoder, multitask_weighting, weargait_encoders
+    from . import classification_losses, dataloader_fbg_fog, dataloader_weargait, feature_encoder, multitask_weighting, weargait_encoders
     root = Path(reference_root)
     for p in (root, root / "data" / "WearGait", root / "train"):
         if str(p) not in sys.path:
@@ -42,6 +42,8 @@ def install_shadow(reference_root, *, data_path: bool = True):
         import data_processing                                           # the reference package (for its other members)
         sys.modules["data_processing.dataloader_weargait"] = dataloader_weargait
         data_processing.dataloader_weargait = dataloader_weargait
+        sys.modules["data_processing.dataloader_fbg_fog"] = dataloader_fbg_fog
+        data_processing.dataloader_fbg_fog = dataloader_fbg_fog
     for mod in ("weargait_train", "fbg_fog_train", "utilities"):            # (re)import the trainers against the shadowed names
         sys.modules.pop(mod, None)
     return importlib.import_module("weargait_train")
