@@ -1132,6 +1132,7 @@ def test_fog_resident_clip_training_equals_dense_batch_training(gk):
         tr, _ = DF.create_fusion_loaders("fog", reader, tr_s, ev_s, batch_size=16, synchronized=False, seed=43, num_workers=0,
                                          pad_skel=101, pad_sens=426)
         if resident:
+            m.set_window(101)                                      # pose length of the resident clips (no dense batch shows it)
             for ib in tr.index_batches():
                 step.step(ib.frames, ib.ys, win_start=ib.win_start)
         else:
