@@ -38,6 +38,7 @@ extern "C" {
 /* model families */
 #define GAITK_FAMILY_WEARGAIT 0   /* data/WearGait/weargait_encoders.py:116-189 WearGaitThreeModal */
 #define GAITK_FAMILY_FOG      1   /* train/feature_encoder.py:149-265 MultiModalMultiTaskModel   */
+#define GAITK_FAMILY_STAGE    2   /* one stage of a fusion baseline (gaitk_stage_create)          */
 
 #define GAITK_MAX_STREAMS 3
 #define GAITK_DENOM_COUNT  24   /* denom[GAITK_DENOM_COUNT + s] = number of labels in stream s's GLOBAL label vector (KL batchmean) */
@@ -252,6 +253,52 @@ int gaitk_fog_prepare_pose(const double* poses, const int64_t* clip_start, const
                            int n_clips, int J, int T_out, float* out, void* stream);
 int gaitk_fog_prepare_sensor(const double* sens, const int64_t* clip_start, const int64_t* clip_len,
                              int n_clips, int D, int T_out, float* out, void* stream);
+
+/* ---- fusion baselines as stages (EarlyFusion3 / CheapXAttn3 weargait_encoders.py:209-245,338-387; EarlyFusionModel /
+ * LateFusionModel / ShareLatentModel / CheapXAttnModel feature_encoder.py:346-596; trained by baselines/fusion_train.py:188-202
+ * and weargait_train.py --baseline).  These models couple the streams between encoder and backbone, so they run as
+ *   encoder stage(s) -> fusion op (concat, or gaitk_xattn_*) -> trunk stage (backbone conv + ReLU + adaptive pool + flatten)
+ *   -> gaitk_linear_* head -> gaitk_loss,
+ * each stage one launch of the fused stream kernel with the intermediate tensor in HBM. */
+#define GAITK_STAGE_CONV_GELU_LN   0   /* WalkwayEncoder / IMUEncoderShallow (weargait_encoders.py:40-69): params w1 b1 lng lnb       */
+#define GAITK_STAGE_INSOLE         1   /* InsoleEncoderDeep (:71-101): w1 b1 w2 b2 lng lnb wsk bsk                                   */
+#define GAITK_STAGE_LINEAR_LN_RELU 2   /* SkeletonMLP (feature_encoder.py:61-77): w1 b1 lng lnb                                      */
+#define GAITK_STAGE_CONV_POOL      3   /* SensorEncoder (:27-58): w1 b1                                                              */
+#define GAITK_STAGE_TRUNK          4   /* SharedBackbone (+ .flatten(1)) on a (B, T, CIN) tensor: wbb bbb                            */
+typedef struct gaitk_stage_desc {
+    int32_t enc;          /* GAITK_STAGE_*                                                         */
+    int32_t CIN;          /* input channels of the stage                                           */
+    int32_t H;            /* insole hidden width (2 C), else 0                                     */
+    int32_t C;            /* encoder output channels (ignored by the trunk)                        */
+    int32_t T_in, T;      /* input / output length (T_in != T only for the pooled sensor encoder)  */
+    int32_t pool_sensor;  /* SensorEncoder: adaptive pool T_in -> T                                */
+    int32_t S, bdim;      /* trunk: backbone channels and pooling bins (encoders: any valid pair)  */
+    int32_t reserved[7];
+} gaitk_stage_desc;
+/* A stage is a one-stream plan (gaitk_plan_destroy / gaitk_param_info / gaitk_param_total / gaitk_workspace_bytes apply);
+ * its parameters live in ONE flat buffer in the order listed above. */
+int gaitk_stage_create(const gaitk_stage_desc* desc, int device, gaitk_plan** out);
+/* out: encoder stage (B, T, C); trunk stage (B, bdim * S) = backbone(x).flatten(1) */
+int gaitk_stage_forward(gaitk_plan* stage, const float* params, const float* x, const int64_t* win_start, int B, int zero_input,
+                        float* out, void* stream);
+/* dout: gradient of the stage output; grads: flat stage layout, gaitk_param_total + 8 floats, accumulated (+=);
+ * dx (trunk only, optional): gradient of the trunk input (B, T, CIN).  The forward pass is recomputed inside. */
+int gaitk_stage_backward(gaitk_plan* stage, const float* params, const float* x, const int64_t* win_start, int B, int zero_input,
+                         const float* dout, float* dx, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+/* CheapCrossAttention (weargait_encoders.py:324-336): out = softmax(A B^T / sqrt(d)) B per window; A, B, out (n, T, d) fp32,
+ * T <= 128, d in {3, 6, 8, 12, 16}.  Backward recomputes the scores; deterministic (no atomics). */
+int gaitk_xattn_forward(const float* A, const float* B, float* out, int n_windows, int T, int d, void* stream);
+int gaitk_xattn_backward(const float* A, const float* B, const float* dout, float* dA, float* dB, int n_windows, int T, int d, void* stream);
+/* nn.Linear on rows: y (R, O) = x (R, I) W^T (O, I) + bias (heads: I = 128 / 256; projections: I = C).  I <= 256, O <= 32.
+ * Backward: dx (optional), dW, db (optional) overwritten; deterministic two-stage batch reduction. */
+int gaitk_linear_forward(const float* x, const float* W, const float* bias, float* y, int R, int I, int O, void* stream);
+size_t gaitk_linear_workspace_bytes(int R, int I, int O);
+int gaitk_linear_backward(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db, int R, int I, int O,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* torch.optim.Adam.step over a table of tensors (baselines/fusion_train.py:202): HOST arrays of n_tensors device pointers /
+ * element counts; `step` = 1 for the first update. */
+int gaitk_adam(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
+               int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
 /* Hardware self-test of the tcgen05 (5th-gen tensor core) layer: runs nops tf32 MMAs (each op = 8 uint32:
  * a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo (bytes), accumulate, idesc) over shared-memory images of A and B

@@ -719,7 +719,8 @@ def test_single_modality_paths_match_reference(gk):
 
 # ---------------------------------------------------------------------------------------------------------------
 # fusion baselines (weargait_train.py --baseline late_fusion | shared_latent): plain mean of the three CE losses
-BL_CASES = ["bl_late_sync", "bl_late_async", "bl_shared_latent_sync", "bl_shared_latent_async"]
+BL_CASES = ["bl_late_sync", "bl_late_async", "bl_shared_latent_sync", "bl_shared_latent_async",
+            "bl_early_sync", "bl_early_async", "bl_xattn_sync", "bl_xattn_async"]       # the last four: staged execution (staged.py)
 
 
 def bl_model(gk, g):
@@ -727,6 +728,10 @@ def bl_model(gk, g):
     kw = dict(enc_out_ch=12, backbone_dim=8, shared_out_ch=16, num_classes=2, synchronized=meta["synchronized"])
     if meta["baseline"] == "shared_latent":
         m = gk.SharedLatent3(proj_ch=16, **kw)
+    elif meta["baseline"] == "early_fusion":
+        m = gk.EarlyFusion3(**kw)
+    elif meta["baseline"] == "cheap_xattn":
+        m = gk.CheapXAttn3(**kw)
     else:
         m = gk.LateFusion3(**kw)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}, strict=True)
@@ -755,7 +760,8 @@ def test_fusion_baseline_autograd_training_matches_reference(gk, name):
             if k.startswith("grad:"):
                 close(named[k[5:]].grad.cpu().numpy(), v, 5e-5, f"step {st} grad {k[5:]}"); n_checked += 1
         assert n_checked >= 14
-        assert named["enc_i.ln1.weight"].grad is None
+        g1 = named["enc_i.ln1.weight"].grad                  # constructed, never applied (weargait_encoders.py:81,93-101)
+        assert g1 is None or float(g1.abs().max()) == 0.0
         opt.step()
         sd = m.state_dict()
         for k, v in ref.items():
@@ -1141,3 +1147,88 @@ def test_fog_resident_clip_training_equals_dense_batch_training(gk):
         return m.flat_params().clone()
     a = run(False); b = run(True)
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-stream fusion baselines (feature_encoder.py:346-596, baselines/fusion_train.py) on the staged CUDA path
+FOGBL_CASES = [f"fogbl_{k}_{s}" for k in ("early", "late", "share_latent", "cheap_xattn") for s in ("sync", "async")]
+
+
+def fogbl_model(gk, g):
+    meta = g["meta"]
+    common = dict(skeleton_input_dim=21, skeleton_output_dim=6, sensor_in_channels=6, sensor_out_channels=6, sensor_length=426,
+                  shared_out_channels=16, backbone_dim=8, num_classes=3, synchronized_loading=meta["synchronized"])
+    cls = {"early": gk.EarlyFusionModel, "late": gk.LateFusionModel, "cheap_xattn": gk.CheapXAttnModel}.get(meta["kind"])
+    m = gk.ShareLatentModel(**common, taskhead_input_dim=128) if cls is None else cls(**common)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state0").items()}, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", FOGBL_CASES)
+def test_two_stream_fusion_baselines_match_reference(gk, name):
+    """EarlyFusionModel / LateFusionModel / ShareLatentModel / CheapXAttnModel: logits, loss and EVERY gradient of the staged CUDA
+    path (encoder stages, cross attention, trunk stage, linear heads) against what the reference produced (fusion_train.py:234-242)."""
+    g = load_golden(name); meta = g["meta"]
+    m = fogbl_model(gk, g)
+    out = m(dev(g["x_skel"]), dev(g["x_sens"]))
+    ce = gk.CrossEntropyLoss()
+    ys, yt = dev(g["ys"]), dev(g["yt"])
+    if meta["synchronized"] and meta["kind"] != "share_latent":
+        close(out.detach().cpu().numpy(), g["logits0"], 2e-5, "logits")
+        loss = ce(out, ys)
+    else:
+        close(out[0].detach().cpu().numpy(), g["logits0"], 2e-5, "logits0"); close(out[1].detach().cpu().numpy(), g["logits1"], 2e-5, "logits1")
+        loss = 0.5 * (ce(out[0], ys) + ce(out[1], yt))
+    assert abs(float(loss) - float(g["loss"])) < 2e-5 * max(1.0, abs(float(g["loss"])))
+    loss.backward()
+    n = 0
+    for k, p in m.named_parameters():
+        if f"grad:{k}" in g:
+            close(p.grad.cpu().numpy(), g[f"grad:{k}"], 5e-5, f"grad {k}"); n += 1
+    assert n == sum(1 for k in g.files if k.startswith("grad:")) and n >= 8
+
+
+def test_fused_adam_matches_torch_adam(gk):
+    """gaitk_adam (one launch over all parameter tensors) against torch.optim.Adam with the defaults of baselines/fusion_train.py:202,
+    five steps on a 2-stream fusion baseline."""
+    g = load_golden("fogbl_cheap_xattn_async")
+    ma, mb = fogbl_model(gk, g), fogbl_model(gk, g)
+    oa = gk.FusedAdam(ma.parameters(), lr=1e-3); ob = torch.optim.Adam(mb.parameters(), lr=1e-3)
+    ce = gk.CrossEntropyLoss()
+    xs, xt, ys, yt = dev(g["x_skel"]), dev(g["x_sens"]), dev(g["ys"]), dev(g["yt"])
+    for _ in range(5):
+        for m, o in ((ma, oa), (mb, ob)):
+            o.zero_grad()
+            a, b = m(xs, xt)
+            (0.5 * (ce(a, ys) + ce(b, yt))).backward()
+            o.step()
+    for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+        err = float((p - q).abs().max()); ref = float(q.abs().max())
+        assert err <= 2e-6 * max(ref, 1.0), (k, err)
+
+
+def test_xattn_and_linear_kernels_match_torch(gk):
+    """The fusion ops alone against torch fp32 references of the same ops (forward and every gradient), at the shapes of both
+    model families, ragged batch sizes included."""
+    from importlib import import_module
+    staged = gk.staged
+    torch.manual_seed(0)
+    for (n, T, d) in [(5, 64, 12), (3, 101, 6), (130, 64, 12)]:
+        A = torch.randn(n, T, d, device="cuda", requires_grad=True); B = torch.randn(n, T, d, device="cuda", requires_grad=True)
+        G = torch.randn(n, T, d, device="cuda")
+        out = staged.cheap_xattn(A, B); out.backward(G)
+        A2 = A.detach().clone().requires_grad_(); B2 = B.detach().clone().requires_grad_()
+        ref = torch.softmax((A2 @ B2.transpose(1, 2)) * d ** -0.5, dim=-1) @ B2; ref.backward(G)
+        close(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), 2e-5, "xattn out")
+        close(A.grad.cpu().numpy(), A2.grad.cpu().numpy(), 5e-5, "xattn dA"); close(B.grad.cpu().numpy(), B2.grad.cpu().numpy(), 5e-5, "xattn dB")
+    for (R, I, O, bias) in [(7, 128, 3, True), (600, 256, 2, True), (3 * 101, 6, 16, True), (1000, 128, 4, False)]:
+        x = torch.randn(R, I, device="cuda", requires_grad=True); W = torch.randn(O, I, device="cuda", requires_grad=True)
+        b = torch.randn(O, device="cuda", requires_grad=True) if bias else None
+        G = torch.randn(R, O, device="cuda")
+        y = staged.linear(x, W, b); y.backward(G)
+        x2 = x.detach().clone().requires_grad_(); W2 = W.detach().clone().requires_grad_(); b2 = b.detach().clone().requires_grad_() if bias else None
+        y2 = torch.nn.functional.linear(x2, W2, b2); y2.backward(G)
+        close(y.detach().cpu().numpy(), y2.detach().cpu().numpy(), 2e-5, "linear y")
+        close(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), 2e-5, "linear dx"); close(W.grad.cpu().numpy(), W2.grad.cpu().numpy(), 5e-5, "linear dW")
+        if bias:
+            close(b.grad.cpu().numpy(), b2.grad.cpu().numpy(), 5e-5, "linear db")

@@ -29,6 +29,8 @@ EXPORTS = [
     "gaitk_sgd", "gaitk_window_indices", "gaitk_stats_accumulate", "gaitk_stats_finalize",
     "gaitk_normalize_frames", "gaitk_window_gather", "gaitk_mask_eval", "gaitk_fog_prepare_pose", "gaitk_fog_prepare_sensor",
     "gaitk_umma_selftest", "gaitk_umma_selftest_bf16", "gaitk_umma_bench", "gaitk_umma_bench_multi",
+    "gaitk_stage_create", "gaitk_stage_forward", "gaitk_stage_backward", "gaitk_xattn_forward", "gaitk_xattn_backward",
+    "gaitk_linear_forward", "gaitk_linear_workspace_bytes", "gaitk_linear_backward", "gaitk_adam",
 ]
 
 
@@ -36,6 +38,13 @@ class ModelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "family", "T", "enc_out_ch", "shared_out_ch", "backbone_dim", "num_classes", "use_norm", "use_cosine",
         "synchronized", "skel_in_dim", "sensor_in_ch", "sensor_len", "sensor_out_len")] + [("reserved", C.c_int32 * 3)]
+
+
+class StageDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("enc", "CIN", "H", "C", "T_in", "T", "pool_sensor", "S", "bdim")] + [("reserved", C.c_int32 * 7)]
+
+
+STAGE_CONV_GELU_LN, STAGE_INSOLE, STAGE_LINEAR_LN_RELU, STAGE_CONV_POOL, STAGE_TRUNK = 0, 1, 2, 3, 4
 
 
 class LossDesc(C.Structure):
@@ -104,6 +113,15 @@ def lib():
     L.gaitk_umma_bench.argtypes = [vp, i32, i32, i32, i32, vp, vp]; L.gaitk_umma_bench.restype = i32
     L.gaitk_umma_bench_multi.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]; L.gaitk_umma_bench_multi.restype = i32
     L.gaitk_umma_selftest_bf16.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp]; L.gaitk_umma_selftest_bf16.restype = i32
+    L.gaitk_stage_create.argtypes = [C.POINTER(StageDesc), i32, pp]; L.gaitk_stage_create.restype = i32
+    L.gaitk_stage_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]; L.gaitk_stage_forward.restype = i32
+    L.gaitk_stage_backward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, sz, vp]; L.gaitk_stage_backward.restype = i32
+    L.gaitk_xattn_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp]; L.gaitk_xattn_forward.restype = i32
+    L.gaitk_xattn_backward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]; L.gaitk_xattn_backward.restype = i32
+    L.gaitk_linear_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]; L.gaitk_linear_forward.restype = i32
+    L.gaitk_linear_workspace_bytes.argtypes = [i32, i32, i32]; L.gaitk_linear_workspace_bytes.restype = sz
+    L.gaitk_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]; L.gaitk_linear_backward.restype = i32
+    L.gaitk_adam.argtypes = [pp, pp, pp, pp, C.POINTER(i64), i32, f32, f32, f32, f32, f32, i32, vp]; L.gaitk_adam.restype = i32
     _lib = L
     return L
 

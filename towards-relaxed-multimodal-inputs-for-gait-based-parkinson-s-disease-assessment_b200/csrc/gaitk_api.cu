@@ -26,6 +26,10 @@ static int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+extern "C" int gaitk_set_error(int code, const char* fmt, ...) {            // for the other translation units (fusion.cu)
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail((int)e_, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
 #define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail((int)e_, "kernel launch: %s", cudaGetErrorString(e_)); } while (0)
 
@@ -882,6 +886,91 @@ extern "C" int gaitk_loss_denominators(const int64_t* const* y, const int* count
     denom_kernel<<<dim3(DENOM_CTAS, n_streams), 256, 0, (cudaStream_t)stream>>>(D, denom);
     LAUNCH_CHECK();
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stages (fusion baselines)
+// EarlyFusion3 / CheapXAttn3 (weargait_encoders.py:209-245, 338-387) and the 2-stream twins (feature_encoder.py:346-596) couple
+// the streams BETWEEN encoder and backbone, so they run as stages with the intermediate tensors in HBM:
+//   encoder stage (one stream kernel, encoder only) -> fusion op (concat / gaitk_xattn_*) -> trunk stage (ENC_NONE stream
+//   kernel: backbone conv + ReLU + adaptive pooling) -> gaitk_linear_* head -> gaitk_loss.
+// A stage is a one-stream gaitk_plan whose parameters are all private: its flat layout (gaitk_param_info) is
+//   conv encoders  w1 b1 lng lnb | insole  w1 b1 w2 b2 lng lnb wsk bsk | linear-LN-ReLU  w1 b1 lng lnb | conv-pool  w1 b1 | trunk  wbb bbb
+extern "C" int gaitk_stage_create(const gaitk_stage_desc* sd, int device, gaitk_plan** out) {
+    if (!sd || !out) return fail(GAITK_E_BADARG, "null argument");
+    *out = nullptr;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(GAITK_E_ARCH, "device %d is sm_%d%d; libgaitk is built for sm_100a only (no fallback path)", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    if (sd->T < 1 || sd->C < 1 || sd->CIN < 1 || sd->S < 1 || sd->bdim < 1 || sd->bdim > sd->T) return fail(GAITK_E_SHAPE, "bad stage dims");
+    gaitk_plan* pl = new gaitk_plan();
+    memset(&pl->d, 0, sizeof(pl->d));
+    pl->d.family = GAITK_FAMILY_STAGE; pl->d.T = sd->T; pl->d.enc_out_ch = sd->enc == ENC_NONE ? sd->CIN : sd->C;
+    pl->d.shared_out_ch = sd->S; pl->d.backbone_dim = sd->bdim; pl->d.num_classes = 2;
+    pl->device = device; pl->sm_count = prop.multiProcessorCount; pl->NP = 0; pl->P = 0; pl->NF = sd->bdim * sd->S;
+    pl->n_streams = 1; pl->p_wbb = pl->p_bbb = -1;
+    for (int s = 0; s < GAITK_MAX_STREAMS; ++s) {
+        StreamPlan& sp = pl->st[s];
+        sp.p_w1 = sp.p_b1 = sp.p_w2 = sp.p_b2 = sp.p_wsk = sp.p_bsk = sp.p_lng = sp.p_lnb = sp.p_hng = sp.p_hnb = sp.p_hw = sp.p_hb = sp.p_wp = sp.p_bp = -1;
+    }
+    StreamPlan& e = pl->st[0];
+    const int C = sd->C, CIN = sd->CIN;
+    int KT1 = 1, H = 0;
+    switch (sd->enc) {
+        case ENC_CONV_GELU_LN:
+            KT1 = 3;
+            e.p_w1 = add_param(pl, "w1", 1, C, CIN, 3); e.p_b1 = add_param(pl, "b1", 1, C);
+            e.p_lng = add_param(pl, "lng", 1, C); e.p_lnb = add_param(pl, "lnb", 1, C);
+            break;
+        case ENC_INSOLE:
+            KT1 = 5; H = sd->H;
+            e.p_w1 = add_param(pl, "w1", 1, H, CIN, 5); e.p_b1 = add_param(pl, "b1", 1, H);
+            e.p_w2 = add_param(pl, "w2", 1, C, H, 3); e.p_b2 = add_param(pl, "b2", 1, C);
+            e.p_lng = add_param(pl, "lng", 1, C); e.p_lnb = add_param(pl, "lnb", 1, C);
+            e.p_wsk = add_param(pl, "wsk", 1, C, H, 1); e.p_bsk = add_param(pl, "bsk", 1, C);
+            break;
+        case ENC_LINEAR_LN_RELU:
+            e.p_w1 = add_param(pl, "w1", 1, C, CIN); e.p_b1 = add_param(pl, "b1", 1, C);
+            e.p_lng = add_param(pl, "lng", 1, C); e.p_lnb = add_param(pl, "lnb", 1, C);
+            break;
+        case ENC_CONV_POOL:
+            KT1 = 3;
+            e.p_w1 = add_param(pl, "w1", 1, C, CIN, 3); e.p_b1 = add_param(pl, "b1", 1, C);
+            break;
+        case ENC_NONE:
+            pl->p_wbb = add_param(pl, "wbb", 1, sd->S, CIN, 3); pl->p_bbb = add_param(pl, "bbb", 1, sd->S);
+            break;
+        default: delete pl; return fail(GAITK_E_BADARG, "unknown stage kind %d", sd->enc);
+    }
+    int rc = plan_stream(pl, 0, sd->enc, CIN, KT1, H, sd->T_in > 0 ? sd->T_in : sd->T, sd->T, sd->pool_sensor);
+    if (rc) { delete pl; return rc; }
+    layout_stream_grads(pl, 0);
+    *out = pl;
+    return 0;
+}
+// out: encoder stage (B, T, C); trunk stage (B, NF).  x: (B, T_in, CIN) dense, or a frame store with win_start.
+extern "C" int gaitk_stage_forward(gaitk_plan* pl, const float* params, const float* x, const int64_t* win_start, int B, int zero_input,
+                                   float* out, void* stream) {
+    if (!pl || !params || !x || !out || pl->d.family != GAITK_FAMILY_STAGE) return fail(GAITK_E_BADARG, "bad argument (stage plan expected)");
+    if (B <= 0) return 0;
+    StreamArgs a; fill_args(pl, 0, params, x, win_start, B, MODE_FWD, zero_input, a);
+    if (pl->st[0].enc == ENC_NONE) a.repr_out = out; else a.feat_out = out;
+    return launch_stream(pl, 0, a, stream_grid(pl, pl->st[0], B), (cudaStream_t)stream);
+}
+// dout: gradient of what gaitk_stage_forward returned.  grads: flat, stage layout, gaitk_param_total + 8 floats, accumulated (+=).
+// dx (trunk stage only, optional): gradient of the trunk input (B, T, CIN).
+extern "C" int gaitk_stage_backward(gaitk_plan* pl, const float* params, const float* x, const int64_t* win_start, int B, int zero_input,
+                                    const float* dout, float* dx, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!pl || !params || !x || !dout || !grads || !workspace || pl->d.family != GAITK_FAMILY_STAGE) return fail(GAITK_E_BADARG, "bad argument (stage plan expected)");
+    if (workspace_bytes < gaitk_workspace_bytes(pl, B)) return fail(GAITK_E_BADARG, "workspace too small");
+    if (B <= 0) return 0;
+    StreamArgs a; fill_args(pl, 0, params, x, win_start, B, MODE_BWD_EXT, zero_input, a);
+    if (pl->st[0].enc == ENC_NONE) { a.drepr_in = dout; a.dx = dx; } else a.dfeat_in = dout;
+    a.partial = (float*)workspace;
+    const int grid = stream_grid(pl, pl->st[0], B);
+    int rc = launch_stream(pl, 0, a, grid, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_reduce(pl, 0, (const float*)workspace, grid, grads, 0, 1.0f, -1, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------ data path

@@ -33,7 +33,8 @@ constexpr int WMAX = 4;        // windows per tile (one warp each in the head ph
 #define GAITK_RB_MOD 4
 #endif
 
-enum EncKind { ENC_CONV_GELU_LN = 0, ENC_INSOLE = 1, ENC_LINEAR_LN_RELU = 2, ENC_CONV_POOL = 3 };
+enum EncKind { ENC_CONV_GELU_LN = 0, ENC_INSOLE = 1, ENC_LINEAR_LN_RELU = 2, ENC_CONV_POOL = 3,
+               ENC_NONE = 4 };       // no encoder: x IS the backbone input (the trunk stage of the fusion baselines)
 enum Mode { MODE_FWD = 0, MODE_FUSED = 1, MODE_BWD_EXT = 2 };
 
 // stream-local gradient layout (offsets in floats into a partial-gradient row; -1 = absent)
@@ -62,7 +63,13 @@ struct StreamArgs {
     // outputs
     float* logits;                 // optional (B,K)
     float* partial;                // [gridDim.x][NGP]
-    float* dx;                     // optional input gradient (dense layout) -- MODE_BWD_EXT only
+    float* dx;                     // ENC_NONE, MODE_BWD_EXT: gradient of the backbone input (B, T, CIN), dense
+    // stage cuts (fusion baselines, weargait_encoders.py:209-387 / feature_encoder.py:346-596): a model is run as
+    // encoder stages -> fusion op -> trunk stage, with the intermediate tensors in global memory
+    float* feat_out;               // encoder stage, forward: encoder output (B, T, C); backbone / head are skipped
+    const float* dfeat_in;         // encoder stage, backward: gradient of the encoder output (B, T, C) (replaces the backbone dgrad)
+    float* repr_out;               // trunk stage, forward: pooled + flattened backbone features (B, NF); the head is skipped
+    const float* drepr_in;         // trunk stage, backward: their gradient (B, NF) (replaces head + loss)
     GradOff go; int NGP;
 };
 
@@ -219,6 +226,21 @@ struct HeadState {
                 float acc = 0.f;
                 for (int t = t0; t < t1; ++t) acc += c.Zs[((s >> 2) * c.RB + c.halo + t * c.W + w_) * 4 + (s & 3)];
                 f[i] = acc / (float)(t1 - t0);
+            }
+            if (A.repr_out || A.drepr_in) {           // trunk stage: features out / feature gradients in, no head
+                if (A.repr_out && wi < A.B) {
+#pragma unroll
+                    for (int i = 0; i < NFL; ++i) A.repr_out[(size_t)wi * NF + lane + 32 * i] = f[i];
+                }
+                if (A.drepr_in) {
+#pragma unroll
+                    for (int i = 0; i < NFL; ++i) {
+                        const int j = lane + 32 * i, b = j / SC;
+                        const float g = wi < A.B ? A.drepr_in[(size_t)wi * NF + j] : 0.f;
+                        c.DPs[w_ * NF + j] = c.inv_bin > 0.f ? g * c.inv_bin : g / (float)(c.bin_e[b] - c.bin_s[b]);
+                    }
+                }
+                return;
             }
             if (A.head_norm) {
                 float m = 0.f;

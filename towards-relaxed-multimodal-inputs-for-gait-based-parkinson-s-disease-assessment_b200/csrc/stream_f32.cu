@@ -26,6 +26,12 @@ StreamKernelFn find_kernel(const KernelKey& k) {
     GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)
     GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
     GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
+    // trunk stages of the fusion baselines (no encoder; C = CIN): EarlyFusion3 3 x 12, CheapXAttn3 12; 2-stream twins
+    // (feature_encoder.py:346-596) early 6 + 6, late / cross-attention 6, shared latent 16
+    GK_CASE(ENC_NONE, 36, 1, 0, 36, 16, 4)
+    GK_CASE(ENC_NONE, 12, 1, 0, 12, 16, 4)
+    GK_CASE(ENC_NONE, 6, 1, 0, 6, 16, 4)
+    GK_CASE(ENC_NONE, 16, 1, 0, 16, 16, 4)
 #undef GK_CASE
 #undef GK_CASE_P
     return nullptr;

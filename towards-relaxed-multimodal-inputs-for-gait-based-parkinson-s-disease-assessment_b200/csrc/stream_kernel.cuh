@@ -131,13 +131,14 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
                                                         // encoder-pool tables (CONV_POOL)
     float* stage = sm + SP.STAGE;
     float* Ls = sm + SP.L; float* DLs = sm + SP.DL; float* wpf = sm + SP.WPF; float* bps = sm + SP.BP; float* wpd = sm + SP.WPD;
-    float* BBin = PROJ ? Ls : Fs;                        // what the backbone convolves
+    float* BBin = PROJ ? Ls : (ENC == ENC_NONE ? Xs : Fs);   // what the backbone convolves
+    const bool enc_only = A.feat_out != nullptr || A.dfeat_in != nullptr;      // encoder stage (no backbone, no head)
 
     // ---- one-time setup: zero everything (halos, padded channels), stage weights, bin tables
     for (int i = tid; i < SP.total; i += NT) sm[i] = 0.f;
     __syncthreads();
     // first conv / linear: PyTorch (O, CIN, KT1) -> wf[tap][ci][o]
-    {
+    if constexpr (ENC != ENC_NONE) {
         const int OUT1 = (ENC == ENC_INSOLE) ? H : C;
         for (int i = tid; i < OUT1 * CIN * KT1; i += NT) {
             const int o = i / (CIN * KT1), ci = (i / KT1) % CIN, tap = i % KT1;
@@ -156,10 +157,10 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         }
         for (int i = tid; i < C; i += NT) b2s[i] = A.b2[i] + (A.skip_identity ? 0.f : A.bsk[i]);
     }
-    if constexpr (ENC != ENC_CONV_POOL) {
+    if constexpr (ENC != ENC_CONV_POOL && ENC != ENC_NONE) {
         for (int i = tid; i < C; i += NT) { lngs[i] = A.lng[i]; lnbs[i] = A.lnb[i]; }
     }
-    for (int i = tid; i < S * CB * 3; i += NT) {
+    if (!enc_only) for (int i = tid; i < S * CB * 3; i += NT) {
         const int o = i / (CB * 3), ci = (i / 3) % CB, tap = i % 3;
         const float w = A.wbb[i];
         wbf[(tap * CBP + ci) * S + o] = w;
@@ -174,8 +175,8 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         }
         for (int i = tid; i < PROJ; i += NT) bps[i] = A.bp[i];
     }
-    for (int i = tid; i < S; i += NT) bbs[i] = A.bbb[i];
-    for (int i = tid; i < K * NF; i += NT) hws[i] = A.hw[i];
+    if (!enc_only) for (int i = tid; i < S; i += NT) bbs[i] = A.bbb[i];
+    if (A.hw) for (int i = tid; i < K * NF; i += NT) hws[i] = A.hw[i];
     if (A.hb) for (int i = tid; i < K; i += NT) hbs[i] = A.hb[i];
     if (A.head_norm) for (int i = tid; i < NF; i += NT) { hngs[i] = A.hng[i]; hnbs[i] = A.hnb[i]; }
     // adaptive pooling tables: bin b covers [floor(b*T/bdim), ceil((b+1)*T/bdim))
@@ -269,7 +270,9 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             }
             __syncthreads();
         }
-        if constexpr (ENC == ENC_CONV_POOL) {
+        if constexpr (ENC == ENC_NONE) {
+            // nothing: Xs is the backbone input
+        } else if constexpr (ENC == ENC_CONV_POOL) {
             // conv over the T_in input rows, no activation; optional adaptive pooling T_in -> T
             for (int r = tid; r < rows_in; r += NT) {
                 float a[CP];
@@ -327,7 +330,21 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             }
             __syncthreads();
         }
+        if (A.feat_out) {
+            // ---- encoder stage, forward: rows of F -> (B, T, C) and on to the next tile
+            for (int r = tid; r < rows; r += NT) {
+                const int t = r / W, w = r - t * W, wi = win0 + w;
+                if (wi >= A.B) continue;
+                float f[CP]; load_row<CP>(Fs, RB, halo, r, f);
+                float* dst = A.feat_out + ((size_t)wi * T + t) * C;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) if (c < C) dst[c] = f[c];
+            }
+            __syncthreads();
+            continue;
+        }
         // ================= shared backbone forward: conv3 -> ReLU
+        if (!A.dfeat_in) {
         for (int r = tid; r < rows; r += NT) {
             float z[S];
             conv_row<3, CB4, S>(BBin, RB, halo, W, r, wbf, bbs, z);
@@ -357,11 +374,32 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         }
         __syncthreads();
         g_wb.accumulate(BBin, RB, Zs, RB, halo, W, rows, tid);
+        }   // !A.dfeat_in
+        // gradient of the encoder output: the backbone's data gradient, or (encoder stage) what the fusion op sent back
+        auto load_dfeat = [&](int r, float (&df)[CP]) {
+            const int t = r / W, w = r - t * W, wi = win0 + w;
+            const float* src = A.dfeat_in + ((size_t)wi * T + t) * C;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) df[c] = (c < C && wi < A.B) ? src[c] : 0.f;
+        };
         // dgrad into the encoder output + encoder-specific backward up to the first-conv pre-activation
-        if constexpr (ENC == ENC_CONV_POOL) {
+        if constexpr (ENC == ENC_NONE) {
+            if (A.dx) {
+                for (int r = tid; r < rows; r += NT) {
+                    const int t = r / W, w = r - t * W, wi = win0 + w;
+                    if (wi >= A.B) continue;
+                    float dxr[CBP];
+                    conv_row<3, S4, CBP>(Zs, RB, halo, W, r, wbd, nullptr, dxr);
+                    float* dst = A.dx + ((size_t)wi * T + t) * CIN;
+#pragma unroll
+                    for (int c = 0; c < CBP; ++c) if (c < CIN) dst[c] = dxr[c];
+                }
+            }
+        } else if constexpr (ENC == ENC_CONV_POOL) {
             for (int r = tid; r < rows; r += NT) {
                 float df[CP];
-                conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
+                if (A.dfeat_in) load_dfeat(r, df);
+                else conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
                 if (A.pool_sensor) {
                     const float inv = 1.0f / (float)(ep_e[r] - ep_s[r]);
 #pragma unroll
@@ -407,7 +445,8 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
 #pragma unroll
                         for (int cc = 0; cc < C; ++cc) df[cc] = fmaf(dl[j], wpd[j * CP + cc], df[cc]);
                 } else {
-                    conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
+                    if (A.dfeat_in) load_dfeat(r, df);
+                    else conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
                 }
                 load_row<CP>(XHs, RB, halo, r, xh);
                 const float rstd = RSTDs[r];
@@ -465,7 +504,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     if (A.mode == MODE_FWD) return;
     __syncthreads();
     const GradOff& go = A.go;
-    {
+    if constexpr (ENC != ENC_NONE) {
         const int OUT1 = (ENC == ENC_INSOLE) ? H : C;
         g_w1.flush(stage, out + go.w1, nullptr, CIN, OUT1, tid);
         flush_rowacc<O1>(g_b1, OUT1, stage, out + go.b1, nullptr, tid);
@@ -474,17 +513,19 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         g_w2.flush(stage, out + go.w2, (A.skip_identity ? nullptr : out + go.wsk), H, C, tid);
         flush_rowacc<CP>(g_b2, C, stage, out + go.b2, (A.skip_identity ? nullptr : out + go.bsk), tid);
     }
-    if constexpr (ENC != ENC_CONV_POOL) {
+    if constexpr (ENC != ENC_CONV_POOL && ENC != ENC_NONE) {
         flush_rowacc<CP>(g_lng, C, stage, out + go.lng, nullptr, tid);
         flush_rowacc<CP>(g_lnb, C, stage, out + go.lnb, nullptr, tid);
     }
-    g_wb.flush(stage, out + go.wbb, nullptr, CB, S, tid);
+    if (go.wbb >= 0) {                                    // absent in an encoder stage
+        g_wb.flush(stage, out + go.wbb, nullptr, CB, S, tid);
+        flush_rowacc<S>(g_bb, S, stage, out + go.bbb, nullptr, tid);
+    }
     if constexpr (PROJ > 0) {
         g_wp.flush(stage, out + go.wp, nullptr, C, PROJ, tid);
         flush_rowacc<CBP>(g_bp, PROJ, stage, out + go.bp, nullptr, tid);
     }
-    flush_rowacc<S>(g_bb, S, stage, out + go.bbb, nullptr, tid);
-    head.flush(A, stage, out, tid);
+    if (go.hw >= 0) head.flush(A, stage, out, tid);       // absent in encoder / trunk stages
 }
 
 }  // namespace gaitk

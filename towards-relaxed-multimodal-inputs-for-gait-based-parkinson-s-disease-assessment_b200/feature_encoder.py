@@ -209,3 +209,124 @@ class SkelModalityModel(_SingleStreamModel):
     def forward(self, x):
         self._cfg["T"] = int(x.shape[1])
         return super().forward(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-stream fusion baselines (feature_encoder.py:346-596, trained by baselines/fusion_train.py): staged execution (staged.py)
+class _StagedTwoStream(nn.Module):
+    """Same sub-modules, construction order and ``state_dict`` keys as the reference classes; every stage a libgaitk.so kernel."""
+
+    def _encoders(self, skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length):
+        self.skel_enc = SkeletonMLP(skeleton_input_dim, skeleton_output_dim)
+        self.sens_enc = SensorEncoder(in_channels=sensor_in_channels, out_channels=sensor_out_channels, sensor_length=sensor_length)
+
+    def _encode(self, x_skel, x_sens):
+        from . import staged
+        k, e = self.skel_enc, self.sens_enc
+        sk = staged.encode(_lib.STAGE_LINEAR_LN_RELU, x_skel, [k.fc1.weight, k.fc1.bias, k.ln1.weight, k.ln1.bias], C_out=k.fc1.out_features)
+        pool = x_sens.shape[1] == e.d2_sensor_length                        # SensorEncoder pools only then (feature_encoder.py:55)
+        se = staged.encode(_lib.STAGE_CONV_POOL, x_sens, [e.conv1d.weight, e.conv1d.bias], C_out=e.conv1d.out_channels,
+                           T_out=e.output_length if pool else None, pool=pool)
+        return sk, se
+
+    def _repr(self, X):
+        from . import staged
+        return staged.trunk(X, self.backbone.conv1d.weight, self.backbone.conv1d.bias, self._bdim)
+
+    def _out(self, r_skel, r_sens=None):
+        from . import staged
+        r_sens = r_skel if r_sens is None else r_sens
+        if self.synchronized_loading:
+            return staged.linear(r_skel, self.head.weight, self.head.bias)
+        return staged.linear(r_skel, self.head_skel.weight, self.head_skel.bias), staged.linear(r_sens, self.head_sens.weight, self.head_sens.bias)
+
+    def _make_heads(self, feature_dim, num_classes, synchronized_loading):
+        if synchronized_loading:
+            self.head = nn.Linear(feature_dim, num_classes)
+        else:
+            self.head_skel = nn.Linear(feature_dim, num_classes)
+            self.head_sens = nn.Linear(feature_dim, num_classes)
+
+
+class EarlyFusionModel(_StagedTwoStream):
+    """feature_encoder.py:347-396: channel concat of the two encoder outputs -> one backbone -> head(s)."""
+
+    def __init__(self, skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length, shared_out_channels,
+                 backbone_dim, num_classes, synchronized_loading=False):
+        super().__init__()
+        self.synchronized_loading = synchronized_loading; self._bdim = backbone_dim
+        self._encoders(skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length)
+        self.backbone = SharedBackbone(in_channels=skeleton_output_dim + sensor_out_channels, shared_out_channels=shared_out_channels,
+                                       backbone_dim=backbone_dim)
+        self._make_heads(backbone_dim * shared_out_channels, num_classes, synchronized_loading)
+
+    def forward(self, x_skel, x_sens):
+        return self._out(self._repr(torch.cat(self._encode(x_skel, x_sens), dim=-1)))
+
+
+class LateFusionModel(_StagedTwoStream):
+    """feature_encoder.py:399-446: one backbone applied to each stream, the two latent vectors concatenated (2 x 128) -> head(s)."""
+
+    def __init__(self, skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length, shared_out_channels,
+                 backbone_dim, num_classes, synchronized_loading=False):
+        super().__init__()
+        self.synchronized_loading = synchronized_loading; self._bdim = backbone_dim
+        self._encoders(skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length)
+        self.backbone = SharedBackbone(in_channels=skeleton_output_dim, shared_out_channels=shared_out_channels, backbone_dim=backbone_dim)
+        self._make_heads(2 * backbone_dim * shared_out_channels, num_classes, synchronized_loading)
+
+    def forward(self, x_skel, x_sens):
+        sk, se = self._encode(x_skel, x_sens)
+        return self._out(torch.cat([self._repr(sk), self._repr(se)], dim=1))
+
+
+class ShareLatentModel(_StagedTwoStream):
+    """feature_encoder.py:449-494: per-stream Linear projection into a common width, shared backbone, ONE head on each latent."""
+
+    def __init__(self, skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length, shared_out_channels,
+                 backbone_dim, taskhead_input_dim, num_classes, synchronized_loading=False):
+        super().__init__()
+        self.synchronized_loading = synchronized_loading; self._bdim = backbone_dim
+        self._encoders(skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length)
+        self.proj_skel = nn.Linear(skeleton_output_dim, shared_out_channels)
+        self.proj_sens = nn.Linear(sensor_out_channels, shared_out_channels)
+        self.backbone = SharedBackbone(in_channels=shared_out_channels, shared_out_channels=shared_out_channels, backbone_dim=backbone_dim)
+        self.head = nn.Linear(backbone_dim * shared_out_channels, num_classes)
+
+    def forward(self, x_skel, x_sens):
+        from . import staged
+        sk, se = self._encode(x_skel, x_sens)
+        r_sk = self._repr(staged.linear(sk, self.proj_skel.weight, self.proj_skel.bias))
+        r_se = self._repr(staged.linear(se, self.proj_sens.weight, self.proj_sens.bias))
+        return staged.linear(r_sk, self.head.weight, self.head.bias), staged.linear(r_se, self.head.weight, self.head.bias)
+
+
+class CheapCrossAttention(nn.Module):
+    """feature_encoder.py:497-528 (symmetric, zero parameters): 0.5 (softmax(S G^T / sqrt d) G + softmax(G S^T / sqrt d) S)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.scale = dim ** -0.5
+
+    def forward(self, S, G):
+        from . import staged
+        return (staged.cheap_xattn(S, G) + staged.cheap_xattn(G, S)) * 0.5
+
+
+class CheapXAttnModel(_StagedTwoStream):
+    """feature_encoder.py:531-596: symmetric cross attention fuses the two encoded sequences -> backbone -> head(s)."""
+
+    def __init__(self, skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length, shared_out_channels,
+                 backbone_dim, num_classes, synchronized_loading=False):
+        super().__init__()
+        if skeleton_output_dim != sensor_out_channels:
+            raise _lib.GaitkError("cross attention needs the same feature width on both modalities")
+        self.synchronized_loading = synchronized_loading; self._bdim = backbone_dim
+        self._encoders(skeleton_input_dim, skeleton_output_dim, sensor_in_channels, sensor_out_channels, sensor_length)
+        self.cross_attn = CheapCrossAttention(dim=skeleton_output_dim)
+        self.backbone = SharedBackbone(in_channels=skeleton_output_dim, shared_out_channels=shared_out_channels, backbone_dim=backbone_dim)
+        self._make_heads(backbone_dim * shared_out_channels, num_classes, synchronized_loading)
+
+    def forward(self, x_skel, x_sens):
+        sk, se = self._encode(x_skel, x_sens)
+        return self._out(self._repr(self.cross_attn(sk, se)))

@@ -323,3 +323,100 @@ class SharedLatent3(_ThreeStreamBase):
 
     def forward(self, xw, xi, xm):
         return tuple(self._streams(xw, xi, xm))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Baselines that couple the streams between encoder and backbone: staged execution (staged.py)
+class _StagedThreeStream(nn.Module):
+    """EarlyFusion3 / CheapXAttn3: same sub-modules, construction order and ``state_dict`` keys as the reference classes; plain
+    ``nn.Parameter``s (any optimizer works), every forward / backward stage a libgaitk.so kernel (staged.py)."""
+
+    def _build(self, enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized, backbone_in):
+        if use_norm or use_cosine:
+            raise _lib.GaitkError("the staged fusion baselines use plain linear heads (weargait_train.py:513-524 builds them without "
+                                  "use_norm / use_cosine)")
+        self.synchronized = synchronized
+        self.enc_w = WalkwayEncoder(out_ch=enc_out_ch)
+        self.enc_i = InsoleEncoderDeep(in_ch=13, out_ch=enc_out_ch)
+        self.enc_m = IMUEncoderShallow(in_ch=24, out_ch=enc_out_ch)
+        self._dims = (enc_out_ch, backbone_dim, shared_out_ch)
+        return backbone_in
+
+    def _heads(self, backbone_dim, shared_out_ch, num_classes, synchronized):
+        self._shared_head, self.head_w, self.head_i, self.head_m = _shared_or_three_heads(
+            shared_out_ch * backbone_dim, num_classes, synchronized, False, False)
+
+    def _encode(self, xw, xi, xm):
+        from . import staged
+        C = self._dims[0]
+        ew, ei, em = self.enc_w, self.enc_i, self.enc_m
+        fw = staged.encode(_lib.STAGE_CONV_GELU_LN, xw, [ew.conv.weight, ew.conv.bias, ew.ln.weight, ew.ln.bias], C_out=C)
+        if isinstance(ei.skip, nn.Identity):
+            raise _lib.GaitkError("insole hidden width == output width (identity skip) is not built by the reference defaults")
+        fi = staged.encode(_lib.STAGE_INSOLE, xi, [ei.conv1.weight, ei.conv1.bias, ei.conv2.weight, ei.conv2.bias, ei.ln2.weight, ei.ln2.bias,
+                                                   ei.skip.weight, ei.skip.bias], C_out=C, H=ei.conv1.out_channels)
+        fm = staged.encode(_lib.STAGE_CONV_GELU_LN, xm, [em.conv.weight, em.conv.bias, em.ln.weight, em.ln.bias], C_out=C)
+        return fw, fi, fm
+
+    def _repr(self, X):
+        from . import staged
+        return staged.trunk(X, self.backbone.conv.weight, self.backbone.conv.bias, self._dims[1])
+
+    @staticmethod
+    def _head(head, r):
+        from . import staged
+        return staged.linear(r, head.fc.weight, head.fc.bias)
+
+    @property
+    def fuses_streams(self) -> bool:
+        return True
+
+
+class EarlyFusion3(_StagedThreeStream):
+    """weargait_encoders.py:209-245: the three encoder outputs concatenated along channels feed ONE backbone (3 C -> S)."""
+
+    def __init__(self, enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm=False, use_cosine=False, synchronized=True):
+        super().__init__()
+        self._build(enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized, 3 * enc_out_ch)
+        self.backbone = SharedBackbone(in_ch=3 * enc_out_ch, out_ch=shared_out_ch, bdim=backbone_dim)
+        self._heads(backbone_dim, shared_out_ch, num_classes, synchronized)
+
+    def forward(self, xw, xi, xm):
+        r = self._repr(torch.cat(self._encode(xw, xi, xm), dim=-1))
+        if self.synchronized:
+            logits = self._head(self._shared_head, r)
+            return logits, logits, logits
+        return self._head(self.head_w, r), self._head(self.head_i, r), self._head(self.head_m, r)
+
+
+class CheapCrossAttention(nn.Module):
+    """weargait_encoders.py:324-336 (zero parameters): softmax(A B^T / sqrt(d)) B."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.scale = dim ** -0.5
+
+    def forward(self, A, B):
+        from . import staged
+        return staged.cheap_xattn(A, B)
+
+
+class CheapXAttn3(_StagedThreeStream):
+    """weargait_encoders.py:338-387: six pairwise cross attentions, each stream's two attended sequences averaged, shared
+    backbone per stream, per-stream (or shared) heads."""
+
+    def __init__(self, enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm=False, use_cosine=False, synchronized=True):
+        super().__init__()
+        self._build(enc_out_ch, backbone_dim, shared_out_ch, num_classes, use_norm, use_cosine, synchronized, enc_out_ch)
+        self.xattn = CheapCrossAttention(dim=enc_out_ch)
+        self.backbone = SharedBackbone(in_ch=enc_out_ch, out_ch=shared_out_ch, bdim=backbone_dim)
+        self._heads(backbone_dim, shared_out_ch, num_classes, synchronized)
+
+    def forward(self, xw, xi, xm):
+        W, I, M = self._encode(xw, xi, xm)
+        xa = self.xattn
+        W_star = (xa(W, I) + xa(W, M)) * 0.5
+        I_star = (xa(I, W) + xa(I, M)) * 0.5
+        M_star = (xa(M, W) + xa(M, I)) * 0.5
+        return (self._head(self.head_w, self._repr(W_star)), self._head(self.head_i, self._repr(I_star)),
+                self._head(self.head_m, self._repr(M_star)))
