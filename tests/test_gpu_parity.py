@@ -10,7 +10,8 @@ from conftest import load_golden, sub
 
 pytestmark = pytest.mark.gpu
 
-WG_CASES = ["wg_sync_gcl", "wg_sync_gcl_drw", "wg_async_ce", "wg_async_gcl", "wg_sync_classwt_nc", "wg_sync_norm"]
+WG_CASES = ["wg_sync_gcl", "wg_sync_gcl_drw", "wg_async_ce", "wg_async_gcl", "wg_sync_classwt_nc", "wg_sync_norm",
+            "wg_scaled"]        # wg_scaled = BASELINE configs[4]: T = 256, enc_out_ch 24 (H = 48), shared_out_ch 32 -> 2-CTA clusters
 FOG_ASYNC = ["fog_async_gcl", "fog_async_ldam", "fbg_async_classwt"]
 FOG_ALL = ["fog_async_gcl", "fog_sync_gcl", "fog_async_ldam", "fog_sync_ce_nc", "fbg_async_classwt"]
 
@@ -1232,3 +1233,36 @@ def test_xattn_and_linear_kernels_match_torch(gk):
         close(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), 2e-5, "linear dx"); close(W.grad.cpu().numpy(), W2.grad.cpu().numpy(), 5e-5, "linear dW")
         if bias:
             close(b.grad.cpu().numpy(), b2.grad.cpu().numpy(), 5e-5, "linear db")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# long windows: a window split by time over a thread-block cluster (distributed-shared-memory halos)
+@pytest.mark.parametrize("T,kw,B", [(256, dict(enc_out_ch=24, shared_out_ch=32), 37), (256, {}, 21), (512, {}, 9), (128, dict(enc_out_ch=24, shared_out_ch=32), 19),
+                                    (64, dict(enc_out_ch=24, shared_out_ch=32), 33)])
+def test_long_windows_and_wide_models_match_oracle(gk, T, kw, B):
+    """T = 256 / 512 run as clusters of 2 / 4 CTAs (conv halos through DSMEM, pooled features all-gathered, head on CTA 0);
+    enc_out_ch / shared_out_ch other than the defaults use their own instantiations.  Two fused steps (async heads, GCL, CAGrad,
+    SGD) against the CPU oracle: losses, accuracy counts, the per-task shared-gradient matrix G, parameters."""
+    import gait_oracle as O
+    torch.manual_seed(7)
+    m = gk.WearGaitThreeModal(synchronized=False, **kw).cuda()
+    state = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    xs, y = O.synth_weargait_batch(B, T, seed=31)
+    r = np.random.default_rng(5); ys = [y, r.permutation(y), r.permutation(y)]
+    counts = [[40, 60], [45, 55], [30, 70]]
+    crit = [gk.GCLLoss(cls_num_list=c, m=0.2, s=25.0, noise_mul=0.0) for c in counts]
+    step = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0)
+    p = O.canonical_params(state, False); bufs = {}
+    for it in range(2):
+        loss, correct = step.step([dev(x) for x in xs], [dev(v) for v in ys])
+        plan = m.plan()
+        G = step._gbuf[:3 * plan.P].view(3, plan.P).cpu().numpy().copy()
+        ex = O.weargait_train_step(p, bufs, [torch.from_numpy(x) for x in xs], [torch.from_numpy(v) for v in ys],
+                                   synchronized=False, wm="gcl", counts=counts, alpha=0.5)
+        close(loss.cpu().numpy(), ex["losses"], 5e-5, "loss")
+        close(G, ex["G"].numpy().T, 2e-4, "G")
+        ref_correct = [int((l.argmax(1) == torch.from_numpy(v)).sum()) for l, v in zip(ex["logits"], ys)]
+        assert correct.cpu().numpy().round().astype(int).tolist() == ref_correct
+    for k, v in m.state_dict().items():
+        if k in p:
+            close(v.cpu().numpy(), p[k].detach().numpy(), 3e-5, k)

@@ -40,6 +40,7 @@ struct ParamInfo {
 
 struct StreamPlan {
     int enc, CIN, T_in, T, W, rows_in, rows, halo, RBi, RB, pool_sensor;
+    int cl;                                                            // thread-block cluster size (long windows split by time), else 1
     int H, C, S, NFL, KT1, skip_identity, PROJ;
     StreamKernelFn fn;
     SmemPlan sp; GradOff go; int NGP; size_t smem_bytes; int ctas_per_sm;
@@ -90,12 +91,22 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     sp.W = (pool_sensor || Tmax > NT / 2) ? 1 : std::min(WMAX, NT / Tmax);
     while (sp.W & (sp.W - 1)) --sp.W;                   // power of two (row <-> (t, w) by shifts)
     sp.rows = T * sp.W; sp.rows_in = T_in * sp.W; sp.halo = (KT1 / 2 > 1 ? KT1 / 2 : 1) * sp.W;
+    // long windows (T a multiple of 128 above 128, e.g. the scaled sweep's T = 256): the window is split by time over a
+    // thread-block cluster of T / 128 CTAs (stream_kernel.cuh); pooling bins must not straddle CTAs
+    sp.cl = 1;
+    if (!pool_sensor && T_in == T && T > NT && T % NT == 0 && enc != ENC_NONE) {
+        const int cl = T / NT;
+        if (cl > 8) return fail(GAITK_E_SHAPE, "window length %d needs a cluster of %d CTAs (> 8)", T, cl);
+        if (T % d.backbone_dim != 0 || d.backbone_dim % cl != 0)
+            return fail(GAITK_E_SHAPE, "window length %d with %d pooling bins: bins would straddle the %d CTAs of a cluster", T, d.backbone_dim, cl);
+        sp.cl = cl; sp.rows = NT; sp.rows_in = NT;
+    }
     sp.RB = round_rb(sp.rows, sp.halo); sp.RBi = round_rb(sp.rows_in, sp.halo);
     KernelKey key = {enc, CIN, KT1, H, sp.C, sp.S, sp.NFL, sp.PROJ};
     sp.fn = find_kernel(key);
     if (!sp.fn)
         return fail(GAITK_E_SHAPE, "no sm_100a kernel instantiated for stream %d (enc=%d Cin=%d k=%d H=%d C=%d S=%d NF=%d); "
-                    "supported: WearGait C=12/S=16/bdim=8, FoG and FBG defaults", s, enc, CIN, KT1, H, sp.C, sp.S, NF);
+                    "supported: WearGait C=12/S=16 and C=24/S=32 (bdim=8), FoG and FBG defaults", s, enc, CIN, KT1, H, sp.C, sp.S, NF);
     // ---- shared memory plan (floats)
     const int CI4 = (CIN + 3) / 4, C4 = (sp.C + 3) / 4, CP = C4 * 4, H4 = (H + 3) / 4, S4 = sp.S / 4;
     const int O1 = (enc == ENC_INSOLE) ? H4 * 4 : CP;
@@ -132,7 +143,7 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     sp.ctas_per_sm = occ;
     // ---- tensor-core variant (tcgen05 + mma.sync, tf32): full 128-row tiles only
     const bool fixed_geo = T == 64 && sp.W == 2 && d.backbone_dim == 8;     // WearGait default window: compile-time geometry
-    sp.fn_tc = (sp.rows == NT && T_in == T && sp.PROJ == 0) ? find_kernel_tc(key, fixed_geo) : nullptr;
+    sp.fn_tc = (sp.rows == NT && T_in == T && sp.PROJ == 0 && sp.cl == 1) ? find_kernel_tc(key, fixed_geo) : nullptr;
     if (sp.fn_tc) {
         auto ev = [](int x) { return (x + 1) / 2 * 2; };
         const int KX = ev(CI4), KH = ev(H4), KC = ev(C4), KS = ev(S4);
@@ -346,6 +357,8 @@ static int stream_grid(const gaitk_plan* pl, const StreamPlan& sp, int B, int dt
     if (dtype == GAITK_DTYPE_BF16X3)                     // one persistent CTA per SM, `groups` tiles in flight in each
         return std::max(1, std::min((ntiles + sp.ws.groups - 1) / sp.ws.groups, pl->sm_count));
     const int per_sm = dtype == GAITK_DTYPE_TF32 ? sp.ctas_tc : sp.ctas_per_sm;
+    if (sp.cl > 1 && dtype == GAITK_DTYPE_F32)            // one cluster per window at a time: grid = clusters * cl
+        return std::max(1, std::min(ntiles, pl->sm_count * per_sm / sp.cl)) * sp.cl;
     return std::max(1, std::min(ntiles, pl->sm_count * per_sm));
 }
 static int check_dtype(const gaitk_plan* pl, int dtype) {
@@ -381,7 +394,7 @@ static void fill_args(const gaitk_plan* pl, int s, const float* params, const fl
     a.x = x; a.win_start = (const long long*)ws; a.B = B; a.T_in = sp.T_in; a.T = sp.T; a.W = sp.W;
     a.bdim = pl->d.backbone_dim; a.K = pl->d.num_classes; a.NF = pl->NF;
     a.rows_in = sp.rows_in; a.rows = sp.rows; a.halo = sp.halo; a.RBi = sp.RBi; a.RB = sp.RB;
-    a.mode = mode; a.zero_input = zero_input; a.pool_sensor = sp.pool_sensor;
+    a.mode = mode; a.zero_input = zero_input; a.pool_sensor = sp.pool_sensor; a.cl = sp.cl;
     a.w1 = pp(params, pl, sp.p_w1); a.b1 = pp(params, pl, sp.p_b1); a.w2 = pp(params, pl, sp.p_w2); a.b2 = pp(params, pl, sp.p_b2);
     a.wsk = pp(params, pl, sp.p_wsk); a.bsk = pp(params, pl, sp.p_bsk); a.lng = pp(params, pl, sp.p_lng); a.lnb = pp(params, pl, sp.p_lnb);
     a.wbb = pp(params, pl, pl->p_wbb); a.bbb = pp(params, pl, pl->p_bbb);
@@ -396,6 +409,14 @@ static int launch_stream(const gaitk_plan* pl, int s, const StreamArgs& a, int g
     const StreamPlan& sp = pl->st[s];
     if (dtype == GAITK_DTYPE_BF16X3) sp.ws.fn<<<grid, sp.ws.threads, sp.ws.smem, st>>>(a);
     else if (dtype == GAITK_DTYPE_TF32) sp.fn_tc<<<grid, sp.tc_threads, sp.smem_tc, st>>>(a, sp.tp);
+    else if (sp.cl > 1) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = sp.smem_bytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = sp.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, sp.fn, a, sp.sp));
+    }
     else sp.fn<<<grid, NT, sp.smem_bytes, st>>>(a, sp.sp);
     LAUNCH_CHECK();
     return 0;

@@ -50,6 +50,8 @@ struct StreamArgs {
     int B, T_in, T, W, bdim, K, NF;
     int rows_in, rows, halo, RBi, RB;
     int mode, zero_input, pool_sensor;
+    int cl;                        // > 1: a window is split by TIME over a thread-block cluster of `cl` CTAs (T = cl * rows, W = 1):
+                                   // conv halos travel through distributed shared memory, pooled features are all-gathered
     // parameters (global memory, PyTorch layouts)
     const float *w1, *b1, *w2, *b2, *wsk, *bsk, *lng, *lnb, *wbb, *bbb, *hng, *hnb, *hw, *hb;
     const float *wp, *bp;          // optional per-stream projection Linear(C -> PROJ) between encoder and backbone (SharedLatent3)

@@ -21,6 +21,10 @@ StreamKernelFn find_kernel(const KernelKey& k) {
     GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
     GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
     GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
+    // scaled sweep (BASELINE configs[4]: --enc_out_ch 24 --shared_out_ch 32, H = 48, NF = 256; T = 256 runs as 2-CTA clusters)
+    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 24, 32, 8)
+    GK_CASE(ENC_INSOLE, 13, 5, 48, 24, 32, 8)
+    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 24, 32, 8)
     // FoG (configs.py:17-31) and FBG (:2-16)
     GK_CASE(ENC_LINEAR_LN_RELU, 21, 1, 0, 6, 16, 4)
     GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)

@@ -2,6 +2,8 @@
 // backward in a single persistent kernel, fp32 FFMA arithmetic ("GAITK_DTYPE_F32" path, parity 1e-5).
 // Layout, tiling and phase structure: see stream_common.cuh and DESIGN.md section 3.1.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "stream_common.cuh"
 
 namespace gaitk {
@@ -133,6 +135,29 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     float* Ls = sm + SP.L; float* DLs = sm + SP.DL; float* wpf = sm + SP.WPF; float* bps = sm + SP.BP; float* wpd = sm + SP.WPD;
     float* BBin = PROJ ? Ls : (ENC == ENC_NONE ? Xs : Fs);   // what the backbone convolves
     const bool enc_only = A.feat_out != nullptr || A.dfeat_in != nullptr;      // encoder stage (no backbone, no head)
+    // ---- long windows (T = cl * 128, W = 1): a thread-block cluster of `cl` CTAs shares one window, CTA k owns frames
+    // [k rows, (k + 1) rows).  After every layer whose output feeds a k-tap convolution the CTAs copy their neighbours' boundary
+    // rows into their own halo rows through distributed shared memory (the outer halos of the first / last CTA stay zero: the
+    // reference pads every layer with zeros at the window edges); pooling bins never straddle CTAs (host check), each CTA pools
+    // its own bins and writes them into every CTA's feature vector, all CTAs run the head, CTA 0 alone keeps its sums.
+    namespace cg = cooperative_groups;
+    const int CLn = A.cl > 1 ? A.cl : 1;
+    const int crank = CLn > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const int t_off = crank * rows;                       // first frame of this CTA (W == 1 when CLn > 1)
+    auto xchg = [&](float* buf, int nch, int RBx) {      // buf: [chunk][RBx rows][4]; own rows written and block-synchronised
+        if (CLn == 1) return;
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        for (int e = tid; e < 2 * nch * halo; e += NT) {
+            const int side = e / (nch * halo), rem = e - side * nch * halo, ch = rem / halo, h = rem - ch * halo;
+            const int peer = side == 0 ? crank - 1 : crank + 1;
+            if (peer < 0 || peer >= CLn) continue;
+            const float4* src = reinterpret_cast<const float4*>(cluster.map_shared_rank(buf, peer)) + (size_t)ch * RBx + halo + (side == 0 ? rows - halo + h : h);
+            float4* dst = reinterpret_cast<float4*>(buf) + (size_t)ch * RBx + (side == 0 ? h : halo + rows + h);
+            *dst = *src;
+        }
+        __syncthreads();
+    };
 
     // ---- one-time setup: zero everything (halos, padded channels), stage weights, bin tables
     for (int i = tid; i < SP.total; i += NT) sm[i] = 0.f;
@@ -240,10 +265,20 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
     const float inv_denom = (A.mode == MODE_FUSED) ? 1.0f / A.denom[0] : 0.f;
 
     const int ntiles = (A.B + W - 1) / W;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x / CLn; tile < ntiles; tile += gridDim.x / CLn) {
         const int win0 = tile * W;
         // ================= load: global (window-major) -> Xs [chunk][row][4]
-        {
+        if (CLn > 1) {
+            // frames [t_off - halo, t_off + rows + halo) of the one window; zero outside [0, T)
+            const int wi = win0;
+            const size_t base = (wi < A.B) ? (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * T_in * CIN) : 0;
+            for (int e = tid; e < (rows + 2 * halo) * CIN; e += NT) {
+                const int rr = e / CIN, c = e - rr * CIN, t = t_off + rr - halo;
+                float v = 0.f;
+                if (t >= 0 && t < T && wi < A.B && !A.zero_input) v = __ldg(A.x + base + (size_t)t * CIN + c);
+                Xs[((c >> 2) * RBi + rr) * 4 + (c & 3)] = v;
+            }
+        } else {
             const int per_win = T_in * CIN;
             for (int e = tid; e < W * per_win; e += NT) {
                 const int w = (e >= per_win) + (e >= 2 * per_win) + (e >= 3 * per_win), rem = e - w * per_win;   // W <= 4
@@ -269,6 +304,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
                 if (train) store_row<O1>(D1s, RB, halo, r, d1);
             }
             __syncthreads();
+            xchg(HAs, H4, RB);
         }
         if constexpr (ENC == ENC_NONE) {
             // nothing: Xs is the backbone input
@@ -329,6 +365,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
                 }
             }
             __syncthreads();
+            xchg(BBin, CB4, RB);
         }
         if (A.feat_out) {
             // ---- encoder stage, forward: rows of F -> (B, T, C) and on to the next tile
@@ -354,6 +391,27 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         }
         __syncthreads();
         // ================= adaptive pool + head + loss: warp w <-> window w of the tile
+        if (CLn > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (wrp == 0) {
+#pragma unroll
+                for (int i = 0; i < NFL; ++i) {
+                    const int j = lane + 32 * i, b = j / S, sch = j - b * S;
+                    const int t0 = bin_s[b], t1 = bin_e[b];
+                    if (t0 < t_off || t1 > t_off + rows) continue;          // another CTA's bin
+                    float acc = 0.f;
+                    for (int t = t0; t < t1; ++t) acc += Zs[((sch >> 2) * RB + halo + (t - t_off)) * 4 + (sch & 3)];
+                    const float f = acc / (float)(t1 - t0);
+                    for (int peer = 0; peer < CLn; ++peer) cluster.map_shared_rank(Ps, peer)[j] = f;
+                }
+            }
+            cluster.sync();
+            hc.Ps = Ps;
+            if (wrp == 0) {
+                head.run(A, hc, 0, lane, win0, train, inv_denom);
+                if (crank != 0) head.zero();                               // CTA 0 alone accounts for the head, loss and accuracy
+            }
+        } else
         if (wrp < W) head.run(A, hc, wrp, lane, win0, train, inv_denom);
         if (!train) { __syncthreads(); continue; }
         __syncthreads();
@@ -362,7 +420,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             const int t = r / W, w = r - t * W;
             float z[S], dz[S];
             load_row<S>(Zs, RB, halo, r, z);
-            const int lo = t_lo[t], hi = t_hi[t];
+            const int lo = t_lo[t + t_off], hi = t_hi[t + t_off];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 float d = 0.f;
@@ -373,6 +431,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             store_row<S>(Zs, RB, halo, r, dz);
         }
         __syncthreads();
+        xchg(Zs, S4, RB);
         g_wb.accumulate(BBin, RB, Zs, RB, halo, W, rows, tid);
         }   // !A.dfeat_in
         // gradient of the encoder output: the backbone's data gradient, or (encoder stage) what the fusion op sent back
@@ -480,6 +539,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
             }
             __syncthreads();
             if constexpr (ENC == ENC_INSOLE) {
+                xchg(XHs, C4, RB);
                 g_w2.accumulate(HAs, RB, XHs, RB, halo, W, rows, tid);
                 for (int r = tid; r < rows; r += NT) {
                     float dh[O1], d1[O1];
@@ -499,6 +559,7 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const Sm
         __syncthreads();
     }
 
+    if (CLn > 1) cg::this_cluster().sync();                // no CTA exits while a neighbour may still read its shared memory
     // ================= flush per-CTA partial sums (deterministic order)
     float* out = A.partial + (size_t)blockIdx.x * A.NGP;
     if (A.mode == MODE_FWD) return;
