@@ -174,8 +174,8 @@ def synth_fog_labels(B: int, seed: int = 0):
     return np.random.default_rng(seed).choice(3, size=B, p=[0.5, 0.3, 0.2]).astype(np.int64)
 
 
-def synth(B, seed):
-    return synth_weargait_batch(B, T_=T, seed=seed)
+def synth(B, seed, T_=T):
+    return synth_weargait_batch(B, T_=T_, seed=seed)
 
 
 def stream_labels(kind: str, B: int, rank: int, i: int):
@@ -262,6 +262,10 @@ def workload_name(B, kind="weargait"):
     if kind == "fog":
         return (f"FoG 2-stream train step (configs[3]): B={B} sequences/GPU of skeleton (101,21) + sensor (426,6) fp32, async heads, "
                 "GCL m=0.2 s=25, CAGrad c=0.1, SGD mom 0.9 wd 1e-4")
+    if kind == "scaled":
+        return (f"WearGait scaled sweep (configs[4]: T=256, enc_out_ch 24 (insole hidden 48), shared_out_ch 32): B={B} windows/GPU of "
+                "(256,2)+(256,13)+(256,24) fp32, sync labels, GCL m=0.2 s=25, CAGrad c=0.5, SGD mom 0.9 wd 1e-4; fp32 FFMA stream kernels, "
+                "every window split by time over a 2-CTA thread-block cluster")
     tag = {"weargait": "configs[1]: sync labels, shared head",
            "weargait_async": "configs[2] async: independent per-stream labels, three private heads",
            "weargait_relaxed": "configs[2] relaxed input: per-step modality mask cycling the 7 MASK_COMBOS, masked streams zero-filled "
@@ -291,11 +295,13 @@ def build_workload(args, gaitk, dev, rank):
         return dict(model=model, crit=crit, host=host, names=("skeleton", "sensor"), dims=((101, 21), (426, 6)),
                     cagrad_c=0.1, private_mult=1.0, dtype="f32", kw=lambda i: {})
     sync = kind != "weargait_async"
-    model = gaitk.WearGaitThreeModal(synchronized=sync).to(dev)
+    scaled = kind == "scaled"
+    Tw = 256 if scaled else T
+    model = gaitk.WearGaitThreeModal(synchronized=sync, **(dict(enc_out_ch=24, shared_out_ch=32) if scaled else {})).to(dev)
     crit = [gaitk.GCLLoss(cls_num_list=c, m=0.2, s=25, noise_mul=0.0) for c in COUNTS]
     host = []
     for i in range(2):
-        xs, y = synth(B, 1000 * rank + i)
+        xs, y = synth(B, 1000 * rank + i, Tw)
         yl = stream_labels(kind, B, rank, i)
         assert np.array_equal(yl[0], y)
         if sync:
@@ -304,8 +310,8 @@ def build_workload(args, gaitk, dev, rank):
             ys = [torch.from_numpy(v).pin_memory() for v in yl]
         host.append(([torch.from_numpy(x).pin_memory() for x in xs], ys))
     kw = (lambda i: dict(enabled=MASK_CYCLE[i % 7], tasks=MASK_CYCLE[i % 7])) if kind == "weargait_relaxed" else (lambda i: {})
-    return dict(model=model, crit=crit, host=host, names=("walkway", "insole", "imu"), dims=((T, 2), (T, 13), (T, 24)),
-                cagrad_c=0.5, private_mult=2.0, dtype=args.dtype, kw=kw)
+    return dict(model=model, crit=crit, host=host, names=("walkway", "insole", "imu"), dims=((Tw, 2), (Tw, 13), (Tw, 24)),
+                cagrad_c=0.5, private_mult=2.0, dtype="f32" if scaled else args.dtype, kw=kw)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -341,7 +347,7 @@ def run_gpu(args):
             return None
         per_rank = [stream_labels(args.workload, B, r, i) for r in range(world)]
         out = [torch.from_numpy(np.concatenate([pr[s_] for pr in per_rank])).to(dev) for s_ in range(ns)]
-        if args.workload in ("weargait", "weargait_relaxed"):
+        if args.workload in ("weargait", "weargait_relaxed", "scaled"):
             out = [out[0]] * ns                           # one shared label vector (same device pointer: one histogram)
         return out
     yglob = [global_labels(i) for i in range(NBUF)]
@@ -504,6 +510,19 @@ def run_gpu(args):
                 "per_stream_ms": per_stream,
                 "step_hbm_gbs": B * bytes_per_unit / (ms_max / args.steps * 1e-3) / 1e9}
 
+        if args.workload == "scaled":
+            # 22.816 MFLOP per window per step, AI 286 FLOP/B > ridge: the only tensor-bound configuration
+            pk = ROOT / "MEASURED_PEAKS.json"
+            tpeak = float(json.loads(pk.read_text())["bf16_tflops_sustained"]) if pk.exists() else 1413.9
+            tf = 22.816e6 * B / (ms_max / args.steps * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "whole step (3 fp32 FFMA stream kernels on 2-CTA clusters + reduce + update)",
+                    "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if pk.exists() else "fallback",
+                    "algorithmic_flops_per_window": 22.816e6, "per_stream_ms": per_stream,
+                    "note": "this configuration runs on the fp32 FFMA path (parity 1e-5 against the wg_scaled golden); the tensor-core "
+                            "kernels are instantiated for the reference's default widths only, so the fraction of the bf16 tensor peak "
+                            "is the honest distance to north_star's >= 50 % tensor-pipe target, not a tensor-pipe measurement"}
+
     # ---- batch sweep of the fused step (device-resident, CUDA-graph replay), rank 0, N = 1: the reference trains at B = 64
     sweep = None
     if rank == 0 and world == 1 and args.workload == "weargait" and not args.no_sweep:
@@ -592,12 +611,14 @@ def main():
     ap.add_argument("--p2p", type=int, default=0, help="1 = data-parallel exchange by the peer-memory all-reduce kernel gaitk_p2p_allreduce "
                     "(one graph per step); 0 = NCCL all_reduce between two graphs (default: measured 4%% faster at N=2)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step (kernels + the NCCL all-reduce when data-parallel) as one CUDA graph")
-    ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog"],
+    ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog", "scaled"],
                     help="default = BASELINE.json configs[1]; the others are extra report lines")
     ap.add_argument("--dtype", default="bf16x3", choices=["f32", "tf32", "bf16x3"],
                     help="contraction arithmetic of the stream kernels: bf16x3 = split-bf16 operands (hi + lo, three tcgen05 passes, "
                          "fp32 accumulate; the warp-specialised kernel), tf32 = round-1 tcgen05 + mma.sync kernel, f32 = FFMA")
     args = ap.parse_args()
+    if args.workload == "scaled" and args.batch == 32768:
+        args.batch = 4096                                   # BASELINE configs[4]: batch 4096 per GPU
     args.warmup = max(args.warmup, 3) if args.impl == "gaitk" else args.warmup
     if args.impl == "gaitk" and args.cpu_batch <= 0:
         args.cpu_batch = 4096
