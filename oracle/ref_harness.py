@@ -176,7 +176,7 @@ def write_synthetic_weargait(root: Path, n_per_class: int = 6, seed: int = 0, fr
 
 
 # ---------------------------------------------------------------------------------------------- synthetic FoG / FBG readers
-def synthetic_fog_reader(dataset: str = "fog", seed: int = 0, n_subjects: int = 9):
+def synthetic_fog_reader(dataset: str = "fog", seed: int = 0, n_subjects: int = 9, scalar_labels: bool = True, informative: bool = False):
     """An object with the attributes `create_fusion_loaders` reads (dataloader_fbg_fog.py:291-327), in the key formats the
     reference's readers produce (preprocess_fog.py:107,146: `<SUB>_<video>_<segment>`; FBG: pose `<SUB>_<on|off>_walk_<i>`,
     GRF `<SUB>_<on|off>_walk` with a trial axis).  Clip lengths straddle the pad lengths; some sensor segments are missing
@@ -187,14 +187,18 @@ def synthetic_fog_reader(dataset: str = "fog", seed: int = 0, n_subjects: int = 
         subs = [f"SUB{i + 1:02d}" for i in range(n_subjects)]
         labels = {}
         for si, sub in enumerate(subs):
-            labels[sub] = [int(si % 3)] if si % 2 == 0 else int(si % 3)       # list and scalar forms (:314-318)
+            # list and scalar forms (:314-318); the trainer's fold generator (utilities.py:97-101) needs the list form
+            labels[sub] = [int(si % 3)] if (si % 2 == 0 or not scalar_labels) else int(si % 3)
+            amp = 1.0 + (si % 3) if informative else 1.0                      # class-dependent scale: a learnable problem
             for v in range(2):
                 for seg in range(1, 3 + int(rng.integers(0, 2))):
                     L = int(rng.integers(40, 150))
                     pose[f"{sub}_v{v}_{seg}"] = rng.random((L, 7, 3)) * 4.0 - 1.0
+                    if informative:                                            # class-dependent jitter of the non-root joints (min-max keeps it)
+                        pose[f"{sub}_v{v}_{seg}"][:, 1:, :] += rng.standard_normal((L, 6, 3)) * (si % 3)
                     if rng.random() < 0.85:
                         Ls = int(rng.integers(140, 520))
-                        sens[f"{sub}_v{v}_{seg}"] = rng.standard_normal((Ls, 6))
+                        sens[f"{sub}_v{v}_{seg}"] = rng.standard_normal((Ls, 6)) * amp
                 if rng.random() < 0.5:                                         # a sensor segment without a pose partner
                     sens[f"{sub}_v{v}_9"] = rng.standard_normal((int(rng.integers(140, 520)), 6))
         reader = SimpleNamespace(pose_dict=pose, sensor_dict=sens, labels_dict=labels)

@@ -61,3 +61,34 @@ def test_unmodified_run_cv_on_the_dropin(harness, name, dtype):
                 assert abs(res["masks"][k][kk] - v[kk]) <= 0.5, (k, kk, res["masks"][k], v)
         else:
             assert abs(res["masks"][k] - v) <= 0.5, (k, res["masks"][k], v)
+
+
+@pytest.mark.parametrize("name", ["fog_main_sync", "fog_main_async"])
+def test_unmodified_fbg_fog_main_on_the_dropin(harness, name):
+    """The UNMODIFIED FoG trainer `fbg_fog_train.main` (train/fbg_fog_train.py:410-438: folds, create_fusion_loaders, choose_model,
+    class counts, GCL branch losses, CAGrad(n_tasks=2), process_batch incl. the symmetric-KL consistency term in the synchronised
+    case, run_epoch, reports) on gaitk through module shadowing -- device-resident clip stores and loaders (dataloader_fbg_fog),
+    fused kernels behind the autograd bridge, CUDA losses, on-device CAGrad -- against what the reference printed on CPU
+    (tests/golden/fog_main_*.json, oracle/make_trainer_golden.py)."""
+    import importlib
+    import gaitk
+    from make_trainer_golden import run_reference_fog_main
+    gold = json.loads((ROOT / "tests" / "golden" / f"{name}.json").read_text())
+    meta = gold["meta"]
+    gaitk.integration.install_shadow(harness.reference_root())
+    FT = importlib.import_module("fbg_fog_train")
+    assert FT.create_fusion_loaders is gaitk.dataloader_fbg_fog.create_fusion_loaders and FT.CAGrad is gaitk.CAGrad
+    import utilities
+    assert utilities.MultiModalMultiTaskModel is gaitk.MultiModalMultiTaskModel
+    FT.DEVICE = torch.device("cuda")
+    reader, _ = harness.synthetic_fog_reader(**meta["reader"])
+    res = run_reference_fog_main(FT, reader, synchronized_loading=meta["synchronized_loading"])
+    assert len(res["epochs"]) == len(gold["epochs"]) > 0
+    for a, b in zip(res["epochs"], gold["epochs"]):
+        assert (a["fold"], a["ep"]) == (b["fold"], b["ep"])
+        assert abs(a["train_loss"] - b["train_loss"]) <= 2e-3 and abs(a["val_loss"] - b["val_loss"]) <= 2e-3, (a, b)
+        assert np.abs(np.array(a["train_acc"]) - np.array(b["train_acc"])).max() <= 0.5, (a, b)
+        assert np.abs(np.array(a["val_acc"]) - np.array(b["val_acc"])).max() <= 0.5, (a, b)
+    assert len(res["best"]) == len(gold["best"]) > 0
+    assert np.abs(np.array(res["best"]) - np.array(gold["best"])).max() <= 0.5, (res["best"], gold["best"])
+    assert np.abs(np.array(res["mean"]) - np.array(gold["mean"])).max() <= 0.5, (res["mean"], gold["mean"])
