@@ -35,7 +35,9 @@ class _CELossFn(torch.autograd.Function):
             raise _lib.GaitkError("gaitk losses run on CUDA only (no CPU path)")
         lg = logits.contiguous().float(); y = target.contiguous().long()
         B, K = lg.shape
-        loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+        # a 0-dim tensor of its own (NOT a view of a buffer): the trainers update losses in place (`l_skel += ...`,
+        # fbg_fog_train.py:123), which autograd forbids on a view returned by a custom Function
+        loss = torch.empty((), dtype=torch.float32, device=lg.device)
         correct = torch.empty(1, dtype=torch.int32, device=lg.device)
         dlog = torch.empty_like(lg)
         off = None if logit_off is None else logit_off.contiguous().float()
@@ -44,7 +46,7 @@ class _CELossFn(torch.autograd.Function):
         ctx.save_for_backward(dlog)
         if stats is not None:
             stats["correct"] = correct
-        return loss[0]
+        return loss
 
     @staticmethod
     def backward(ctx, g):
