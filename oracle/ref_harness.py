@@ -251,3 +251,46 @@ def loader_trace(train_loader, eval_loader, epochs: int = 2):
             out[f"{nm}_ep{ep}/ys"] = np.array(ys); out[f"{nm}_ep{ep}/yt"] = np.array(yt)
             out[f"{nm}_ep{ep}/cs"] = np.array(cs); out[f"{nm}_ep{ep}/ct"] = np.array(ct); out[f"{nm}_ep{ep}/bs"] = np.array(bs)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- synthetic raw WearGait CSVs (ETL)
+def write_synthetic_weargait_csvs(root: Path, n_per_class: int = 2, seed: int = 0, rows=(400, 700)):
+    """Raw recordings in the layout preprocess_weargait.run_end_to_end expects (preprocess_weargait.py:14-19, 22-52): per-subject
+    `<SID>_SelfPace_matTURN.csv` at ~100 Hz with a `Time` column written as "12,345 sec", a `GeneralEvent` column with some
+    "Standing" rows, foot pressures, insole forces / CoP / accelerometers, eight IMU sites, NaN holes and one subject without an
+    IMU site; demographic sheets whose real header is the second row.  -> (hc_root, pd_root, hc_demo, pd_demo, subject ids)"""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    sites = ["L_Ankle", "R_Ankle", "L_DorsalFoot", "R_DorsalFoot", "L_MidLatThigh", "R_MidLatThigh", "L_LatShank", "R_LatShank"]
+    sids = []
+    out = {}
+    for cls, tag in ((0, "HC"), (1, "PD")):
+        d = root / "data" / "WearGait" / tag
+        d.mkdir(parents=True, exist_ok=True)
+        demo = [["", "", ""], ["Subject ID", "Age", "Weight (kg)"]]
+        for i in range(n_per_class):
+            sid = f"{tag}{i + 1:03d}"; sids.append(sid)
+            n = int(rng.integers(rows[0], rows[1]))
+            t = np.cumsum(rng.uniform(0.006, 0.014, n)) - 0.2 * (i == 1)          # irregular ~100 Hz clock; one subject starts at t < 0
+            cols = {"Time": [f"{v:.4f}".replace(".", ",") + " sec" for v in t],
+                    "GeneralEvent": np.where(rng.random(n) < 0.1, "Standing", "Walking"),
+                    "L Foot Pressure": rng.random(n) * 800, "R Foot Pressure": rng.random(n) * 800,
+                    "LTotalForce": rng.random(n) * 700, "RTotalForce": rng.random(n) * 700,
+                    "LCoP_X": rng.standard_normal(n), "LCoP_Y": rng.standard_normal(n), "RCoP_X": rng.standard_normal(n), "RCoP_Y": rng.standard_normal(n)}
+            for side in ("Linsole", "Rinsole"):
+                for ax in "XYZ":
+                    cols[f"{side}:Acc_{ax}"] = rng.standard_normal(n) * 3 + 1
+            for s_ in sites:
+                if cls == 1 and i == 0 and s_ == "R_LatShank":
+                    continue
+                for ax in "ENU":
+                    cols[f"{s_}_FreeAcc_{ax}"] = rng.standard_normal(n) * (2.0 if cls else 1.0)
+            df = pd.DataFrame(cols)
+            for c in ("L Foot Pressure", "LCoP_X", "Linsole:Acc_Y", "L_Ankle_FreeAcc_E"):
+                df.loc[rng.random(n) < 0.05, c] = np.nan
+            df.loc[5:9, "Time"] = "n/a"
+            df.to_csv(d / f"{sid}_SelfPace_matTURN.csv", index=False)
+            demo.append([sid, str(50 + i), f"{60 + 7.5 * i + 5 * cls:.1f} kg"])
+        pd.DataFrame(demo).to_csv(d / f"{tag.lower()}_demographic.csv", header=False, index=False)
+        out[tag] = (str(d), str(d / f"{tag.lower()}_demographic.csv"))
+    return out["HC"][0], out["PD"][0], out["HC"][1], out["PD"][1], sids

@@ -233,3 +233,63 @@ def test_fog_pairing_and_oversampling_match_the_reference():
     assert np.allclose(DF.compute_class_weights([10, 20, 30]).numpy(), (lambda w: w / w.sum() * 3)(1 / np.array([10, 20, 30.0])), rtol=1e-6)
     a = np.arange(12.0).reshape(6, 2)
     assert DF.pad_or_trim(a, 6) is a and DF.pad_or_trim(a, 4).shape == (4, 2) and np.array_equal(DF.pad_or_trim(a, 8)[6:], np.zeros((2, 2)))
+
+
+def test_weargait_etl_matches_the_reference(tmp_path):
+    """f3: raw CSVs -> 30 Hz PKLs (preprocess_weargait.run_end_to_end, :228-343) against the reference's own ETL on the same synthetic
+    recordings -- fold-agnostic (`*_base.pkl`) and with train statistics -- frame by frame, and the direct CSV -> frame-matrix path
+    against the PKL round trip through the loader."""
+    import contextlib, io, json, sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    import ref_harness as H
+    if H.load_reference() is None:
+        pytest.skip("no reference copy (oracle/_ref or /root/reference)")
+    import pandas as pd
+    from data_processing import preprocess_weargait as REF
+    import gaitk
+    from importlib import import_module
+    ETL = import_module(gaitk.__name__ + ".preprocess_weargait")
+    hc, pdr, hcd, pdd, sids = H.write_synthetic_weargait_csvs(tmp_path, n_per_class=2, seed=4)
+    for mode, train in (("base", None), ("fold", [sids[0], sids[2]])):
+        outs = {}
+        for tag, mod in (("ref", REF), ("new", ETL)):
+            o = tmp_path / f"{mode}_{tag}"
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                mod.run_end_to_end(hc, pdr, hcd, pdd, str(o), train_subject_ids=train, segment_len_rows=64)
+            outs[tag] = (o, buf.getvalue())
+        assert outs["ref"][1] == outs["new"][1]                        # the printed per-subject / total counts
+        files = sorted(p.name for p in outs["ref"][0].iterdir())
+        assert files == sorted(p.name for p in outs["new"][0].iterdir()) and len(files) >= 3 * len(sids)
+        for f in files:
+            if f.endswith(".json"):
+                a = json.loads((outs["ref"][0] / f).read_text()); b = json.loads((outs["new"][0] / f).read_text())
+                assert a.keys() == b.keys() and all(np.allclose(a[k], b[k], rtol=1e-13, atol=0) for k in a)
+                continue
+            a = pd.read_pickle(outs["ref"][0] / f); b = pd.read_pickle(outs["new"][0] / f)
+            assert list(a.columns) == list(b.columns) and len(a) == len(b) > 50, f
+            for c in a.columns:
+                if a[c].dtype == object:
+                    xa = np.array([np.asarray(t, dtype=float) for t in a[c]]); xb = np.array([np.asarray(t, dtype=float) for t in b[c]])
+                else:
+                    xa = a[c].to_numpy(dtype=float); xb = b[c].to_numpy(dtype=float)
+                assert np.allclose(xa, xb, rtol=1e-13, atol=0, equal_nan=True), (f, c)
+    # CSV -> frame matrices directly == CSV -> PKL -> loader
+    wmap = ETL.build_weight_map(hcd, pdd)
+    files = {**ETL.find_subject_files(hc), **ETL.find_subject_files(pdr)}
+    d = tmp_path / "base_new"
+    for sid in sids:
+        direct = ETL.subject_frames(files[sid.lower()], wmap[sid.lower()])
+        for nm in ("insole", "imu"):                                    # the loader reads <sid>_<m>.pkl: give it the base tables
+            (d / f"{sid.lower()}_{nm}.pkl").write_bytes((d / f"{sid.lower()}_{nm}_base.pkl").read_bytes())
+        via = gaitk.dataloader_weargait.load_subject_frames(d, sid)
+        for m in ("walkway", "insole", "imu"):
+            a = np.nan_to_num(direct[m], nan=0.0) if m != "walkway" else direct[m]
+            # the loader maps wholly missing columns to 0 (ensure_cols); isolated NaNs stay NaN in both
+            for j in range(via[m].shape[1]):
+                col_d, col_v = direct[m][:, j], via[m][:, j]
+                if np.isnan(col_d).all():
+                    assert (col_v == 0).all()
+                else:
+                    assert np.array_equal(col_d, col_v, equal_nan=True), (sid, m, j)
