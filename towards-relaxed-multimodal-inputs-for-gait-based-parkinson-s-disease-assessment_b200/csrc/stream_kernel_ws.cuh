@@ -31,6 +31,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "stream_common.cuh"
 #include "umma.cuh"
 
@@ -38,9 +40,13 @@ namespace gaitk {
 
 constexpr int WS_NPH = 6;                    // operand-ready sync points per tile (simple encoders use 4)
 
-template <class Cfg, int G_>
+template <class Cfg, int G_, int SL_ = 1>
 struct WsLayout {
     static constexpr int G = G_;
+    // SL tiles ("slots") per row warpgroup: a row thread alternates between the same phase of its SL tiles, so the MMA of one
+    // tile runs under the epilogue of the other (ping-pong) instead of under other warps' epilogues; RG = G / SL row warpgroups
+    static constexpr int SL = SL_, RG = G_ / SL_;
+    static_assert(G_ % SL_ == 0, "groups = row warpgroups x slots");
     static constexpr int ENC = Cfg::ENC, CIN = Cfg::CIN, KT1 = Cfg::KT1, H = Cfg::H, C = Cfg::C, S = Cfg::S;
     static constexpr bool INS = ENC == ENC_INSOLE;
     static_assert(ENC == ENC_CONV_GELU_LN || ENC == ENC_INSOLE, "WearGait encoders");
@@ -106,10 +112,11 @@ struct WsLayout {
     static constexpr int C_BB = C_B2 + (INS ? 16 : 0);
     static constexpr int C_END = C_BB + 16;
     static_assert(C_END <= 512, "TMEM columns");
-    static constexpr int NTH = (G + 1) * 128;                            // G row warpgroups + one service warpgroup
+    static constexpr int NTH = (RG + 1) * 128;                           // RG row warpgroups + one service warpgroup
     static constexpr int REG_SERVICE = G == 3 ? 80 : 64;
     static constexpr int REG_LAUNCH = (65536 / NTH) / 8 * 8;
-    static constexpr int REG_ROW = ((NTH * REG_LAUNCH - 128 * REG_SERVICE) / (G * 128)) / 8 * 8;
+    static constexpr int REG_ROW_ = ((NTH * REG_LAUNCH - 128 * REG_SERVICE) / (RG * 128)) / 8 * 8;
+    static constexpr int REG_ROW = REG_ROW_ > 232 ? 232 : REG_ROW_;
 };
 
 namespace ws {
@@ -173,6 +180,9 @@ __device__ __forceinline__ void st_zero_x8(uint32_t taddr) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+template <int N, class F> __device__ __forceinline__ void static_for(F&& f) {          // f(integral_constant<0>) ... f(integral_constant<N - 1>)
+    if constexpr (N > 0) { static_for<N - 1>(f); f(std::integral_constant<int, N - 1>{}); }
+}
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -338,14 +348,15 @@ struct HeadLite {
 #define WT(i) do { } while (0)
 #endif
 
-template <class Cfg, int G, int K>
-__global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(const StreamArgs A) {
+template <class Cfg, int G, int K, int SL = 1>
+__global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws(const StreamArgs A) {
 #ifdef GAITK_WS_TIMING
     long long wt_acc[16], wt_last = 0; bool wt_on = false;
 #pragma unroll
     for (int i = 0; i < 16; ++i) wt_acc[i] = 0;
 #endif
-    using L = WsLayout<Cfg, G>;
+    using L = WsLayout<Cfg, G, SL>;
+    constexpr int RG = L::RG;
     constexpr int CIN = L::CIN, KT1 = L::KT1, H = L::H, C = L::C, HALO = L::HALO, PL = L::PL;
     constexpr bool INS = L::INS;
     constexpr int NX8 = L::NX8, NX8E = L::NX8E, NH8 = L::NH8, NH8E = L::NH8E, NC8 = L::NC8, NS8 = L::NS8, N1 = L::N1, O1 = L::O1, NH = L::NH;
@@ -429,7 +440,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
     const int per_it = (int)gridDim.x * G;
     const int nit = (ntiles + per_it - 1) / per_it;
     auto tile_of = [&](int it, int g) { return (it * (int)gridDim.x + (int)blockIdx.x) * G + g; };
-    constexpr int ROW_WARPS = 4 * G;
+    constexpr int ROW_WARPS = 4 * RG;
 
     if (warp >= ROW_WARPS) {                               // the LAST warpgroup: the hardware arbiter prefers high warp ids, so an
                                                            // MMA / TMA issue never queues behind the row warps' epilogue instructions
@@ -581,78 +592,76 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         for (int i = 0; i < 16; ++i) { g_lng[i] = 0.f; g_lnb[i] = 0.f; }
         head.zero();
         const int rw = warp;                               // row warp index
-        const int g = rw >> 2, wq = rw & 3, r = wq * 32 + lane;
-        uint8_t* gb = smw + g * L::GRP;
-        const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + g * 32;
-        float* Ps = reinterpret_cast<float*>(gb + L::O_P); float* DPs = reinterpret_cast<float*>(gb + L::O_DP);
+        const int rg = rw >> 2, wq = rw & 3, r = wq * 32 + lane;      // row warpgroup, lane quarter, row of the tile
         const float inv_denom = (A.mode == MODE_FUSED) ? 1.0f / A.denom[0] : 0.f;
         const float* b1s = f32 + L::F_B1; const float* b2s = f32 + L::F_B2; const float* lngs = f32 + L::F_LNG; const float* lnbs = f32 + L::F_LNB;
         const float* bbs = f32 + L::F_BB;
-        uint32_t dph = 0;                                  // parity of the group's `done` barrier
-        // every thread orders its operand stores before the async proxy, the warp converges, ONE lane arrives (128 arrivals on one
-        // shared-memory word serialise 32-way per warp instruction: half of all shared-memory wavefronts in the v10 profile)
-        auto arrive = [&](int k) {
-            umma::fence_smem_to_async(); umma::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(bar_rdy(g, k));
-        };
-        auto wait_done = [&]() { umma::mbar_wait(bar_done(g), dph); dph ^= 1u; umma::fence_after_sync(); };
         const int t = r >> 1, w = r & 1;
-#ifdef GAITK_WS_TIMING
-        wt_on = blockIdx.x == 0 && g == 0 && r == 0; wt_last = clock64();
-#endif
-        for (int it = 0; it < nit; ++it) {
+        // per-slot state: slot s of this row warpgroup <-> group g = rg * SL + s (own planes, barriers, TMEM columns, service warp)
+        float rstd_row[SL]; uint32_t zmask[SL], dph[SL]; int ylab[SL];
+#pragma unroll
+        for (int q = 0; q < SL; ++q) { rstd_row[q] = 0.f; zmask[q] = 0u; dph[q] = 0u; ylab[q] = 0; }
+        // One phase of one slot.  Every phase ends with the arrival that lets the slot's service warp issue the next MMAs, and the
+        // thread moves on to the SAME phase of its next slot: that slot's accumulator has been computed meanwhile.
+        constexpr int NHP = INS ? NH8 * 8 : 8;              // padded conv1 width (the insole-only phases are never run otherwise)
+        auto phase = [&](auto P_, auto S_, int it) {
+            constexpr int P = decltype(P_)::value, sl = decltype(S_)::value;
+            const int g = rg * SL + sl;
+            uint8_t* gb = smw + g * L::GRP;
+            const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + g * 32;
+            float* Ps = reinterpret_cast<float*>(gb + L::O_P); float* DPs = reinterpret_cast<float*>(gb + L::O_DP);
             const uint32_t par = it & 1;
-            const int tile = tile_of(it, g), win0 = tile * 2;
-            int kk = 0;
-            // the head warps fetch their window's label now; it is consumed a few thousand clocks later
-            int ylab = 0;
-            if (wq < 2 && A.mode == MODE_FUSED && win0 + wq < A.B) ylab = (int)A.y[win0 + wq];
-            // ------------------------------------------------ staged window bytes -> X planes (hi, lo)
-            umma::mbar_wait(bar_ld(g), par);
-            WT(0);
-            if (!A.zero_input) {
-                const bool live = win0 + w < A.B;
-                const int j = t / L::FPC;
-                const float* src = reinterpret_cast<const float*>(gb + (L::P_F + w * L::CPW + j) * PL + HALO * 16) + (t - j * L::FPC) * CIN;
-                float v[NX8 * 8];
-                if constexpr (CIN % 4 == 0) {
+            const int win0 = tile_of(it, g) * 2;
+            // every thread orders its operand stores before the async proxy, the warp converges, ONE lane arrives
+            auto arrive = [&](int k) {
+                umma::fence_smem_to_async(); umma::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(bar_rdy(g, k));
+            };
+            auto wait_done = [&]() { umma::mbar_wait(bar_done(g), dph[sl]); dph[sl] ^= 1u; umma::fence_after_sync(); };
+            if constexpr (P == 0) {
+                // the head warps fetch their window's label now; it is consumed a few thousand clocks later
+                ylab[sl] = 0;
+                if (wq < 2 && A.mode == MODE_FUSED && win0 + wq < A.B) ylab[sl] = (int)A.y[win0 + wq];
+                // ------------------------------------------------ staged window bytes -> X planes (hi, lo)
+                umma::mbar_wait(bar_ld(g), par);
+                if (!A.zero_input) {
+                    const bool live = win0 + w < A.B;
+                    const int j = t / L::FPC;
+                    const float* src = reinterpret_cast<const float*>(gb + (L::P_F + w * L::CPW + j) * PL + HALO * 16) + (t - j * L::FPC) * CIN;
+                    float v[NX8 * 8];
+                    if constexpr (CIN % 4 == 0) {
 #pragma unroll
-                    for (int c4 = 0; c4 < CIN / 4; ++c4) {
-                        const float4 q = reinterpret_cast<const float4*>(src)[c4];
-                        v[4 * c4] = q.x; v[4 * c4 + 1] = q.y; v[4 * c4 + 2] = q.z; v[4 * c4 + 3] = q.w;
+                        for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                            const float4 q = reinterpret_cast<const float4*>(src)[c4];
+                            v[4 * c4] = q.x; v[4 * c4 + 1] = q.y; v[4 * c4 + 2] = q.z; v[4 * c4 + 3] = q.w;
+                        }
+                    } else if constexpr (CIN == 2) {
+                        const float2 q = *reinterpret_cast<const float2*>(src); v[0] = q.x; v[1] = q.y;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CIN; ++c) v[c] = src[c];
                     }
-                } else if constexpr (CIN == 2) {
-                    const float2 q = *reinterpret_cast<const float2*>(src); v[0] = q.x; v[1] = q.y;
-                } else {
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) v[c] = src[c];
+                    for (int c = 0; c < NX8 * 8; ++c) v[c] = (c < CIN && live) ? v[c] : 0.f;
+                    ws::store_split<NX8 * 8, PL>(gb + L::P_X * PL, HALO + r, v);
                 }
-#pragma unroll
-                for (int c = 0; c < NX8 * 8; ++c) v[c] = (c < CIN && live) ? v[c] : 0.f;
-                ws::store_split<NX8 * 8, PL>(gb + L::P_X * PL, HALO + r, v);
+                arrive(0);
             }
-            arrive(kk++);
-            WT(1);
-            // ------------------------------------------------ encoder forward
-            if constexpr (INS) {
+            if constexpr (P == 1 && INS) {
+                // ------------------------------------------------ conv1 epilogue: GELU -> HA planes (+ saved derivative)
                 wait_done();
-                WT(2);
-                {
-                    float a1[N1], ha[NH8 * 8], d1[NH8 * 8];
-                    umma::ld_x16(trow, a1); umma::ld_x8(trow + 16, a1 + 16); umma::ld_wait();
+                float a1[32], ha[NHP], d1[NHP];
+                umma::ld_x16(trow, a1); umma::ld_x8(trow + 16, a1 + 16); umma::ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NH8 * 8; ++c) { if (c < H) gelu_fwd_fast(a1[c] + b1s[c], ha[c], d1[c]); else { ha[c] = 0.f; d1[c] = 0.f; } }
-                    ws::store_split<NH8 * 8, PL>(gb + L::P_HA * PL, HALO + r, ha);
-                    if (train) ws::store_half<NH8 * 8, PL>(gb + L::P_D1 * PL, HALO + r, d1);
-                }
-                arrive(kk++);
-                WT(3);
+                for (int c = 0; c < NHP; ++c) { if (c < H) gelu_fwd_fast(a1[c] + b1s[c], ha[c], d1[c]); else { ha[c] = 0.f; d1[c] = 0.f; } }
+                ws::store_split<NHP, PL>(gb + L::P_HA * PL, HALO + r, ha);
+                if (train) ws::store_half<NHP, PL>(gb + L::P_D1 * PL, HALO + r, d1);
+                arrive(1);
             }
-            wait_done();
-            WT(4);
-            float rstd_row = 0.f;
-            {
+            if constexpr (P == 2) {
+                // ------------------------------------------------ encoder epilogue: GELU, LayerNorm -> F planes
+                wait_done();
                 float a[16], gl[16], d[16], xh[16], f[16]; float rstd;
                 ws::ld_merged16(trow, a);
                 const float* bias = INS ? b2s : b1s;
@@ -670,59 +679,54 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                     float4* xp = reinterpret_cast<float4*>(gb + L::P_XH * PL) + (HALO + r);
 #pragma unroll
                     for (int c4 = 0; c4 < (C + 3) / 4; ++c4) xp[c4 * L::RB] = make_float4(xh[4 * c4], xh[4 * c4 + 1], xh[4 * c4 + 2], xh[4 * c4 + 3]);
-                    rstd_row = rstd;
+                    rstd_row[sl] = rstd;
+                }
+                arrive(INS ? 2 : 1);
+            }
+            if constexpr (P == 3) {
+                // ------------------------------------------------ shared backbone forward: ReLU + adaptive pooling (8 frames per bin)
+                wait_done();
+                uint32_t zm = 0;
+                {
+                    float z[16];
+                    ws::ld_merged16(trow, z);
+                    umma::fence_before_sync();
+                    float zz[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { zz[q] = fmaxf(z[q] + bbs[q], 0.f); zm |= (zz[q] > 0.f ? 1u : 0u) << q; }
+                    // the 8 rows of one (window, bin) are the lanes with equal (lane & 1, lane >> 4): reduce-scatter butterfly over lane
+                    // bits 3, 2, 1; afterwards lane l holds the sums of channels 2 * ((l >> 1) & 7) and + 1
+                    float a8[8], a4[4], a2[2];
+                    const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const float keep = h8 ? zz[8 + i] : zz[i], send = h8 ? zz[i] : zz[8 + i]; a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float keep = h4 ? a8[4 + i] : a8[i], send = h4 ? a8[i] : a8[4 + i]; a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) { const float keep = h2 ? a4[2 + i] : a4[i], send = h2 ? a4[i] : a4[2 + i]; a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+                    const int ch = (h8 ? 8 : 0) + (h4 ? 4 : 0) + (h2 ? 2 : 0);
+                    *reinterpret_cast<float2*>(Ps + w * 128 + (r >> 4) * 16 + ch) = make_float2(a2[0] * 0.125f, a2[1] * 0.125f);
+                }
+                zmask[sl] = zm;
+                ws::bar_sync(1 + rg, 128);
+                // ------------------------------------------------ head + loss: warp q < 2 <-> window q of the tile
+                if (wq < 2) head.run(A, Ps + wq * 128, DPs + wq * 128, f32 + L::F_HW, f32 + L::F_HB, lane, win0 + wq, train, inv_denom, ylab[sl]);
+                ws::bar_sync(1 + rg, 128);
+                if (train) {
+                    // ------------------------------------------------ dz through pooling + ReLU -> Z planes
+                    float dz[16];
+                    const float4* dp = reinterpret_cast<const float4*>(DPs + w * 128 + (t >> 3) * 16);
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) { const float4 q = dp[s4]; dz[4 * s4] = q.x; dz[4 * s4 + 1] = q.y; dz[4 * s4 + 2] = q.z; dz[4 * s4 + 3] = q.w; }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) dz[q] = ((zm >> q) & 1u) ? dz[q] : 0.f;
+                    ws::store_split<16, PL>(gb + L::P_Z * PL, HALO + r, dz);
+                    arrive(INS ? 3 : 2);
                 }
             }
-            arrive(kk++);
-            WT(5);
-            // ------------------------------------------------ shared backbone forward: ReLU + adaptive pooling (8 frames per bin)
-            wait_done();
-            WT(6);
-            uint32_t zmask = 0;
-            {
-                float z[16];
-                ws::ld_merged16(trow, z);
-                umma::fence_before_sync();
-                float zz[16];
-#pragma unroll
-                for (int s = 0; s < 16; ++s) { zz[s] = fmaxf(z[s] + bbs[s], 0.f); zmask |= (zz[s] > 0.f ? 1u : 0u) << s; }
-                // the 8 rows of one (window, bin) are the lanes with equal (lane & 1, lane >> 4): reduce-scatter butterfly over lane
-                // bits 3, 2, 1; afterwards lane l holds the sums of channels 2 * ((l >> 1) & 7) and + 1
-                float a8[8], a4[4], a2[2];
-                const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const float keep = h8 ? zz[8 + i] : zz[i], send = h8 ? zz[i] : zz[8 + i]; a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const float keep = h4 ? a8[4 + i] : a8[i], send = h4 ? a8[i] : a8[4 + i]; a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) { const float keep = h2 ? a4[2 + i] : a4[i], send = h2 ? a4[i] : a4[2 + i]; a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
-                const int ch = (h8 ? 8 : 0) + (h4 ? 4 : 0) + (h2 ? 2 : 0);
-                *reinterpret_cast<float2*>(Ps + w * 128 + (r >> 4) * 16 + ch) = make_float2(a2[0] * 0.125f, a2[1] * 0.125f);
-            }
-            WT(7);
-            ws::bar_sync(1 + g, 128);
-            WT(8);
-            // ------------------------------------------------ head + loss: warp q < 2 <-> window q of the tile
-            if (wq < 2) head.run(A, Ps + wq * 128, DPs + wq * 128, f32 + L::F_HW, f32 + L::F_HB, lane, win0 + wq, train, inv_denom, ylab);
-            ws::bar_sync(1 + g, 128);
-            WT(9);
-            if (!train) continue;
-            // ------------------------------------------------ dz through pooling + ReLU -> Z planes
-            {
-                float dz[16];
-                const float4* dp = reinterpret_cast<const float4*>(DPs + w * 128 + (t >> 3) * 16);
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) { const float4 q = dp[s4]; dz[4 * s4] = q.x; dz[4 * s4 + 1] = q.y; dz[4 * s4 + 2] = q.z; dz[4 * s4 + 3] = q.w; }
-#pragma unroll
-                for (int s = 0; s < 16; ++s) dz[s] = ((zmask >> s) & 1u) ? dz[s] : 0.f;
-                ws::store_split<16, PL>(gb + L::P_Z * PL, HALO + r, dz);
-            }
-            arrive(kk++);
-            WT(10);
-            // ------------------------------------------------ LayerNorm / GELU backward -> dA (over XH)
-            wait_done();
-            WT(11);
-            {
+            if constexpr (P == 4) {
+                // ------------------------------------------------ LayerNorm / GELU backward -> dA (over XH)
+                wait_done();
                 float df[16], xh[16], dxh[16], dg[16], d[(C + 3) / 4 * 4], da[16];
                 ws::ld_merged16(trow, df);
                 const float4* xp = reinterpret_cast<const float4*>(gb + L::P_XH * PL) + (HALO + r);
@@ -739,36 +743,37 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
                     g_lng[c] = fmaf(dfc, xh[c], g_lng[c]); g_lnb[c] += dfc;
                     dxh[c] = c < C ? dfc * lngs[c] : 0.f;
                 }
-                ln_bwd<16, C>(dxh, xh, rstd_row, dg);
+                ln_bwd<16, C>(dxh, xh, rstd_row[sl], dg);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) da[c] = c < C ? dg[c] * d[c] : 0.f;
                 ws::store_split<16, PL>(gb + L::P_XH * PL, HALO + r, da);
+                arrive(INS ? 4 : 3);
             }
-            arrive(kk++);
-            WT(12);
-            if constexpr (INS) {
+            if constexpr (P == 5 && INS) {
                 // ------------------------------------------------ conv2 data gradient -> dA1 (over HA, once conv2's weight gradient has read it)
                 wait_done();
-                {
-                    float dh[NH], d1[NH8 * 8], da1[NH8 * 8];
-                    umma::ld_x16(trow, dh); umma::ld_x8(trow + 16, dh + 16); umma::ld_wait();
-                    ws::load_half<NH8 * 8, PL>(gb + L::P_D1 * PL, HALO + r, d1);
+                float dh[32], d1[NHP], da1[NHP];
+                umma::ld_x16(trow, dh); umma::ld_x8(trow + 16, dh + 16); umma::ld_wait();
+                ws::load_half<NHP, PL>(gb + L::P_D1 * PL, HALO + r, d1);
 #pragma unroll
-                    for (int c = 0; c < NH8 * 8; ++c) da1[c] = c < H ? dh[c] * d1[c] : 0.f;
-                    umma::mbar_wait(bar_wfree(g), par);
-                    ws::store_split<NH8 * 8, PL>(gb + L::P_HA * PL, HALO + r, da1);
-                }
-                arrive(kk++);
-                WT(13);
+                for (int c = 0; c < NHP; ++c) da1[c] = c < H ? dh[c] * d1[c] : 0.f;
+                umma::mbar_wait(bar_wfree(g), par);
+                ws::store_split<NHP, PL>(gb + L::P_HA * PL, HALO + r, da1);
+                arrive(5);
             }
-            wait_done();                                   // the first-layer weight gradient has read X and dA: the tile's buffers are free
-            WT(14);
+            if constexpr (P == 6) wait_done();             // the first-layer weight gradient has read X and dA: the tile's buffers are free
+        };
+        auto all_slots = [&](auto P_, int it) { ws::static_for<SL>([&](auto S_) { phase(P_, S_, it); }); };
+        for (int it = 0; it < nit; ++it) {
+            all_slots(std::integral_constant<int, 0>{}, it);
+            if constexpr (INS) all_slots(std::integral_constant<int, 1>{}, it);
+            all_slots(std::integral_constant<int, 2>{}, it);
+            all_slots(std::integral_constant<int, 3>{}, it);
+            if (!train) continue;
+            all_slots(std::integral_constant<int, 4>{}, it);
+            if constexpr (INS) all_slots(std::integral_constant<int, 5>{}, it);
+            all_slots(std::integral_constant<int, 6>{}, it);
         }
-#ifdef GAITK_WS_TIMING
-        if (wt_on) printf("ROW    CIN%d nit %d: ld %lld conv %lld | w1 %lld e1 %lld | w %lld enc %lld | wbb %lld pool %lld bar %lld head %lld | dz %lld | wdg %lld lnb %lld | ins %lld | wfinal %lld\n", CIN, nit,
-                          wt_acc[0] / nit, wt_acc[1] / nit, wt_acc[2] / nit, wt_acc[3] / nit, wt_acc[4] / nit, wt_acc[5] / nit, wt_acc[6] / nit, wt_acc[7] / nit, wt_acc[8] / nit, wt_acc[9] / nit,
-                          wt_acc[10] / nit, wt_acc[11] / nit, wt_acc[12] / nit, wt_acc[13] / nit, wt_acc[14] / nit);
-#endif
         // -------------------------------------------------------------------------------------- teardown + flush
         umma::fence_before_sync();
         asm volatile("bar.sync 0;" ::: "memory");          // every group has seen its last commit: all MMAs are complete
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         float* hstage = stage + ROW_WARPS * 32;            // [head warp][K * 128 + K + 2]
         constexpr int HS = K * 128 + K + 2;
         if (wq < 2) {
-            float* hs = hstage + (g * 2 + wq) * HS;
+            float* hs = hstage + (rg * 2 + wq) * HS;
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -807,14 +812,14 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G>::NTH, 1) stream_kernel_ws(con
         }
         for (int e = rt; e < HS; e += ROW_WARPS * 32) {
             float s = 0.f;
-            for (int q = 0; q < 2 * G; ++q) s += hstage[q * HS + e];
+            for (int q = 0; q < 2 * RG; ++q) s += hstage[q * HS + e];
             if (e < K * 128) out[go.hw + e] = s;
             else if (e < K * 128 + K) { if (go.hb >= 0) out[go.hb + e - K * 128] = s; }
             else out[go.total + (e - K * 128 - K)] = s;    // [NG] = loss, [NG + 1] = correct
         }
-        if (g == 0) {
+        if (rg == 0) {
             const uint32_t tq = tmem + ((uint32_t)(wq * 32) << 16);
-            float* bst = hstage + 2 * G * HS;              // [4 warps][64] per-row sums
+            float* bst = hstage + 2 * RG * HS;             // [4 warps][64] per-row sums
             float* wst = bst + 256;                        // [tap][64 rows][32 columns] one weight-gradient region at a time
             // per-row sums (bias gradients): reduce over the 128 lanes
             auto colsum = [&](int col0, int n, int slot) {
