@@ -57,7 +57,23 @@ struct gaitk_plan {
     int n_streams; StreamPlan st[GAITK_MAX_STREAMS];
     int p_wbb, p_bbb;
     int NF;
+    // side streams + events: the stream kernels of a small batch (no kernel fills the GPU) run concurrently, forked from and
+    // joined back into the caller's stream (capturable: the fork / join become graph edges); created on first use
+    cudaStream_t side[GAITK_MAX_STREAMS - 1] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[GAITK_MAX_STREAMS - 1] = {nullptr, nullptr};
+    ~gaitk_plan() {
+        for (auto& e : ev_join) if (e) cudaEventDestroy(e);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto& q : side) if (q) cudaStreamDestroy(q);
+    }
 };
+static int ensure_side_streams(gaitk_plan* pl) {
+    if (pl->ev_fork) return 0;
+    for (auto& q : pl->side) CUDA_TRY(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    for (auto& e : pl->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+    return 0;
+}
 
 static int add_param(gaitk_plan* pl, const std::string& name, int group, int d0, int d1 = 0, int d2 = 0) {
     ParamInfo p; p.name = name; p.off = pl->NP; p.group = group;
@@ -627,6 +643,16 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
     ReduceArgsMulti M; memset(&M, 0, sizeof(M));
     int n_active = 0, max_ng = 0;
     float* part = (float*)workspace;
+    // small batch (no stream kernel fills the GPU): the kernels of the streams run side by side on forked streams
+    bool fork = false;
+    {
+        int live = 0, widest = 0;
+        for (int s = 0; s < pl->n_streams; ++s)
+            if (task_mask & (1u << s)) { ++live; widest = std::max(widest, stream_grid(pl, pl->st[s], B, dtype) * (dtype == GAITK_DTYPE_BF16X3 ? 1 : 1)); }
+        fork = live > 1 && widest < pl->sm_count;
+        if (fork) { int rc_ = ensure_side_streams(pl); if (rc_) return rc_; CUDA_TRY(cudaEventRecord(pl->ev_fork, st)); }
+    }
+    int n_forked = 0;
     for (int s = 0; s < pl->n_streams; ++s) {
         const size_t ws_floats = (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64;
         float* my_part = part; part += ws_floats;
@@ -638,8 +664,14 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         a.logits = logits ? logits[s] : nullptr;
         a.partial = my_part;
         const int grid = stream_grid(pl, pl->st[s], B, dtype);
-        int rc = launch_stream(pl, s, a, grid, st, dtype);
+        cudaStream_t ks = st;
+        if (fork && n_active > 0) {                       // first active stream stays on the caller's stream
+            ks = pl->side[n_forked];
+            CUDA_TRY(cudaStreamWaitEvent(ks, pl->ev_fork, 0));
+        }
+        int rc = launch_stream(pl, s, a, grid, ks, dtype);
         if (rc) return rc;
+        if (ks != st) { CUDA_TRY(cudaEventRecord(pl->ev_join[n_forked], ks)); CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join[n_forked], 0)); ++n_forked; }
         fill_reduce(pl, s, my_part, grid, gbuf, s, private_mult, s, M.r[n_active]);
         max_ng = std::max(max_ng, M.r[n_active].NG + 2);
         ++n_active;
