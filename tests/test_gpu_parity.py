@@ -1266,3 +1266,30 @@ def test_long_windows_and_wide_models_match_oracle(gk, T, kw, B):
     for k, v in m.state_dict().items():
         if k in p:
             close(v.cpu().numpy(), p[k].detach().numpy(), 3e-5, k)
+
+
+def test_fused_step_with_gcl_noise_matches_the_criterion_path(gk):
+    """GCL with noise_mul != 0 (classification_losses.py:99-105) inside the fused step: with the same seed the fused step
+    draws the same clamped-normal noise as the criterion's own call, so one fused step equals one autograd-path step."""
+    torch.manual_seed(0)
+    B = 50
+    xs = [torch.rand(B, 64, 2, device="cuda"), torch.randn(B, 64, 13, device="cuda"), torch.randn(B, 64, 24, device="cuda")]
+    y = torch.randint(0, 2, (B,), device="cuda"); y[0], y[1] = 0, 1
+    def build():
+        torch.manual_seed(4)
+        m = gk.WearGaitThreeModal(synchronized=True).cuda()
+        crit = [gk.GCLLoss(cls_num_list=[40, 60], m=0.2, s=25.0, noise_mul=0.5) for _ in range(3)]
+        return m, crit
+    ma, ca = build()
+    step = gk.FusedTrainStep(ma, ca, cagrad_c=0.5, private_mult=2.0)
+    torch.manual_seed(123)
+    loss_a, _ = step.step(xs, [y, y, y]); loss_a = loss_a.clone()
+    mb, cb = build()
+    opt = torch.optim.SGD(mb.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    cag = gk.CAGrad(n_tasks=3, device=torch.device("cuda"), c=0.5, max_norm=1.0)
+    torch.manual_seed(123)
+    lg = mb(*xs)
+    L = [c(l, y) for c, l in zip(cb, lg)]
+    close(loss_a.cpu().numpy(), torch.stack([l.detach() for l in L]).cpu().numpy(), 2e-5, "losses with noise")
+    reference_style_step(mb, L, opt, cag, True)
+    close(ma.flat_params().detach().cpu().numpy(), mb.flat_params().detach().cpu().numpy(), 2e-5, "parameters after one noisy step")

@@ -54,6 +54,19 @@ class FusedTrainStep:
             self._red = self._gbuf
         return self._gbuf, self._denom, self._diag, self._mom
 
+    def _noise_buffers(self, B, K, dev, off_fns):
+        """persistent (B, K) logit-offset buffers (stable addresses: CUDA-graph replays read them); refreshed with a new draw
+        on every eager call, and by step() before every replay -- never while a capture is in progress"""
+        key = (B, K, str(dev))
+        if getattr(self, "_noise_key", None) != key:
+            self._noise = [None if f is None else torch.zeros(B, K, dtype=torch.float32, device=dev) for f in off_fns]
+            self._noise_key = key
+        if not torch.cuda.is_current_stream_capturing():
+            for b, f in zip(self._noise, off_fns):
+                if b is not None:
+                    b.copy_(f(b))
+        return self._noise
+
     def _p2p_state(self, plan):
         """Symmetric allocation [gbuf parity 0 | gbuf parity 1 | flag word] mapped by every rank of the group (torch
         symmetric memory does the handle exchange), device arrays of the peers' pointers, the local exchange counter and
@@ -145,14 +158,18 @@ class FusedTrainStep:
         self._red = ps["gsum"] if p2p else gbuf
         K = plan.K
         descs = (LossDesc * _lib.MAX_STREAMS)()
-        offs = []
+        off_fns = []
         for s in range(n):
             d, off_fn = criterion_spec(self.criterions[s], K)
             descs[s] = d
-            offs.append(None)          # logit noise is only defined through the criterion call path
-            if getattr(self.criterions[s], "noise_mul", 0) not in (0, 0.0):
-                raise _lib.GaitkError("FusedTrainStep supports noise_mul == 0 (the trainers' default); use the autograd path")
+            # GCL logit noise (classification_losses.py:99-105, noise_mul != 0): drawn on the host exactly as the criterion's own
+            # call does (same RNG stream), uploaded into a persistent (B, K) buffer the kernels subtract from the logits
+            off_fns.append(off_fn if getattr(self.criterions[s], "noise_mul", 0) not in (0, 0.0) else None)
         B = plan._check_inputs(xs, win_start)
+        off_ptrs = None
+        if any(f is not None for f in off_fns):
+            bufs = self._noise_buffers(B, K, flat.device, off_fns)
+            off_ptrs = ptr_array([0 if b is None else b.data_ptr() for b in bufs])
         enabled_mask = 0b111 if enabled is None else sum(1 << s for s, e in enumerate(enabled) if e)
         task_mask = ((1 << n) - 1) if tasks is None else sum(1 << s for s, e in enumerate(tasks) if e)
         if ys_global is None and self._distributed():
@@ -168,7 +185,7 @@ class FusedTrainStep:
         ws = plan.workspace(B)
         check(lib().gaitk_step_grads(plan.handle, flat.data_ptr(), ptr_array([x.data_ptr() for x in xs]),
                                      None if win_start is None else ptr_array([0 if w is None else w.data_ptr() for w in win_start]),
-                                     ptr_array([y.data_ptr() for y in ys]), B, descs, None, denom.data_ptr(), enabled_mask,
+                                     ptr_array([y.data_ptr() for y in ys]), B, descs, off_ptrs, denom.data_ptr(), enabled_mask,
                                      task_mask, self.private_mult, self.consistency_lambda,
                                      None if logits_out is None else ptr_array([0 if l is None else l.data_ptr() for l in logits_out]),
                                      gbuf.data_ptr(), ws.data_ptr(), ws.numel(), self.dtype, st), "gaitk_step_grads")
@@ -243,6 +260,10 @@ class FusedTrainStep:
                 self._graphs[key] = (g1, g2)
             return self.stats()
         g1, g2 = g
+        if getattr(self, "_noise", None) is not None:        # a fresh GCL noise draw per step (same buffers the graph reads)
+            for b, c in zip(self._noise, self.criterions):
+                if b is not None:
+                    b.copy_(c.logit_offset(b))
         g1.replay()
         if p2p:
             self._p2p["steps"] += 1
