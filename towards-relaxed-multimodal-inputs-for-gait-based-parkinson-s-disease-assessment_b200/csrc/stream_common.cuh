@@ -29,6 +29,9 @@ constexpr int WMAX = 4;        // windows per tile (one warp each in the head ph
 // rows per chunk plane (RB) modulo 8.  Row-wise float4 accesses are conflict-free for any RB (a quarter warp reads
 // 128 contiguous bytes); the mma.sync fragment loads of the weight gradients read lanes (g, t) -> channel g, row t:
 // chunk g >> 2, word 4 t + (g & 3), so the two chunks must sit 16 banks apart: 4 RB = 16 (mod 32)  <=>  RB = 4 (mod 8).
+#ifndef GAITK_FOG_MINB
+#define GAITK_FOG_MINB 1
+#endif
 #ifndef GAITK_RB_MOD
 #define GAITK_RB_MOD 4
 #endif
@@ -172,6 +175,11 @@ struct StreamCfg {
     static constexpr int CB4 = (CB + 3) / 4;
     static constexpr int CBP = CB4 * 4;
     static constexpr int O1 = (ENC_ == ENC_INSOLE) ? H4 * 4 : CP;   // padded outputs of the first conv
+    // resident CTAs per SM the fp32 kernel is compiled for.  Measured (round 2): the narrow FoG / FBG encoders fit 168 registers
+    // without a spill (GAITK_FOG_MINB = 3: 12 warps per SM instead of 8) and run NO faster (3.78 vs 3.70 ms per step: 17.7 K warp
+    // instructions per window of runtime-geometry bookkeeping at IPC 1.4 is the limiter, not occupancy; profiles/r2_ncu_fog.txt);
+    // the WearGait encoders would spill (160 - 1140 B).  Default 1 everywhere.
+    static constexpr int MINB = (ENC_ == ENC_LINEAR_LN_RELU || ENC_ == ENC_CONV_POOL) ? GAITK_FOG_MINB : 1;
 };
 
 // shared-memory plan (offsets in floats); filled on the host, passed by value

@@ -1,18 +1,20 @@
-// stream_f32.cu -- instantiations of the fp32 (FFMA) stream kernel
+// stream_f32.cu -- instantiations of the fp32 (FFMA) stream kernel: WearGait default widths (one translation unit per family: they build in parallel)
 #include "stream_kernel.cuh"
 #include "stream_dispatch.h"
 
 namespace gaitk {
-// kernel instantiations -------------------------------------------------------------------
 template <class Cfg> static StreamKernelFn kfn() { return &stream_kernel<Cfg>; }
-
-StreamKernelFn find_kernel(const KernelKey& k) {
 #define GK_CASE(e_, ci_, kt_, h_, c_, s_, nfl_) \
     if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == 0) \
         return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_>>();
 #define GK_CASE_P(e_, ci_, kt_, h_, c_, s_, nfl_, p_) \
     if (k.enc == e_ && k.CIN == ci_ && k.KT1 == kt_ && k.H == h_ && k.C == c_ && k.S == s_ && k.NFL == nfl_ && k.PROJ == p_) \
         return kfn<StreamCfg<e_, ci_, kt_, h_, c_, s_, nfl_, p_>>();
+
+StreamKernelFn find_kernel_fog(const KernelKey& k);       // stream_f32_fog.cu
+StreamKernelFn find_kernel_wide(const KernelKey& k);      // stream_f32_wide.cu
+
+StreamKernelFn find_kernel(const KernelKey& k) {
     // SharedLatent3 (weargait_encoders.py:284-322): per-stream Linear(12 -> proj_ch=16) before the backbone
     GK_CASE_P(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4, 16)
     GK_CASE_P(ENC_INSOLE, 13, 5, 24, 12, 16, 4, 16)
@@ -21,24 +23,8 @@ StreamKernelFn find_kernel(const KernelKey& k) {
     GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 12, 16, 4)
     GK_CASE(ENC_INSOLE, 13, 5, 24, 12, 16, 4)
     GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 12, 16, 4)
-    // scaled sweep (BASELINE configs[4]: --enc_out_ch 24 --shared_out_ch 32, H = 48, NF = 256; T = 256 runs as 2-CTA clusters)
-    GK_CASE(ENC_CONV_GELU_LN, 2, 3, 0, 24, 32, 8)
-    GK_CASE(ENC_INSOLE, 13, 5, 48, 24, 32, 8)
-    GK_CASE(ENC_CONV_GELU_LN, 24, 3, 0, 24, 32, 8)
-    // FoG (configs.py:17-31) and FBG (:2-16)
-    GK_CASE(ENC_LINEAR_LN_RELU, 21, 1, 0, 6, 16, 4)
-    GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)
-    GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
-    GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
-    // trunk stages of the fusion baselines (no encoder; C = CIN): EarlyFusion3 3 x 12, CheapXAttn3 12; 2-stream twins
-    // (feature_encoder.py:346-596) early 6 + 6, late / cross-attention 6, shared latent 16
-    GK_CASE(ENC_NONE, 36, 1, 0, 36, 16, 4)
-    GK_CASE(ENC_NONE, 12, 1, 0, 12, 16, 4)
-    GK_CASE(ENC_NONE, 6, 1, 0, 6, 16, 4)
-    GK_CASE(ENC_NONE, 16, 1, 0, 16, 16, 4)
-#undef GK_CASE
-#undef GK_CASE_P
-    return nullptr;
+    if (StreamKernelFn f = find_kernel_fog(k)) return f;
+    return find_kernel_wide(k);
 }
 
 }  // namespace gaitk

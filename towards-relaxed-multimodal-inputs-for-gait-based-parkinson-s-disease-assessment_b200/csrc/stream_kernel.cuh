@@ -109,7 +109,7 @@ struct Wgrad {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs A, const SmemPlan SP) {
+__global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs A, const SmemPlan SP) {
     extern __shared__ __align__(1024) float sm[];      // one alignment for every kernel of the translation unit
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     constexpr int ENC = Cfg::ENC, CIN = Cfg::CIN, CI4 = Cfg::CI4, KT1 = Cfg::KT1, H = Cfg::H, H4 = Cfg::H4;
