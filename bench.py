@@ -583,7 +583,9 @@ def run_gpu(args):
                        "l2": "inputs larger than L2 (2 rotating batches)" if l2_flush is None else "256 MiB L2 flush between steps",
                        "timing": "CUDA events on the launching stream, barrier+sync both sides, max over ranks",
                        "cuda_graph": bool(args.graph),
-                       "exchange": "none (1 GPU)" if world == 1 else ("gaitk_p2p_allreduce over NVLink peer memory, fused into the step graph" if args.p2p else "NCCL all_reduce of gbuf")},
+                       "exchange": "none (1 GPU)" if world == 1 else ("gaitk_p2p_allreduce over NVLink peer memory, inside the step's single CUDA graph"
+                                                                    if (args.p2p and getattr(step, "_p2p", None) is not None) else
+                                                                    "NCCL all_reduce of gbuf between two CUDA graphs" + (" (peer-memory exchange unavailable: fell back)" if args.p2p else ""))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host batch of (B,64,2)+(B,64,13)+(B,64,24) fp32 + labels copied every step (copy of batch i+1 "
                             "overlaps step i), result (loss[3], correct[3]) read back every step"},
@@ -613,8 +615,9 @@ def main():
                     "--impl reference, shrunk only if the run would exceed a few minutes; 4096 for the gaitk arm's cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the B = 64 .. 32768 sweep of the fused step")
-    ap.add_argument("--p2p", type=int, default=0, help="1 = data-parallel exchange by the peer-memory all-reduce kernel gaitk_p2p_allreduce "
-                    "(one graph per step); 0 = NCCL all_reduce between two graphs (default: measured 4%% faster at N=2)")
+    ap.add_argument("--p2p", type=int, default=1, help="1 (default) = data-parallel exchange by the in-tree peer-memory all-reduce kernel "
+                    "gaitk_p2p_allreduce inside the step's single CUDA graph (round 2, 8 GPUs: 1.098 vs 1.110 ms per step with NCCL; falls back "
+                    "to NCCL when torch symmetric memory is unavailable, and says so in config.exchange); 0 = NCCL all_reduce between two graphs")
     ap.add_argument("--graph", type=int, default=1, help="replay the step (kernels + the NCCL all-reduce when data-parallel) as one CUDA graph")
     ap.add_argument("--workload", default="weargait", choices=["weargait", "weargait_async", "weargait_relaxed", "fog", "scaled"],
                     help="default = BASELINE.json configs[1]; the others are extra report lines")
