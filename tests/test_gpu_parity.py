@@ -1293,3 +1293,26 @@ def test_fused_step_with_gcl_noise_matches_the_criterion_path(gk):
     close(loss_a.cpu().numpy(), torch.stack([l.detach() for l in L]).cpu().numpy(), 2e-5, "losses with noise")
     reference_style_step(mb, L, opt, cag, True)
     close(ma.flat_params().detach().cpu().numpy(), mb.flat_params().detach().cpu().numpy(), 2e-5, "parameters after one noisy step")
+
+
+def test_graph_replay_with_fresh_tensors_every_step(gk):
+    """The CUDA-graph path must not re-capture when the trainer hands over NEW tensors every step (the normal case): small
+    inputs are staged into static buffers, so the graph cache holds one entry per shape and the result equals the eager path."""
+    torch.manual_seed(2)
+    def build(graph):
+        torch.manual_seed(9)
+        m = gk.WearGaitThreeModal(synchronized=True).cuda()
+        crit = [gk.GCLLoss(cls_num_list=[40, 60], m=0.2, s=25.0, noise_mul=0.0) for _ in range(3)]
+        return m, gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, use_graph=graph)
+    ma, sa = build(True); mb, sb = build(False)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(12):
+        B = 40 if it % 3 else 24                                      # two shapes
+        xs = [torch.rand(B, 64, 2, device="cuda", generator=g), torch.randn(B, 64, 13, device="cuda", generator=g),
+              torch.randn(B, 64, 24, device="cuda", generator=g)]     # fresh tensors, fresh addresses
+        y = torch.randint(0, 2, (B,), device="cuda", generator=g); y[0], y[1] = 0, 1
+        la, _ = sa.step([x.clone() for x in xs], [y.clone()] * 3)
+        lb, _ = sb.step(xs, [y, y, y])
+        assert torch.equal(la, lb), (it, la, lb)
+    assert torch.equal(ma.flat_params(), mb.flat_params())
+    assert len(sa._graphs) == 2, len(sa._graphs)                    # one graph per batch shape, not one per step

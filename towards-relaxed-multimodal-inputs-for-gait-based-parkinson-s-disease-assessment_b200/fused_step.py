@@ -54,6 +54,30 @@ class FusedTrainStep:
             self._red = self._gbuf
         return self._gbuf, self._denom, self._diag, self._mom
 
+    STAGE_LIMIT = 16 << 20            # bytes per tensor: larger inputs are not copied into staging buffers
+
+    def _static(self, name, seq):
+        """inputs -> address-stable tensors: tensors of at most STAGE_LIMIT bytes are copied into per-(position, shape) staging
+        buffers (aliases among the inputs, e.g. ys = [y, y, y], stay aliases: the label histogram is shared by address)"""
+        if seq is None:
+            return None
+        store = self.__dict__.setdefault("_static_in", {})
+        out, first = [], {}
+        for i, t in enumerate(seq):
+            if t is None or not t.is_cuda or t.numel() * t.element_size() > self.STAGE_LIMIT:
+                out.append(t); continue
+            j = first.setdefault(id(t), i)
+            if j != i:
+                out.append(out[j]); continue
+            key = (name, i, tuple(t.shape), t.dtype, t.device)
+            buf = store.get(key)
+            if buf is None:
+                buf = store[key] = torch.empty_like(t, memory_format=torch.contiguous_format)
+            if buf.data_ptr() != t.data_ptr():
+                buf.copy_(t)
+            out.append(buf)
+        return out
+
     def _noise_buffers(self, B, K, dev, off_fns):
         """persistent (B, K) logit-offset buffers (stable addresses: CUDA-graph replays read them); refreshed with a new draw
         on every eager call, and by step() before every replay -- never while a capture is in progress"""
@@ -219,6 +243,14 @@ class FusedTrainStep:
         ws = kw.get("win_start")
         if hasattr(self.model, "set_window") and (ws is None or ws[0] is None):
             self.model.set_window(xs[0].shape[1])
+        # A captured graph bakes buffer ADDRESSES in.  Trainers hand over fresh tensors every step, so small inputs (batches up
+        # to a few thousand windows, index / label vectors) are first copied into static per-shape staging buffers: the graph is
+        # then keyed by shapes and options only and is captured once.  Large inputs (resident frame stores, big dense batches) keep
+        # their own addresses; if those keep changing the step stops re-capturing and runs eagerly (see below).
+        xs = self._static("x", xs); ys = self._static("y", ys)
+        for name in ("ys_global", "win_start"):
+            if kw.get(name) is not None:
+                kw[name] = self._static(name, kw[name])
         def ptrs(seq):
             return None if seq is None else tuple(0 if t is None else t.data_ptr() for t in seq)
         dist_mode = self._distributed()
@@ -234,6 +266,10 @@ class FusedTrainStep:
                self.max_norm, self.private_mult, self.solver, self.consistency_lambda, self.dtype, dist_mode, p2p, par)
         g = self._graphs.get(key)
         if g is None:
+            # fresh (unstaged, large) tensors on every call would mean one capture per step: after 8 misses in a row stay eager
+            self._miss_run = getattr(self, "_miss_run", 0) + 1
+            if self._miss_run > 8:
+                return self._step_impl(xs, ys, **kw)
             self._step_impl(xs, ys, **kw)                      # this call's step, eagerly (also allocates buffers / workspace)
             torch.cuda.synchronize()
             # capture records the launch sequence without executing it; later calls replay it
@@ -260,6 +296,7 @@ class FusedTrainStep:
                 self._graphs[key] = (g1, g2)
             return self.stats()
         g1, g2 = g
+        self._miss_run = 0
         if getattr(self, "_noise", None) is not None:        # a fresh GCL noise draw per step (same buffers the graph reads)
             for b, c in zip(self._noise, self.criterions):
                 if b is not None:
