@@ -243,14 +243,12 @@ class FusedTrainStep:
         ws = kw.get("win_start")
         if hasattr(self.model, "set_window") and (ws is None or ws[0] is None):
             self.model.set_window(xs[0].shape[1])
-        # A captured graph bakes buffer ADDRESSES in.  Trainers hand over fresh tensors every step, so small inputs (batches up
-        # to a few thousand windows, index / label vectors) are first copied into static per-shape staging buffers: the graph is
-        # then keyed by shapes and options only and is captured once.  Large inputs (resident frame stores, big dense batches) keep
-        # their own addresses; if those keep changing the step stops re-capturing and runs eagerly (see below).
-        xs = self._static("x", xs); ys = self._static("y", ys)
-        for name in ("ys_global", "win_start"):
-            if kw.get(name) is not None:
-                kw[name] = self._static(name, kw[name])
+        # A captured graph bakes buffer ADDRESSES in.  (1) Tensors the caller reuses (resident stores, rotating device batches) are
+        # recognised by address: the second time a set of addresses shows up it gets its own graph, replayed without any copy.
+        # (2) Trainers hand over fresh tensors every step: on the first sighting of a set of addresses the small inputs (batches up
+        # to a few thousand windows, index / label vectors) are copied into static per-shape staging buffers, so the graph is keyed
+        # by shapes and options only and is captured once.  (3) Large fresh tensors cannot be staged cheaply: after 8 captures in a
+        # row that were never replayed the step stays eager (see below).
         def ptrs(seq):
             return None if seq is None else tuple(0 if t is None else t.data_ptr() for t in seq)
         dist_mode = self._distributed()
@@ -260,10 +258,26 @@ class FusedTrainStep:
         # (class weights after a DRW update, margins, scale, NaN flag) and every scalar option of the step
         K = self.model.plan().K
         desc_bytes = b"".join(bytes(criterion_spec(c, K)[0]) for c in self.criterions)
-        key = (ptrs(xs), ptrs(ys), ptrs(kw.get("ys_global")), ptrs(kw.get("win_start")), tuple(kw.get("enabled") or ()),
-               tuple(kw.get("tasks") or ()), kw.get("update", True), xs[0].shape[0] if kw.get("win_start") is None else kw["win_start"][0].numel(),
-               desc_bytes, self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c,
-               self.max_norm, self.private_mult, self.solver, self.consistency_lambda, self.dtype, dist_mode, p2p, par)
+        def make_key(xs_, ys_, kw_):
+            return (ptrs(xs_), ptrs(ys_), ptrs(kw_.get("ys_global")), ptrs(kw_.get("win_start")), tuple(kw_.get("enabled") or ()),
+                    tuple(kw_.get("tasks") or ()), kw_.get("update", True),
+                    xs_[0].shape[0] if kw_.get("win_start") is None else kw_["win_start"][0].numel(),
+                    desc_bytes, self.model.flat_params().data_ptr(), self.lr, self.momentum, self.weight_decay, self.cagrad_c,
+                    self.max_norm, self.private_mult, self.solver, self.consistency_lambda, self.dtype, dist_mode, p2p, par)
+        key = make_key(xs, ys, kw)
+        if key not in self._graphs:
+            seen = self.__dict__.setdefault("_raw_seen", {})
+            if len(seen) > 512:
+                seen.clear()
+            first_sighting = key not in seen
+            seen[key] = True
+            if first_sighting:
+                xs = self._static("x", xs); ys = self._static("y", ys)
+                kw = dict(kw)
+                for name in ("ys_global", "win_start"):
+                    if kw.get(name) is not None:
+                        kw[name] = self._static(name, kw[name])
+                key = make_key(xs, ys, kw)
         g = self._graphs.get(key)
         if g is None:
             # fresh (unstaged, large) tensors on every call would mean one capture per step: after 8 misses in a row stay eager
