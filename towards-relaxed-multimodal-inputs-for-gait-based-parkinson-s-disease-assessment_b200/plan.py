@@ -76,6 +76,9 @@ class Plan:
     def workspace(self, B: int, extra_floats: int = 0) -> torch.Tensor:
         need = self.workspace_bytes(B) + 4 * extra_floats + 512
         if self._ws is None or self._ws.numel() < need:
+            # grow-only, and every buffer ever handed out stays alive: captured CUDA graphs keep the ADDRESS of the workspace
+            # they were captured with (a smaller batch captured earlier must not find its workspace freed and reused)
+            self.__dict__.setdefault("_ws_keep", []).append(self._ws)
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
