@@ -203,7 +203,10 @@ GAITK_HD inline int slsqp_simplex(const Quad3& q, int n, double* x, int* iters, 
             h1 = h3b;
             for (int i = 0; i < n; ++i) u[i] = h4 * u[i] + (1.0 - h4) * v[i];
         }
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) B[i][j] += u[i] * u[j] / h1 - v[i] * v[j] / h2;
+        // two reciprocals instead of 2 n^2 divisions: an fp64 division is a ~1 K-clock dependent chain for the single warp that
+        // runs the solve on the device (the whole CTA waits for it)
+        const double r1 = 1.0 / h1, r2 = 1.0 / h2;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) B[i][j] += u[i] * u[j] * r1 - v[i] * v[j] * r2;
         for (int i = 0; i < n; ++i) g[i] = gn[i];
     }
 }
@@ -265,7 +268,7 @@ GAITK_HD inline int cagrad_weights(const float* a, int n, float alpha, int solve
     const float g0 = sqrtf((float)mean + 1e-8f);
     // the reference evaluates (alpha * g0_norm + 1e-8) as a float32 tensor expression, then .item()
     q.c = (double)(alpha * g0 + 1e-8f);
-    for (int i = 0; i < n; ++i) { q.Ab[i] = 0; for (int j = 0; j < n; ++j) q.Ab[i] += q.A[i][j] / n; }
+    for (int i = 0; i < n; ++i) { double rs = 0; for (int j = 0; j < n; ++j) rs += q.A[i][j]; q.Ab[i] = rs / n; }      // A b, b = 1/n
     *c_out = q.c;
     int mode = 0;
     if (solver == 1) exact_simplex(q, n, w, iters); else mode = slsqp_simplex(q, n, w, iters);

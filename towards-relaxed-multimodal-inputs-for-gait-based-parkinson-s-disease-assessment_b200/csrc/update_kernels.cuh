@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
         if (plain_mean) { for (int i = 0; i < n; ++i) w[i] = 1.0 / n; }
         else cagrad_weights(&a[0][0], n, U.alpha, U.solver, w, &c, &iters);
         q.c = c;
-        for (int i = 0; i < n; ++i) { q.Ab[i] = 0; for (int j = 0; j < n; ++j) q.Ab[i] += q.A[i][j] / n; }
+        for (int i = 0; i < n; ++i) { double rs = 0; for (int j = 0; j < n; ++j) rs += q.A[i][j]; q.Ab[i] = rs / n; }
         // gw = G w with w cast to fp32 as torch.Tensor(w_cpu) does (:719)
         for (int i = 0; i < n; ++i) w[i] = (double)(float)w[i];
         double gw2 = 0;
