@@ -53,162 +53,256 @@ GAITK_HD inline void cg_clip01(const double* x, double* y, int n) {
     for (int i = 0; i < n; ++i) y[i] = x[i] < 0 ? 0.0 : (x[i] > 1 ? 1.0 : x[i]);
 }
 
-// Gaussian elimination with partial pivoting, m <= 4 (one reciprocal per pivot).  Returns false when singular.
-GAITK_HD inline bool cg_solve_small(double K[4][4], double* r, int m) {
-    double inv[4];
-    for (int col = 0; col < m; ++col) {
+// ---- everything below is templated on the number of tasks N (2 or 3) and written with STATIC array indices only: on the
+// device one warp runs the solve while the whole update CTA waits for it, and the first version (runtime n, index lists,
+// a run-time-sized elimination) kept its small arrays in local memory: ~31 K clocks per SLSQP iteration, 48 - 140 us per
+// step (scratch/update_timing.py).  With static indices everything lives in registers.
+template <int N> GAITK_HD inline double cg_obj_t(const Quad3& q, const double* w) {
+    double lin = 0, quad = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        lin += w[i] * q.Ab[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j) quad += w[i] * q.A[i][j] * w[j];
+    }
+    return lin + q.c * sqrt(quad + 1e-8);
+}
+template <int N> GAITK_HD inline void cg_grad_t(const Quad3& q, const double* w, double* g) {
+    double Aw[N], quad = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        Aw[i] = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) Aw[i] += q.A[i][j] * w[j];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) quad += w[i] * Aw[i];
+    const double r = q.c / sqrt(quad + 1e-8);
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = q.Ab[i] + r * Aw[i];
+}
+
+// Gaussian elimination with partial pivoting on an M x M system (M <= 4), rows swapped by selects.  false when singular.
+template <int M> GAITK_HD inline bool cg_solve_static(double (&K)[M][M], double (&r)[M]) {
+    double inv[M];
+#pragma unroll
+    for (int col = 0; col < M; ++col) {
         int piv = col; double best = fabs(K[col][col]);
-        for (int i = col + 1; i < m; ++i) if (fabs(K[i][col]) > best) { best = fabs(K[i][col]); piv = i; }
+#pragma unroll
+        for (int i = col + 1; i < M; ++i) { const double a = fabs(K[i][col]); if (a > best) { best = a; piv = i; } }
         if (!(best > 1e-300)) return false;
-        if (piv != col) {
-            for (int j = 0; j < m; ++j) { const double t = K[col][j]; K[col][j] = K[piv][j]; K[piv][j] = t; }
-            const double t = r[col]; r[col] = r[piv]; r[piv] = t;
+#pragma unroll
+        for (int i = col + 1; i < M; ++i) {
+            const bool sw = piv == i;
+#pragma unroll
+            for (int j = 0; j < M; ++j) { const double a = K[col][j], b = K[i][j]; K[col][j] = sw ? b : a; K[i][j] = sw ? a : b; }
+            const double a = r[col], b = r[i]; r[col] = sw ? b : a; r[i] = sw ? a : b;
         }
         inv[col] = 1.0 / K[col][col];
-        for (int i = col + 1; i < m; ++i) {
+#pragma unroll
+        for (int i = col + 1; i < M; ++i) {
             const double f = K[i][col] * inv[col];
-            if (f != 0.0) { for (int j = col; j < m; ++j) K[i][j] -= f * K[col][j]; r[i] -= f * r[col]; }
+#pragma unroll
+            for (int j = col; j < M; ++j) K[i][j] -= f * K[col][j];
+            r[i] -= f * r[col];
         }
     }
-    for (int i = m - 1; i >= 0; --i) {
-        double s = r[i];
-        for (int j = i + 1; j < m; ++j) s -= K[i][j] * r[j];
-        r[i] = s * inv[i];
+#pragma unroll
+    for (int i = M - 1; i >= 0; --i) {
+        double acc = r[i];
+#pragma unroll
+        for (int j = i + 1; j < M; ++j) acc -= K[i][j] * r[j];
+        r[i] = acc * inv[i];
     }
     return true;
 }
 
-// min 1/2 s^T B s + g^T s   s.t.  sum s = c0,  lo <= s <= hi     (B positive definite, n <= 3)
-// One bound-activity pattern `comb` (base-3 digits: 0 free, 1 at lower, 2 at upper): solve the equality-
-// constrained sub-problem and check the KKT conditions.  Returns true with (s, val) when it is THE solution.
-GAITK_HD inline bool cg_qp_combo(const double B[3][3], const double* g, const double* lo, const double* hi, double c0, int n,
-                                 int comb, double* s, double* val_out) {
-    int st[3]; { int t = comb; for (int i = n - 1; i >= 0; --i) { st[i] = t % 3; t /= 3; } }
-    int F[3], nf = 0; double fixed_sum = 0;
-    for (int i = 0; i < 3; ++i) s[i] = 0.0;
-    for (int i = 0; i < n; ++i) { if (st[i] == 0) F[nf++] = i; else { s[i] = st[i] == 1 ? lo[i] : hi[i]; fixed_sum += s[i]; } }
+// min 1/2 s^T B s + g^T s   s.t.  sum s = c0,  lo <= s <= hi     (B positive definite)
+// One bound-activity pattern `comb` (base-3 digits: 0 free, 1 at lower, 2 at upper): solve the equality-constrained
+// sub-problem and check the KKT conditions.  Returns true with (s, val) when it is THE solution.  The sub-problem is ONE
+// (N + 1) x (N + 1) system for every pattern: a free variable contributes its stationarity row  B_i. s + lambda = -g_i,
+// a fixed variable the identity row  s_i = bound,  the last row the constraint over the free variables.
+template <int N>
+GAITK_HD inline bool cg_qp_combo_t(const double (&B)[3][3], const double* g, const double* lo, const double* hi, double c0,
+                                   int comb, double* s, double* val_out) {
+    int st[N];
+    { int t = comb;
+#pragma unroll
+      for (int i = N - 1; i >= 0; --i) { st[i] = t % 3; t /= 3; } }
+    int nf = 0; double fixed_sum = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool fr = st[i] == 0;
+        nf += fr ? 1 : 0;
+        s[i] = fr ? 0.0 : (st[i] == 1 ? lo[i] : hi[i]);
+        fixed_sum += s[i];
+    }
     const double rhs_sum = c0 - fixed_sum;
-    double lam = 0; bool has_lam = false;
-    if (nf == 0) {
+    double lam = 0; const bool has_lam = nf > 0;
+    if (!has_lam) {
         if (fabs(rhs_sum) > 1e-12) return false;
     } else {
-        double K[4][4]; double r[4];
-        for (int a = 0; a < nf; ++a) {
-            for (int b = 0; b < nf; ++b) K[a][b] = B[F[a]][F[b]];
-            K[a][nf] = 1.0; K[nf][a] = 1.0;
-            double acc = -g[F[a]];
-            for (int j = 0; j < n; ++j) if (st[j] != 0) acc -= B[F[a]][j] * s[j];
-            r[a] = acc;
+        double K[N + 1][N + 1], r[N + 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool fr = st[i] == 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) K[i][j] = fr ? B[i][j] : (i == j ? 1.0 : 0.0);
+            K[i][N] = fr ? 1.0 : 0.0;
+            r[i] = fr ? -g[i] : s[i];
+            K[N][i] = fr ? 1.0 : 0.0;
         }
-        K[nf][nf] = 0.0; r[nf] = rhs_sum;
-        if (!cg_solve_small(K, r, nf + 1)) return false;
-        for (int a = 0; a < nf; ++a) s[F[a]] = r[a];
-        lam = r[nf]; has_lam = true;
+        K[N][N] = 0.0; r[N] = rhs_sum;
+        if (!cg_solve_static<N + 1>(K, r)) return false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i] = st[i] == 0 ? r[i] : s[i];
+        lam = r[N];
     }
-    for (int a = 0; a < nf; ++a) { const int i = F[a]; if (s[i] < lo[i] - 1e-13 || s[i] > hi[i] + 1e-13) return false; }
-    double grad[3];
-    for (int i = 0; i < n; ++i) { grad[i] = g[i]; for (int j = 0; j < n; ++j) grad[i] += B[i][j] * s[j]; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) if (st[i] == 0 && (s[i] < lo[i] - 1e-13 || s[i] > hi[i] + 1e-13)) return false;
+    double grad[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        grad[i] = g[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j) grad[i] += B[i][j] * s[j];
+    }
     if (!has_lam) {
         double lo_l = -INFINITY, hi_l = INFINITY;
-        for (int i = 0; i < n; ++i) { if (st[i] == 1) lo_l = fmax(lo_l, -grad[i]); else hi_l = fmin(hi_l, -grad[i]); }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { if (st[i] == 1) lo_l = fmax(lo_l, -grad[i]); else hi_l = fmin(hi_l, -grad[i]); }
         if (lo_l > hi_l + 1e-12) return false;
     } else {
-        for (int i = 0; i < n; ++i) {
-            if (st[i] == 0) continue;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
             const double m = grad[i] + lam, t = 1e-12 * fmax(1.0, fabs(grad[i]));
             if (st[i] == 1 && m < -t) return false;
             if (st[i] == 2 && m > t) return false;
         }
     }
     double val = 0;
-    for (int i = 0; i < n; ++i) { val += g[i] * s[i]; for (int j = 0; j < n; ++j) val += 0.5 * s[i] * B[i][j] * s[j]; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        val += g[i] * s[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j) val += 0.5 * s[i] * B[i][j] * s[j];
+    }
     *val_out = val;
     return true;
 }
 
-GAITK_HD inline void cg_qp(const double B[3][3], const double* g, const double* lo, const double* hi, double c0, int n, double* s_out) {
-    int ncomb = 1; for (int i = 0; i < n; ++i) ncomb *= 3;
+template <int N>
+GAITK_HD inline void cg_qp_t(const double (&B)[3][3], const double* g, const double* lo, const double* hi, double c0, double* s_out) {
+    constexpr int ncomb = N == 2 ? 9 : 27;
 #if defined(__CUDA_ARCH__)
     // device: the <= 27 patterns are evaluated by the lanes of the (fully active) calling warp
     const int lane = threadIdx.x & 31;
-    double s[3] = {0, 0, 0}, val = INFINITY;
-    const bool ok = lane < ncomb && cg_qp_combo(B, g, lo, hi, c0, n, lane, s, &val);
+    double s[N], val = INFINITY;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] = 0.0;
+    const bool ok = lane < ncomb && cg_qp_combo_t<N>(B, g, lo, hi, c0, lane, s, &val);
     if (!ok) val = INFINITY;
     double best = val; int who = lane;
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int ow = __shfl_xor_sync(0xffffffffu, who, o);
         if (ov < best || (ov == best && ow < who)) { best = ov; who = ow; }
     }
-    for (int i = 0; i < 3; ++i) { const double v = __shfl_sync(0xffffffffu, s[i], who); s_out[i] = (best < INFINITY && i < n) ? v : 0.0; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double v = __shfl_sync(0xffffffffu, s[i], who); s_out[i] = best < INFINITY ? v : 0.0; }
 #else
     double best_val = 0; bool have = false;
-    for (int i = 0; i < 3; ++i) s_out[i] = 0.0;
+    for (int i = 0; i < N; ++i) s_out[i] = 0.0;
     for (int comb = 0; comb < ncomb; ++comb) {
-        double s[3], val;
-        if (!cg_qp_combo(B, g, lo, hi, c0, n, comb, s, &val)) continue;
-        if (!have || val < best_val - 1e-15) { have = true; best_val = val; for (int i = 0; i < n; ++i) s_out[i] = s[i]; }
+        double s[N], val;
+        if (!cg_qp_combo_t<N>(B, g, lo, hi, c0, comb, s, &val)) continue;
+        if (!have || val < best_val - 1e-15) { have = true; best_val = val; for (int i = 0; i < N; ++i) s_out[i] = s[i]; }
     }
 #endif
 }
 
 // SLSQP iteration from x = 1/n.  Returns the exit mode (0 converged, 8 positive directional derivative,
 // 9 iteration limit); *iters = major iterations.
-GAITK_HD inline int slsqp_simplex(const Quad3& q, int n, double* x, int* iters, double acc = 1e-6, int itermax = 100) {
-    for (int i = 0; i < n; ++i) x[i] = 1.0 / n;
-    if (n == 1) { x[0] = 1.0; *iters = 0; return 0; }
+template <int N>
+GAITK_HD inline int slsqp_simplex_t(const Quad3& q, double* x, int* iters, double acc = 1e-6, int itermax = 100) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 1.0 / N;
     double B[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    double xc[3], g[3], s[3], x0[3], gn[3], u[3], v[3], lo[3], hi[3];
-    cg_clip01(x, xc, n);
-    double fx = cg_obj(q, xc, n); cg_grad(q, xc, n, g);
+    double xc[N], g[N], s[N], x0[N], gn[N], u[N], v[N], lo[N], hi[N];
+    cg_clip01(x, xc, N);
+    double fx = cg_obj_t<N>(q, xc); cg_grad_t<N>(q, xc, g);
     const double tol = 10.0 * acc;
     int ireset = 1, it = 0;
     for (;;) {
         ++it;
         if (it > itermax) { *iters = it; return 9; }
-        double sx = 0; for (int i = 0; i < n; ++i) { lo[i] = 0.0 - x[i]; hi[i] = 1.0 - x[i]; sx += x[i]; }
-        cg_qp(B, g, lo, hi, 1.0 - sx, n, s);
+        double sx = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { lo[i] = 0.0 - x[i]; hi[i] = 1.0 - x[i]; sx += x[i]; }
+        cg_qp_t<N>(B, g, lo, hi, 1.0 - sx, s);
         const double f0 = fx;
         double gs = 0, snorm = 0;
-        for (int i = 0; i < n; ++i) { x0[i] = x[i]; gs += g[i] * s[i]; snorm += s[i] * s[i]; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { x0[i] = x[i]; gs += g[i] * s[i]; snorm += s[i] * s[i]; }
         snorm = sqrt(snorm);
         if (fabs(gs) < acc && fabs(1.0 - sx) < acc) { *iters = it; return 0; }
         double h3 = gs;
         if (h3 >= 0.0) {
             ++ireset;
             if (ireset > 5) { *iters = it; return (fabs(fx - f0) < tol || snorm < tol) ? 0 : 8; }
-            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) B[i][j] = i == j ? 1.0 : 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) B[i][j] = i == j ? 1.0 : 0.0;
             continue;
         }
         int line = 0; double alpha = 1.0;
         for (;;) {
             ++line;
             h3 *= alpha;
-            for (int i = 0; i < n; ++i) { s[i] *= alpha; x[i] = x0[i] + s[i]; }
-            cg_clip01(x, xc, n);
-            fx = cg_obj(q, xc, n);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { s[i] *= alpha; x[i] = x0[i] + s[i]; }
+            cg_clip01(x, xc, N);
+            fx = cg_obj_t<N>(q, xc);
             const double h1 = fx - f0;
             if (h1 <= h3 / 10.0 || line > 10) break;
             alpha = fmax(h3 / (2.0 * (h3 - h1)), 0.1);
         }
-        snorm = 0; for (int i = 0; i < n; ++i) snorm += s[i] * s[i];
+        snorm = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) snorm += s[i] * s[i];
         snorm = sqrt(snorm);
         if (fabs(fx - f0) < acc || snorm < acc) { *iters = it; return 0; }
-        cg_grad(q, xc, n, gn);
+        cg_grad_t<N>(q, xc, gn);
         double h1 = 0, h2 = 0;
-        for (int i = 0; i < n; ++i) { u[i] = gn[i] - g[i]; v[i] = 0; for (int j = 0; j < n; ++j) v[i] += B[i][j] * s[j]; }
-        for (int i = 0; i < n; ++i) { h1 += s[i] * u[i]; h2 += s[i] * v[i]; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            u[i] = gn[i] - g[i]; v[i] = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) v[i] += B[i][j] * s[j];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { h1 += s[i] * u[i]; h2 += s[i] * v[i]; }
         const double h3b = 0.2 * h2;
         if (h1 < h3b) {
             const double h4 = (h2 - h3b) / (h2 - h1);
             h1 = h3b;
-            for (int i = 0; i < n; ++i) u[i] = h4 * u[i] + (1.0 - h4) * v[i];
+#pragma unroll
+            for (int i = 0; i < N; ++i) u[i] = h4 * u[i] + (1.0 - h4) * v[i];
         }
-        // two reciprocals instead of 2 n^2 divisions: an fp64 division is a ~1 K-clock dependent chain for the single warp that
-        // runs the solve on the device (the whole CTA waits for it)
+        // two reciprocals instead of 2 n^2 divisions (an fp64 division is a long dependent chain for the one warp that solves)
         const double r1 = 1.0 / h1, r2 = 1.0 / h2;
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) B[i][j] += u[i] * u[j] * r1 - v[i] * v[j] * r2;
-        for (int i = 0; i < n; ++i) g[i] = gn[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) B[i][j] += u[i] * u[j] * r1 - v[i] * v[j] * r2;
+#pragma unroll
+        for (int i = 0; i < N; ++i) g[i] = gn[i];
     }
+}
+GAITK_HD inline int slsqp_simplex(const Quad3& q, int n, double* x, int* iters) {
+    if (n == 1) { x[0] = 1.0; *iters = 0; return 0; }
+    return n == 2 ? slsqp_simplex_t<2>(q, x, iters) : slsqp_simplex_t<3>(q, x, iters);
 }
 
 // ---- exact optimum (solver mode 1) ---------------------------------------------------------------------

@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
     __shared__ int tl[MAXT];
     __shared__ int nt_s;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wrp = tid >> 5;
+#ifdef GAITK_UPDATE_TIMING          // phase clocks -> diag[17..19] (scratch/update_timing.py)
+    const long long tk0 = clock64(); long long tk1 = 0, tk2 = 0;
+#endif
     const float* G = U.gbuf; const float* PG = U.gbuf + (size_t)MAXT * U.P;
     // a failed data-parallel exchange (a peer never published its gradients) must not be applied: gbuf is incomplete
     if (U.check_exchange && U.diag && U.diag[DIAG_EXCHANGE] < 0.f) return;
@@ -123,6 +126,9 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
     const long long total = U.NP > 0 ? U.NP : (U.nparams ? U.ps[0].numel : 0);      // gaitk_cagrad: one pseudo-parameter
     const int passes = (int)((total + (long long)nth * UPD_EPT - 1) / ((long long)nth * UPD_EPT));
     __syncthreads();
+#ifdef GAITK_UPDATE_TIMING
+    tk1 = clock64();
+#endif
     if (tid < 32) {
         // warp 0 runs the solve (all lanes redundantly; the QP enumeration is lane-parallel)
         double g6[6];
@@ -187,6 +193,9 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
             if (U.do_sgd && s.has_grad) { pv[j] = U.params[e]; mv[j] = U.momentum[e]; }
         }
         if (pass == 0) __syncthreads();                    // coefficients from the solve
+#ifdef GAITK_UPDATE_TIMING
+        if (pass == 0) tk2 = clock64();
+#endif
         const float k0 = (float)coef[0], k1 = (float)coef[1], k2 = (float)coef[2];
 #pragma unroll
         for (int j = 0; j < UPD_EPT; ++j) {
@@ -204,6 +213,9 @@ __global__ void __launch_bounds__(UPD_THREADS) cagrad_update_kernel(const Update
             }
         }
     }
+#ifdef GAITK_UPDATE_TIMING
+    if (tid == 0 && U.diag) { U.diag[17] = (float)(tk1 - tk0); U.diag[18] = (float)(tk2 - tk1); U.diag[19] = (float)(clock64() - tk2); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
