@@ -97,7 +97,8 @@ struct WsLayout {
     static constexpr int O_F32 = O_ID + 4096;                            // b1[32] b2[16] lng[16] lnb[16] bb[16] hw[4*128] hb[4]
     static constexpr int F_B1 = 0, F_B2 = 32, F_LNG = 48, F_LNB = 64, F_BB = 80, F_HW = 96, F_HB = 96 + 512, F_END = 96 + 512 + 8;
     static constexpr int O_BAR = O_F32 + F_END * 4;                      // per group 16 mbarriers
-    static constexpr int O_END = O_BAR + G * 16 * 8 + 16;
+    static constexpr int O_Q = O_BAR + G * 16 * 8 + 16;                  // tile queue: [next slot][tile id of group g, parity p]
+    static constexpr int O_END = O_Q + 16 + G * 8;
     // M = 128 MN-major operands read 16 planes from their start: keep that inside the allocation
     static constexpr int SPAN = (G - 1) * GRP + (P_F + NC8 + 17) * PL;
     static constexpr int TOTAL = ((O_END > SPAN ? O_END : SPAN) + 127) / 128 * 128;
@@ -357,6 +358,9 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
 #endif
     using L = WsLayout<Cfg, G, SL>;
     constexpr int RG = L::RG;
+#ifdef GAITK_WS_TIMING
+    const long long wt_k0 = clock64();
+#endif
     constexpr int CIN = L::CIN, KT1 = L::KT1, H = L::H, C = L::C, HALO = L::HALO, PL = L::PL;
     constexpr bool INS = L::INS;
     constexpr int NX8 = L::NX8, NX8E = L::NX8E, NH8 = L::NH8, NH8E = L::NH8E, NC8 = L::NC8, NS8 = L::NS8, N1 = L::N1, O1 = L::O1, NH = L::NH;
@@ -373,6 +377,12 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
     auto bar_free = [&](int g) { return bars + g * 16 + 9; };
     auto bar_wfree = [&](int g) { return bars + g * 16 + 10; };
     auto bar_ld = [&](int g) { return bars + g * 16 + 11; };
+    // Work distribution inside the CTA: the CTA owns the tiles (it * gridDim + blockIdx) * G + q, q < G, it < nit, as a QUEUE of
+    // slots j = it * G + q.  A group's service warp takes the next slot when it starts the load of the group's next tile and
+    // publishes the tile id next to the load barrier; the row warps read it there.  (Static ownership -- slot q belongs to group q --
+    // let the groups the warp arbiter favours run ~9 tiles ahead: the last quarter of every kernel ran with one or two groups.)
+    int* q_next = reinterpret_cast<int*>(smw + L::O_Q);
+    auto tile_slot = [&](int g, uint32_t par) { return reinterpret_cast<volatile int*>(smw + L::O_Q + 16) + g * 2 + par; };
 
     // ------------------------------------------------------------------------------------------ one-time setup
     for (int i = tid; i < L::TOTAL / 16; i += L::NTH) reinterpret_cast<uint4*>(smw)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -439,9 +449,11 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
     const int ntiles = (A.B + 1) / 2;
     const int per_it = (int)gridDim.x * G;
     const int nit = (ntiles + per_it - 1) / per_it;
-    auto tile_of = [&](int it, int g) { return (it * (int)gridDim.x + (int)blockIdx.x) * G + g; };
     constexpr int ROW_WARPS = 4 * RG;
 
+#ifdef GAITK_WS_TIMING
+    const long long wt_k1 = clock64();
+#endif
     if (warp >= ROW_WARPS) {                               // the LAST warpgroup: the hardware arbiter prefers high warp ids, so an
                                                            // MMA / TMA issue never queues behind the row warps' epilogue instructions
         // ====================================================================================== service warpgroup
@@ -460,20 +472,30 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             const uint32_t gb = sbase + g * L::GRP, acc = tmem + g * 32;
             uint8_t* gbp = smw + g * L::GRP;
             const int per_win = 64 * CIN;
-            // window w's source address for the NEXT load_tile call, held by lane w (its win_start entry is read one tile ahead:
-            // no global-load latency on the issuing path)
+            // window w's source address for the NEXT load, held by lane w (its win_start entry is read one tile ahead: no
+            // global-load latency on the issuing path); tile_next = the tile those addresses belong to (-1: the queue is empty)
             const float* src_next = nullptr;
-            auto prefetch_src = [&](int it) {
+            int tile_next = -1;
+            auto grab = [&]() {                            // whole warp: next slot of the CTA's queue -> tile id or -1
+                int j = 0;
+                if (lane == 0) j = atomicAdd(q_next, 1);
+                j = __shfl_sync(0xffffffffu, j, 0);
+                const int it_ = j / G, q_ = j - it_ * G;
+                const int tile = (it_ * (int)gridDim.x + (int)blockIdx.x) * G + q_;
+                tile_next = (j < nit * G && tile < ntiles) ? tile : -1;
                 if (lane < 2) {
-                    const int wi = tile_of(it, g) * 2 + lane;
-                    src_next = (it < nit && wi < A.B && !A.zero_input)
+                    const int wi = tile_next * 2 + lane;
+                    src_next = (tile_next >= 0 && wi < A.B && !A.zero_input)
                                    ? A.x + (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * per_win) : nullptr;
                 }
             };
-            auto load_tile = [&](int it) {                 // whole warp: windows of tile `it` -> staging (inside F|Z)
+            // whole warp: windows of tile_next -> staging (inside F|Z) and its id -> tile_slot(g, par); then takes the following slot.
+            // With an empty queue it publishes -1 (the row warps leave their loop).  Returns the tile it loaded.
+            auto load_tile = [&](uint32_t par) {
+                const int tile = tile_next;
                 const float* src0 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src_next, 0);
                 const float* src1 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src_next, 1);
-                prefetch_src(it + 1);
+                if (tile >= 0) grab();
                 uint32_t bytes = 0;
 #pragma unroll
                 for (int w = 0; w < 2; ++w) {
@@ -488,6 +510,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
                 __syncwarp();
                 WT(11);
                 if (lane == 0) {
+                    *tile_slot(g, par) = tile;             // ordered before the arrival below (release), read after the rows' wait (acquire)
                     if (bytes == 0) {
                         umma::mbar_arrive(bar_ld(g));
                     } else {
@@ -509,16 +532,17 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
                     }
                 }
                 __syncwarp();
+                return tile;
             };
             const bool leader = umma::elect_one();
             auto wait_rdy = [&](int k, uint32_t par) { umma::mbar_wait(bar_rdy(g, k), par); umma::fence_after_sync(); };
             auto commit = [&](uint64_t* bar) { if (leader) umma::commit(bar); };
-            prefetch_src(0);
-            load_tile(0);
+            grab();
+            int cur = load_tile(0u);
 #ifdef GAITK_WS_TIMING
             wt_on = blockIdx.x == 0 && g == 0 && lane == 0; wt_last = clock64();
 #endif
-            for (int it = 0; it < nit; ++it) {
+            for (int it = 0; cur >= 0; ++it) {             // `it` counts THIS group's tiles (barrier parities are per group)
                 const uint32_t par = it & 1;
                 int k = 0;
                 wait_rdy(k++, par);
@@ -552,7 +576,7 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
                 // this warp's backbone MMAs (data gradient included) have read F and Z: the staging area inside them is free
                 umma::mbar_wait(bar_free(g), par);
                 WT(7);
-                if (it + 1 < nit) load_tile(it + 1);
+                cur = load_tile(par ^ 1u);                 // the group's next tile, or the end-of-queue mark
                 WT(8);
                 if (train) {
                     wait_rdy(INS ? 4 : 3, par);            // dA is in the XH planes
@@ -598,9 +622,9 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
         const float* bbs = f32 + L::F_BB;
         const int t = r >> 1, w = r & 1;
         // per-slot state: slot s of this row warpgroup <-> group g = rg * SL + s (own planes, barriers, TMEM columns, service warp)
-        float rstd_row[SL]; uint32_t zmask[SL], dph[SL]; int ylab[SL];
+        float rstd_row[SL]; uint32_t zmask[SL], dph[SL]; int ylab[SL], cur_tile[SL];
 #pragma unroll
-        for (int q = 0; q < SL; ++q) { rstd_row[q] = 0.f; zmask[q] = 0u; dph[q] = 0u; ylab[q] = 0; }
+        for (int q = 0; q < SL; ++q) { rstd_row[q] = 0.f; zmask[q] = 0u; dph[q] = 0u; ylab[q] = 0; cur_tile[q] = 0; }
         // One phase of one slot.  Every phase ends with the arrival that lets the slot's service warp issue the next MMAs, and the
         // thread moves on to the SAME phase of its next slot: that slot's accumulator has been computed meanwhile.
         constexpr int NHP = INS ? NH8 * 8 : 8;              // padded conv1 width (the insole-only phases are never run otherwise)
@@ -611,7 +635,8 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + g * 32;
             float* Ps = reinterpret_cast<float*>(gb + L::O_P); float* DPs = reinterpret_cast<float*>(gb + L::O_DP);
             const uint32_t par = it & 1;
-            const int win0 = tile_of(it, g) * 2;
+            if (P > 0 && cur_tile[sl] < 0) return;         // this slot's group has drained the queue
+            int win0 = cur_tile[sl] * 2;
             // every thread orders its operand stores before the async proxy, the warp converges, ONE lane arrives
             auto arrive = [&](int k) {
                 umma::fence_smem_to_async(); umma::fence_before_sync();
@@ -620,11 +645,15 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             };
             auto wait_done = [&]() { umma::mbar_wait(bar_done(g), dph[sl]); dph[sl] ^= 1u; umma::fence_after_sync(); };
             if constexpr (P == 0) {
+                if (cur_tile[sl] < 0) return;
+                // ------------------------------------------------ staged window bytes -> X planes (hi, lo)
+                umma::mbar_wait(bar_ld(g), par);
+                cur_tile[sl] = *tile_slot(g, par);         // published by the service warp before the load barrier completed
+                if (cur_tile[sl] < 0) return;
+                win0 = cur_tile[sl] * 2;
                 // the head warps fetch their window's label now; it is consumed a few thousand clocks later
                 ylab[sl] = 0;
                 if (wq < 2 && A.mode == MODE_FUSED && win0 + wq < A.B) ylab[sl] = (int)A.y[win0 + wq];
-                // ------------------------------------------------ staged window bytes -> X planes (hi, lo)
-                umma::mbar_wait(bar_ld(g), par);
                 if (!A.zero_input) {
                     const bool live = win0 + w < A.B;
                     const int j = t / L::FPC;
@@ -764,8 +793,12 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             if constexpr (P == 6) wait_done();             // the first-layer weight gradient has read X and dA: the tile's buffers are free
         };
         auto all_slots = [&](auto P_, int it) { ws::static_for<SL>([&](auto S_) { phase(P_, S_, it); }); };
-        for (int it = 0; it < nit; ++it) {
+        for (int it = 0;; ++it) {                          // `it` counts this warpgroup's rounds (barrier parities are per group)
             all_slots(std::integral_constant<int, 0>{}, it);
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < SL; ++q) any = any || cur_tile[q] >= 0;
+            if (!any) break;
             if constexpr (INS) all_slots(std::integral_constant<int, 1>{}, it);
             all_slots(std::integral_constant<int, 2>{}, it);
             all_slots(std::integral_constant<int, 3>{}, it);
@@ -775,9 +808,15 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             all_slots(std::integral_constant<int, 6>{}, it);
         }
         // -------------------------------------------------------------------------------------- teardown + flush
+#ifdef GAITK_WS_TIMING
+        const long long wt_k2 = clock64();
+#endif
         umma::fence_before_sync();
         asm volatile("bar.sync 0;" ::: "memory");          // every group has seen its last commit: all MMAs are complete
         umma::fence_after_sync();
+#ifdef GAITK_WS_TIMING
+        const long long wt_k3 = clock64(); long long wt_k4 = 0, wt_k5 = 0, wt_k6 = 0;
+#endif
         if (A.mode != MODE_FWD) {
         float* out = A.partial + (size_t)blockIdx.x * A.NGP;
         const GradOff& go = A.go;
@@ -803,6 +842,9 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             }
         }
         ws::bar_sync(15, ROW_WARPS * 32);
+#ifdef GAITK_WS_TIMING
+        wt_k4 = clock64();
+#endif
         const int rt = tid;                                // row threads 0 .. 128 G - 1
         if (rt < 2 * C) {
             const int c = rt % C, which = rt / C;
@@ -833,6 +875,9 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
             colsum(L::C_B1, N1, 0);
             if constexpr (INS) colsum(L::C_B2, 16, 32);
             colsum(L::C_BB, 16, 48);
+#ifdef GAITK_WS_TIMING
+            wt_k5 = clock64();
+#endif
             // weight-gradient regions: M = 64 accumulator rows sit on lanes 0..15 of every lane quarter (row = 16 * quarter + lane);
             // rows = A's planes [hi chunks | lo chunks] x 8 channels, columns = B's [hi 16 | lo 16]: dW = hh + hl + lh + ll
             auto dump = [&](int col0, int KT) {
@@ -881,6 +926,9 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
                 const int tap = e / (C * 16), ci = (e / 16) % C, co = e % 16;
                 out[go.wbb + (co * C + ci) * 3 + tap] = wval(tap, NC8, ci, co);
             }
+#ifdef GAITK_WS_TIMING
+            wt_k6 = clock64();
+#endif
             if (rt < 64) {
                 const float s = (bst[rt] + bst[64 + rt]) + (bst[128 + rt] + bst[192 + rt]);
                 if (rt < 32) { if (rt < O1) out[go.b1 + rt] = s; }
@@ -891,6 +939,11 @@ __global__ void __launch_bounds__(WsLayout<Cfg, G, SL>::NTH, 1) stream_kernel_ws
         }
         umma::fence_before_sync();
         asm volatile("bar.sync 0;" ::: "memory");
+#ifdef GAITK_WS_TIMING
+        if (blockIdx.x == 0 && tid == 0)
+            printf("KERNEL CIN%d grid %d nit %d: setup %lld | tile loop %lld (%lld per round) | teardown %lld clocks = barrier %lld + stage %lld + sums %lld + dumps %lld + rest %lld\n", CIN, (int)gridDim.x, nit,
+                   wt_k1 - wt_k0, wt_k2 - wt_k1, (wt_k2 - wt_k1) / (nit > 0 ? nit : 1), clock64() - wt_k2, wt_k3 - wt_k2, wt_k4 - wt_k3, wt_k5 - wt_k4, wt_k6 - wt_k5, clock64() - wt_k6);
+#endif
     }
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
