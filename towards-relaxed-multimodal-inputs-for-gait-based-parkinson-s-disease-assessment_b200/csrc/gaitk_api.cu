@@ -656,7 +656,7 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         fork = live > 1 && (fork_mode == 1 || (fork_mode == 2 && widest < pl->sm_count));
         if (fork) { int rc_ = ensure_side_streams(pl); if (rc_) return rc_; CUDA_TRY(cudaEventRecord(pl->ev_fork, st)); }
     }
-    int n_forked = 0;
+    int n_forked = 0, n_launched = 0;
     for (int s = 0; s < pl->n_streams; ++s) {
         const size_t ws_floats = (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64;
         float* my_part = part; part += ws_floats;
@@ -669,18 +669,25 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         a.partial = my_part;
         const int grid = stream_grid(pl, pl->st[s], B, dtype);
         cudaStream_t ks = st;
-        if (fork && n_active > 0) {                       // first active stream stays on the caller's stream
+        if (fork && n_launched > 0) {                     // first active stream stays on the caller's stream
             ks = pl->side[n_forked];
             CUDA_TRY(cudaStreamWaitEvent(ks, pl->ev_fork, 0));
         }
         int rc = launch_stream(pl, s, a, grid, ks, dtype);
         if (rc) return rc;
-        if (ks != st) { CUDA_TRY(cudaEventRecord(pl->ev_join[n_forked], ks)); CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join[n_forked], 0)); ++n_forked; }
+        ++n_launched;
+        if (fork) {
+            // forked: every stream's reduce follows its kernel on the same stream (the streams' targets in gbuf are disjoint:
+            // task column = stream, private segments, stat slots), so it runs under the other streams' kernels
+            if ((rc = launch_reduce(pl, s, my_part, grid, gbuf, s, private_mult, s, ks))) return rc;
+            if (ks != st) { CUDA_TRY(cudaEventRecord(pl->ev_join[n_forked], ks)); CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join[n_forked], 0)); ++n_forked; }
+            continue;
+        }
         fill_reduce(pl, s, my_part, grid, gbuf, s, private_mult, s, M.r[n_active]);
         max_ng = std::max(max_ng, M.r[n_active].NG + 2);
         ++n_active;
     }
-    if (n_active) {
+    if (n_active && !fork) {
         reduce_partials_multi_kernel<<<dim3((max_ng + 127) / 128, n_active), dim3(128, 8), 0, st>>>(M);
         LAUNCH_CHECK();
     }
