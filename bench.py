@@ -56,8 +56,8 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~10 ms from a thread on rank 0 (a
-    20-step timed region lasts ~25 ms, too short for nvidia-smi's own loop; a faster poll on every rank competes with the
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread on rank 0 (a
+    20-step timed region lasts ~18 ms, too short for nvidia-smi's own loop; a faster poll on every rank competes with the
     launching threads for the host cores), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -87,7 +87,7 @@ class ClockSampler:
                 self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
             except Exception:
                 break
-            time.sleep(0.01)
+            time.sleep(0.002)       # a 20-step timed region lasts ~18 ms: ~2 ms polling gives it 8-10 samples (rank 0 only)
 
     def start(self):
         try:
