@@ -473,15 +473,17 @@ def run_gpu(args):
         for s_ in range(ns):
             tasks = [k == s_ for k in range(ns)]
             xs, ys = devb[0]
+            # the gradient half of the step for this stream alone (label histogram + zero fill + THE stream kernel + its reduce;
+            # no solve / update), launched eagerly on the current stream
             for _ in range(2):
-                step.step(xs, ys, tasks=tasks, update=False, grads_out=scratch)
+                step._step_impl(xs, ys, tasks=tasks, part="grads")
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
             a.record()
             for r in range(reps):
                 xs, ys = devb[r % NBUF]
-                step.step(xs, ys, tasks=tasks, update=False, grads_out=scratch)
+                step._step_impl(xs, ys, tasks=tasks, part="grads")
             b.record(); torch.cuda.synchronize()
             per_stream[names[s_]] = a.elapsed_time(b) / reps
         dom = max(per_stream, key=per_stream.get)
@@ -510,8 +512,8 @@ def run_gpu(args):
                 "note": "not HBM-bound (DESIGN.md 3.1c): DRAM traffic equals the algorithmic bytes (inputs are read once); at the "
                         "reference's channel widths (N = 16 outputs) the kernel is bound by the tensor pipe's fixed per-instruction "
                         "cost (~40 clocks per M = 128 tcgen05.mma whatever N <= 32 is; 70 / 134 / 76 MMAs per tile) and the row warps' "
-                        "epilogues between them; the timed launch also contains the small reduce kernel and the single-CTA "
-                        "update kernel",
+                        "epilogues between them; the timed launch also contains the label histogram, the zero fill and the stream's "
+                        "reduce kernel (~15 us together)",
                 "per_stream_ms": per_stream,
                 "step_hbm_gbs": B * bytes_per_unit / (ms_max / args.steps * 1e-3) / 1e9}
 
