@@ -360,13 +360,21 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i):
+    seq = [0]                                          # running step index: batch rotation, mask cycle and (data-parallel) exchange-buffer
+                                                       # parity advance together, so the same few (batch, options, parity) combinations recur
+    def one_step(_i=None):
+        i = seq[0]; seq[0] += 1
         xs, ys = devb[i % NBUF]
         if l2_flush is not None:
             l2_flush.fill_(i & 0xff)
         step.step(xs, ys, ys_global=yglob[i % NBUF], **wl["kw"](i))
 
     # ---- device-resident timing
+    # CUDA-graph priming (untimed, before the W warm-up steps): every (batch, options, parity) combination is captured on its second
+    # sighting (fused_step.py), so two passes over the combinations leave nothing to capture inside the warm-up or the timed region
+    n_combo = (14 if args.workload == "weargait_relaxed" else 2)
+    for _ in range(2 * n_combo + 2):
+        one_step()
     for i in range(args.warmup):
         one_step(i)
     # the sampler starts BEFORE the barrier: NVML initialisation on rank 0 must not delay its first timed step, or the

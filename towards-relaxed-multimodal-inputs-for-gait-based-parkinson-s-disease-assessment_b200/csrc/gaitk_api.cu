@@ -676,18 +676,14 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         int rc = launch_stream(pl, s, a, grid, ks, dtype);
         if (rc) return rc;
         ++n_launched;
-        if (fork) {
-            // forked: every stream's reduce follows its kernel on the same stream (the streams' targets in gbuf are disjoint:
-            // task column = stream, private segments, stat slots), so it runs under the other streams' kernels
-            if ((rc = launch_reduce(pl, s, my_part, grid, gbuf, s, private_mult, s, ks))) return rc;
-            if (ks != st) { CUDA_TRY(cudaEventRecord(pl->ev_join[n_forked], ks)); CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join[n_forked], 0)); ++n_forked; }
-            continue;
-        }
+        if (ks != st) { CUDA_TRY(cudaEventRecord(pl->ev_join[n_forked], ks)); CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join[n_forked], 0)); ++n_forked; }
+        // (a per-stream reduce on the forked streams, right after each kernel, was tried: B = 4096 step 0.230 -> 0.224 ms, but the
+        // data-parallel step with the peer-memory exchange went from 0.93 to 1.10 ms at N = 2 -- one reduce after the join it is)
         fill_reduce(pl, s, my_part, grid, gbuf, s, private_mult, s, M.r[n_active]);
         max_ng = std::max(max_ng, M.r[n_active].NG + 2);
         ++n_active;
     }
-    if (n_active && !fork) {
+    if (n_active) {
         reduce_partials_multi_kernel<<<dim3((max_ng + 127) / 128, n_active), dim3(128, 8), 0, st>>>(M);
         LAUNCH_CHECK();
     }
