@@ -468,6 +468,8 @@ def run_gpu(args):
             step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3, ys_global=yg_res[i % 4])
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:                                   # align the GPUs on the device (see the device-resident loop above)
+            step.step_indices(stores, [idx_host[3]] * 3, [y_host[3]] * 3, ys_global=yg_res[3])
         r0.record()
         for i in range(args.steps):
             step.step_indices(stores, [idx_host[i % 4]] * 3, [y_host[i % 4]] * 3, ys_global=yg_res[i % 4])
