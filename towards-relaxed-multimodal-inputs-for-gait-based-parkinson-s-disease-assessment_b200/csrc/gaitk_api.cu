@@ -653,7 +653,9 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         // one persistent kernel that finish a round early are followed at once by the next kernel's CTAs (0.9915 -> 0.9863 ms at
         // B = 32768, repeatable)
         static const int fork_mode = [] { const char* e = getenv("GAITK_FORK"); return e ? atoi(e) : 1; }();
-        fork = live > 1 && (fork_mode == 1 || (fork_mode == 2 && widest < pl->sm_count));
+        // "always" applies to the warp-specialised kernels (one persistent CTA per SM each); the fp32 / tf32 kernels (several CTAs
+        // per SM, full grids) slow each other down when they share the SMs (FoG step at B = 32768: 3.7 -> 5.1 ms): small batches only
+        fork = live > 1 && ((fork_mode == 1 && dtype == GAITK_DTYPE_BF16X3) || (fork_mode != 0 && widest < pl->sm_count));
         if (fork) { int rc_ = ensure_side_streams(pl); if (rc_) return rc_; CUDA_TRY(cudaEventRecord(pl->ev_fork, st)); }
     }
     int n_forked = 0, n_launched = 0;
