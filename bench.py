@@ -524,11 +524,15 @@ def run_gpu(args):
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "tensor_pipe_pct_of_peak": tensor_pct, "peak_source": peak_src,
                 "ms_per_launch": per_stream[dom], "algorithmic_bytes_per_launch": alg,
-                "note": "not HBM-bound (DESIGN.md 3.1c): DRAM traffic equals the algorithmic bytes (inputs are read once); at the "
-                        "reference's channel widths (N = 16 outputs) the kernel is bound by the tensor pipe's fixed per-instruction "
-                        "cost (~40 clocks per M = 128 tcgen05.mma whatever N <= 32 is; 70 / 134 / 76 MMAs per tile) and the row warps' "
-                        "epilogues between them; the timed launch also contains the label histogram, the zero fill and the stream's "
-                        "reduce kernel (~15 us together)",
+                "note": ("fp32 FFMA kernel, one 101-row clip per 128-thread CTA, 3 CTAs per SM: issue- and latency-bound "
+                         "(DESIGN.md 3.1d), DRAM traffic equals the algorithmic bytes (the next clip is bulk-prefetched while "
+                         "one is computed); the timed launch also contains the label histogram, the zero fill and the stream's "
+                         "reduce kernel" if wl["dtype"] == "f32" else
+                         "not HBM-bound (DESIGN.md 3.1c): DRAM traffic equals the algorithmic bytes (inputs are read once); at the "
+                         "reference's channel widths (N = 16 outputs) the kernel is bound by the tensor pipe's fixed per-instruction "
+                         "cost (~40 clocks per M = 128 tcgen05.mma whatever N <= 32 is; 70 / 134 / 76 MMAs per tile) and the row warps' "
+                         "epilogues between them; the timed launch also contains the label histogram, the zero fill and the stream's "
+                         "reduce kernel (~15 us together)"),
                 "per_stream_ms": per_stream,
                 "step_hbm_gbs": B * bytes_per_unit / (ms_max / args.steps * 1e-3) / 1e9}
 
@@ -604,8 +608,8 @@ def run_gpu(args):
                                                                     if (args.p2p and getattr(step, "_p2p", None) is not None) else
                                                                     "NCCL all_reduce of gbuf between two CUDA graphs" + (" (peer-memory exchange unavailable: fell back)" if args.p2p else ""))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pinned host batch of (B,64,2)+(B,64,13)+(B,64,24) fp32 + labels copied every step (copy of batch i+1 "
-                            "overlaps step i), result (loss[3], correct[3]) read back every step"},
+                    "note": "pinned host batch of " + "+".join("(B,%d,%d)" % (t_, c_) for t_, c_ in dims) + " fp32 + labels copied every "
+                            "step (copy of batch i+1 overlaps step i), result (loss[n], correct[n]) read back every step"},
             "e2e_resident": None if res_value is None else {
                 "value": res_value, "unit": UNIT, "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": d2h,
                 "note": "frame stores resident in HBM, sharded by window over the ranks (uploaded once per fold); per step the "

@@ -145,3 +145,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     env["RANK"] = "1"
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("t_in,t_out,cin,cout", [(426, 101, 6, 6), (426, 101, 3, 3), (300, 101, 3, 3), (101, 101, 6, 6), (7, 5, 2, 4)])
+def test_pooled_taps_identity_of_the_sensor_encoder(t_in, t_out, cin, cout):
+    """The pooled-taps kernel (ENC_POOL_LINEAR, csrc/stream_common.cuh) rests on: AdaptiveAvgPool1d(conv1d_k3(x)) ==
+    Linear over the three tap-shifted bin means of x with conv1d.weight (C, Cin, 3) read as (C, 3 Cin), because
+    SensorEncoder (feature_encoder.py:27-58) has nothing non-linear between the two.  Checked here against torch
+    (fp32 CPU) with the bins the kernel uses: [floor(i T_in / T), ceil((i + 1) T_in / T)), zero padding outside the clip."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, t_in, cin, generator=g)
+    w = torch.randn(cout, cin, 3, generator=g) * 0.3
+    b = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.adaptive_avg_pool1d(torch.nn.functional.conv1d(x.transpose(1, 2), w, b, padding=1), t_out).transpose(1, 2)
+    xp = torch.nn.functional.pad(x, (0, 0, 1, 1))                       # frame t of x is row t + 1
+    P = torch.zeros(3, t_out, cin * 3)
+    for i in range(t_out):
+        s0, s1 = (i * t_in) // t_out, -((-(i + 1) * t_in) // t_out)
+        for tap in range(3):
+            P[:, i, tap::3] = xp[:, s0 + tap:s1 + tap].mean(1)          # channel ci * 3 + tap
+    got = P @ w.reshape(cout, cin * 3).t() + b
+    assert torch.allclose(got, ref, rtol=1e-5, atol=2e-6), float((got - ref).abs().max())

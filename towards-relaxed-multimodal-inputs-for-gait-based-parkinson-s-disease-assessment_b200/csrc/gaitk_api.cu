@@ -40,6 +40,7 @@ struct ParamInfo {
 
 struct StreamPlan {
     int enc, CIN, T_in, T, W, rows_in, rows, halo, RBi, RB, pool_sensor;
+    int pooled_taps;                                                   // sensor encoder in its pooled-taps form (ENC_POOL_LINEAR kernel)
     int cl;                                                            // thread-block cluster size (long windows split by time), else 1
     int H, C, S, NFL, KT1, skip_identity, PROJ;
     StreamKernelFn fn;
@@ -117,12 +118,25 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
             return fail(GAITK_E_SHAPE, "window length %d with %d pooling bins: bins would straddle the %d CTAs of a cluster", T, d.backbone_dim, cl);
         sp.cl = cl; sp.rows = NT; sp.rows_in = NT;
     }
-    sp.RB = round_rb(sp.rows, sp.halo); sp.RBi = round_rb(sp.rows_in, sp.halo);
+    // SensorEncoder that pools (no non-linearity between Conv1d and AdaptiveAvgPool1d): the pooled-taps kernel pools the raw clip
+    // while loading it and runs Linear(3 CIN -> C) over the T pooled rows (stream_common.cuh, ENC_POOL_LINEAR); GAITK_POOLED_TAPS=0
+    // keeps the literal conv-over-T_in-rows-then-pool kernel (the A/B switch of the parity tests)
+    static const int pooled_mode = [] { const char* e = getenv("GAITK_POOLED_TAPS"); return e ? atoi(e) : 1; }();
+    sp.pooled_taps = 0;
     KernelKey key = {enc, CIN, KT1, H, sp.C, sp.S, sp.NFL, sp.PROJ};
-    sp.fn = find_kernel(key);
+    sp.fn = nullptr;
+    if (enc == ENC_CONV_POOL && pool_sensor && KT1 == 3 && pooled_mode) {
+        KernelKey kp = {ENC_POOL_LINEAR, 3 * CIN, 1, H, sp.C, sp.S, sp.NFL, sp.PROJ};
+        sp.fn = find_kernel(kp);
+        if (sp.fn) { sp.pooled_taps = 1; sp.rows_in = sp.rows; key = kp; }
+    }
+    sp.RB = round_rb(sp.rows, sp.halo); sp.RBi = round_rb(sp.rows_in, sp.halo);
+    if (!sp.fn) sp.fn = find_kernel(key);
     if (!sp.fn)
         return fail(GAITK_E_SHAPE, "no sm_100a kernel instantiated for stream %d (enc=%d Cin=%d k=%d H=%d C=%d S=%d NF=%d); "
                     "supported: WearGait C=12/S=16 and C=24/S=32 (bdim=8), FoG and FBG defaults", s, enc, CIN, KT1, H, sp.C, sp.S, NF);
+    const int raw_cin = CIN;
+    if (sp.pooled_taps) { CIN = 3 * CIN; KT1 = 1; }                    // what the kernel convolves (sp.CIN / sp.KT1 keep the model's)
     // ---- shared memory plan (floats)
     const int CI4 = (CIN + 3) / 4, C4 = (sp.C + 3) / 4, CP = C4 * 4, H4 = (H + 3) / 4, S4 = sp.S / 4;
     const int O1 = (enc == ENC_INSOLE) ? H4 * 4 : CP;
@@ -147,7 +161,17 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     m.P = take(WMAX * NF); m.DP = take(WMAX * NF); m.LOGIT = take(WMAX * KMAX);
     m.BINS = take(2 * d.backbone_dim + 4 * T + 2 * T_in + 8);
     int nblk_max = std::max(std::max(KT1 * CI4 * (O1 / 4), 3 * CB4 * S4), enc == ENC_INSOLE ? 3 * H4 * C4 : 0);
-    m.STAGE = take(16 * std::max(std::max(NF, 256), std::max(nblk_max, NT)));
+    const int stage_floats = 16 * std::max(std::max(NF, 256), std::max(nblk_max, NT));
+    m.STAGE = take(stage_floats);
+    // bulk-prefetch staging of the next tile's raw windows (stream_kernel.cuh): the FoG / FBG streams, whose kernels were
+    // bound by the synchronous global -> shared scatter; the pooled-taps kernel has no other load path
+    static const int prefetch_mode = [] { const char* e = getenv("GAITK_F32_PREFETCH"); return e ? atoi(e) : 1; }();
+    if (sp.pooled_taps || (prefetch_mode && enc == ENC_LINEAR_LN_RELU && sp.cl == 1 && T_in * raw_cin >= 8)) {
+        m.STGN = (T_in * raw_cin + 3) / 4 * 4 + 4;
+        // the flush scratch is idle inside the tile loop (and no copy is in flight when the flush starts): the staging aliases it
+        m.STG = sp.W * m.STGN <= stage_floats ? m.STAGE : take(sp.W * m.STGN);
+        m.MBAR = take(4);
+    }
     m.total = o;
     sp.smem_bytes = (size_t)o * sizeof(float);
     if (sp.smem_bytes > 227 * 1024)
@@ -410,7 +434,7 @@ static void fill_args(const gaitk_plan* pl, int s, const float* params, const fl
     a.x = x; a.win_start = (const long long*)ws; a.B = B; a.T_in = sp.T_in; a.T = sp.T; a.W = sp.W;
     a.bdim = pl->d.backbone_dim; a.K = pl->d.num_classes; a.NF = pl->NF;
     a.rows_in = sp.rows_in; a.rows = sp.rows; a.halo = sp.halo; a.RBi = sp.RBi; a.RB = sp.RB;
-    a.mode = mode; a.zero_input = zero_input; a.pool_sensor = sp.pool_sensor; a.cl = sp.cl;
+    a.mode = mode; a.zero_input = zero_input; a.pool_sensor = sp.pooled_taps ? 0 : sp.pool_sensor; a.cl = sp.cl;
     a.w1 = pp(params, pl, sp.p_w1); a.b1 = pp(params, pl, sp.p_b1); a.w2 = pp(params, pl, sp.p_w2); a.b2 = pp(params, pl, sp.p_b2);
     a.wsk = pp(params, pl, sp.p_wsk); a.bsk = pp(params, pl, sp.p_bsk); a.lng = pp(params, pl, sp.p_lng); a.lnb = pp(params, pl, sp.p_lnb);
     a.wbb = pp(params, pl, pl->p_wbb); a.bbb = pp(params, pl, pl->p_bbb);

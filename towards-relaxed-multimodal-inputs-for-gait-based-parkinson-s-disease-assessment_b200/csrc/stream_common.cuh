@@ -30,14 +30,20 @@ constexpr int WMAX = 4;        // windows per tile (one warp each in the head ph
 // 128 contiguous bytes); the mma.sync fragment loads of the weight gradients read lanes (g, t) -> channel g, row t:
 // chunk g >> 2, word 4 t + (g & 3), so the two chunks must sit 16 banks apart: 4 RB = 16 (mod 32)  <=>  RB = 4 (mod 8).
 #ifndef GAITK_FOG_MINB
-#define GAITK_FOG_MINB 1
+#define GAITK_FOG_MINB 3
 #endif
 #ifndef GAITK_RB_MOD
 #define GAITK_RB_MOD 4
 #endif
 
 enum EncKind { ENC_CONV_GELU_LN = 0, ENC_INSOLE = 1, ENC_LINEAR_LN_RELU = 2, ENC_CONV_POOL = 3,
-               ENC_NONE = 4 };       // no encoder: x IS the backbone input (the trunk stage of the fusion baselines)
+               ENC_NONE = 4,         // no encoder: x IS the backbone input (the trunk stage of the fusion baselines)
+               // SensorEncoder when it pools (feature_encoder.py:27-58: Conv1d k3 -> AdaptiveAvgPool1d, NOTHING non-linear in
+               // between): mean_bin(conv(x)) == Linear over the three tap-shifted bin means of x.  The kernel pools the raw clip
+               // while it loads it (T_in -> T rows of 3 CIN_raw channels, channel ci * 3 + tap) and runs a 1-tap "conv" whose
+               // weight matrix IS conv1d.weight (C, CIN_raw, 3) read as (C, 3 CIN_raw): T_in / T times fewer MACs in the
+               // forward and in the weight gradient, no (T_in, C) intermediate.  Cfg::CIN = 3 CIN_raw, Cfg::KT1 = 1.
+               ENC_POOL_LINEAR = 5 };
 enum Mode { MODE_FWD = 0, MODE_FUSED = 1, MODE_BWD_EXT = 2 };
 
 // stream-local gradient layout (offsets in floats into a partial-gradient row; -1 = absent)
@@ -175,11 +181,12 @@ struct StreamCfg {
     static constexpr int CB4 = (CB + 3) / 4;
     static constexpr int CBP = CB4 * 4;
     static constexpr int O1 = (ENC_ == ENC_INSOLE) ? H4 * 4 : CP;   // padded outputs of the first conv
-    // resident CTAs per SM the fp32 kernel is compiled for.  Measured (round 2): the narrow FoG / FBG encoders fit 168 registers
-    // without a spill (GAITK_FOG_MINB = 3: 12 warps per SM instead of 8) and run NO faster (3.78 vs 3.70 ms per step: 17.7 K warp
-    // instructions per window of runtime-geometry bookkeeping at IPC 1.4 is the limiter, not occupancy; profiles/r2_ncu_fog.txt);
-    // the WearGait encoders would spill (160 - 1140 B).  Default 1 everywhere.
-    static constexpr int MINB = (ENC_ == ENC_LINEAR_LN_RELU || ENC_ == ENC_CONV_POOL) ? GAITK_FOG_MINB : 1;
+    // resident CTAs per SM the fp32 kernel is compiled for.  The narrow FoG / FBG encoders fit 168 registers with a handful of
+    // spilled words (GAITK_FOG_MINB = 3: 12 warps per SM); left alone ptxas takes ~250 registers = 2 CTAs per SM, and these
+    // latency-bound kernels then run at IPC 0.9 instead of 1.4 (FoG step at B = 32768: 5.1 vs 3.7 ms, profiles/r3_fog.md -- the
+    // round-2 note that occupancy made no difference compared two builds that both ran 3 CTAs per SM).  4 CTAs per SM (128
+    // registers) spills 0.5 - 0.9 KB per thread.  The WearGait encoders would spill at 3 (160 - 1140 B): 1 there.
+    static constexpr int MINB = (ENC_ == ENC_LINEAR_LN_RELU || ENC_ == ENC_CONV_POOL || ENC_ == ENC_POOL_LINEAR) ? GAITK_FOG_MINB : 1;
 };
 
 // shared-memory plan (offsets in floats); filled on the host, passed by value
@@ -188,6 +195,7 @@ struct SmemPlan {
     int W1F, B1, W2F, B2, W2D, LNG, LNB, WBF, BB, WBD, HW, HB, HNG, HNB, INW;   // weights
     int P, DP, LOGIT, BINS, STAGE;                   // head / pooling scratch
     int L, DL, WPF, BP, WPD;                         // projection stage (SharedLatent3)
+    int STG, STGN, MBAR;                             // bulk-prefetch staging: raw bytes of the NEXT tile (STGN floats per window, 0 = off)
     int total;
 };
 

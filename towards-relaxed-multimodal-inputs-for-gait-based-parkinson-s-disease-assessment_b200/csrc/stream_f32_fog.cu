@@ -17,6 +17,9 @@ StreamKernelFn find_kernel_fog(const KernelKey& k) {
     GK_CASE(ENC_CONV_POOL, 6, 3, 0, 6, 16, 4)
     GK_CASE(ENC_LINEAR_LN_RELU, 51, 1, 0, 3, 16, 4)
     GK_CASE(ENC_CONV_POOL, 3, 3, 0, 3, 16, 4)
+    // the same sensor encoders in pooled-taps form (3 x raw channels, one tap; stream_common.cuh)
+    GK_CASE(ENC_POOL_LINEAR, 18, 1, 0, 6, 16, 4)
+    GK_CASE(ENC_POOL_LINEAR, 9, 1, 0, 3, 16, 4)
     // trunk stages of the fusion baselines (no encoder; C = CIN): EarlyFusion3 3 x 12, CheapXAttn3 12; 2-stream twins
     // (feature_encoder.py:346-596) early 6 + 6, late / cross-attention 6, shared latent 16
     GK_CASE(ENC_NONE, 36, 1, 0, 36, 16, 4)

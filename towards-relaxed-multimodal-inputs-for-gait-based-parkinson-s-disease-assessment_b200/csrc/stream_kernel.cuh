@@ -5,6 +5,7 @@
 #include <cooperative_groups.h>
 
 #include "stream_common.cuh"
+#include "umma.cuh"
 
 namespace gaitk {
 
@@ -115,7 +116,11 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
     constexpr int ENC = Cfg::ENC, CIN = Cfg::CIN, CI4 = Cfg::CI4, KT1 = Cfg::KT1, H = Cfg::H, H4 = Cfg::H4;
     constexpr int C = Cfg::C, C4 = Cfg::C4, CP = Cfg::CP, S = Cfg::S, S4 = Cfg::S4, NFL = Cfg::NFL, O1 = Cfg::O1;
     constexpr int PROJ = Cfg::PROJ, CB = Cfg::CB, CB4 = Cfg::CB4, CBP = Cfg::CBP;
-    static_assert(PROJ == 0 || (ENC != ENC_CONV_POOL && ENC != ENC_LINEAR_LN_RELU), "projection stage: WearGait encoders");
+    static_assert(PROJ == 0 || (ENC != ENC_CONV_POOL && ENC != ENC_LINEAR_LN_RELU && ENC != ENC_POOL_LINEAR), "projection stage: WearGait encoders");
+    constexpr bool POOLLIN = ENC == ENC_POOL_LINEAR;                 // pooled-taps sensor encoder (see EncKind)
+    constexpr bool CONVP = ENC == ENC_CONV_POOL || POOLLIN;          // conv (or its pooled-taps form), no activation, no LayerNorm
+    constexpr int RC = POOLLIN ? CIN / 3 : CIN;                      // channels of a raw input frame
+    static_assert(!POOLLIN || (CIN % 3 == 0 && KT1 == 1), "pooled taps: CIN = 3 x raw channels, one tap");
     const int W = A.W, halo = A.halo, RB = A.RB, RBi = A.RBi, rows = A.rows, rows_in = A.rows_in, T = A.T, T_in = A.T_in;
     const int K = A.K, NF = A.NF, bdim = A.bdim;
     const bool train = A.mode != MODE_FWD;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
         }
         for (int i = tid; i < C; i += NT) b2s[i] = A.b2[i] + (A.skip_identity ? 0.f : A.bsk[i]);
     }
-    if constexpr (ENC != ENC_CONV_POOL && ENC != ENC_NONE) {
+    if constexpr (!CONVP && ENC != ENC_NONE) {
         for (int i = tid; i < C; i += NT) { lngs[i] = A.lng[i]; lnbs[i] = A.lnb[i]; }
     }
     if (!enc_only) for (int i = tid; i < S * CB * 3; i += NT) {
@@ -208,8 +213,8 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
     int* bin_s = bins; int* bin_e = bins + bdim; int* t_lo = bins + 2 * bdim; int* t_hi = t_lo + T;
     for (int b = tid; b < bdim; b += NT) { bin_s[b] = (b * T) / bdim; bin_e[b] = ((b + 1) * T + bdim - 1) / bdim; }
     int* ep_s = t_hi + T; int* ep_e = ep_s + T; int* ep_lo = ep_e + T; int* ep_hi = ep_lo + T_in;   // encoder pool (T_in -> T)
-    if constexpr (ENC == ENC_CONV_POOL) {
-        if (A.pool_sensor)
+    if constexpr (CONVP) {
+        if (A.pool_sensor || POOLLIN)
             for (int i = tid; i < T; i += NT) { ep_s[i] = (i * T_in) / T; ep_e[i] = ((i + 1) * T_in + T - 1) / T; }
     }
     __syncthreads();
@@ -265,10 +270,98 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
     const float inv_denom = (A.mode == MODE_FUSED) ? 1.0f / A.denom[0] : 0.f;
 
     const int ntiles = (A.B + W - 1) / W;
+    // ---- bulk prefetch (host: SP.STGN > 0 -- the FoG / FBG streams): while a tile is computed the raw bytes of the CTA's NEXT
+    // tile travel global -> staging by cp.async.bulk (the 16-byte aligned body of every window; a clip of 101 x 21 floats
+    // starts on a 4-byte boundary only) plus up to 3 + 3 four-byte cp.async copies for the unaligned head / tail; nothing is
+    // read outside the window.  The staged window keeps the source's misalignment so that both ends of the bulk copy are
+    // 16-byte aligned.  The synchronous global -> shared scatter this replaces was a third of all stall samples.
+    float* STGs = sm + SP.STG;
+    uint64_t* ldbar = reinterpret_cast<uint64_t*>(sm + SP.MBAR);
+    const int per_raw = T_in * RC;                                   // floats of one raw window
+    const bool PF = SP.STGN > 0 && !A.zero_input && CLn == 1;
+    uint32_t ldphase = 0;
+    auto win_src = [&](int wi) { return A.x + (A.win_start ? (size_t)A.win_start[wi] * RC : (size_t)wi * per_raw); };
+    auto prefetch = [&](int tile_) {
+        if (tid == 0) {
+            uint32_t bytes = 0;
+            for (int w = 0; w < W; ++w) {
+                const int wi = tile_ * W + w;
+                if (wi >= A.B) continue;
+                const int mis = (int)((reinterpret_cast<uintptr_t>(win_src(wi)) >> 2) & 3), head = (4 - mis) & 3;
+                bytes += (uint32_t)((per_raw - head) & ~3) * 4u;
+            }
+            umma::mbar_expect_tx(ldbar, bytes);
+        }
+        for (int w = 0; w < W; ++w) {
+            const int wi = tile_ * W + w;
+            if (wi >= A.B) continue;
+            const float* src = win_src(wi);
+            const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3), head = (4 - mis) & 3;
+            const int body = (per_raw - head) & ~3, tail = per_raw - head - body;
+            float* dst = STGs + w * SP.STGN + mis;
+            if (tid == 0) { if (body > 0) umma::bulk_g2s(dst + head, src + head, (uint32_t)body * 4u, ldbar); }
+            else if (tid <= head + tail) {
+                const int e = tid - 1 < head ? tid - 1 : head + body + (tid - 1 - head);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(dst + e)), "l"(src + e) : "memory");
+            }
+        }
+    };
+    if (PF) {
+        if (tid == 0) { umma::mbar_init(ldbar, 1); umma::fence_mbar_init(); }
+        __syncthreads();
+        if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
+    }
     for (int tile = blockIdx.x / CLn; tile < ntiles; tile += gridDim.x / CLn) {
         const int win0 = tile * W;
         // ================= load: global (window-major) -> Xs [chunk][row][4]
-        if (CLn > 1) {
+        if (PF) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            umma::mbar_wait(ldbar, ldphase); ldphase ^= 1u;
+            __syncthreads();                                          // the 4-byte copies of the other threads
+            for (int w = 0; w < W; ++w) {
+                const int wi = win0 + w;
+                const bool live = wi < A.B;
+                const float* sw = STGs + w * SP.STGN + (live ? (int)((reinterpret_cast<uintptr_t>(win_src(wi)) >> 2) & 3) : 0);
+                if constexpr (POOLLIN) {
+                    // row i, channel ci * 3 + tap = mean over bin i of x[t + tap - 1][ci] (zero outside the clip)
+                    for (int it = tid; it < T * RC; it += NT) {
+                        const int i = it / RC, ci = it - i * RC;
+                        const int s0 = ep_s[i], s1 = ep_e[i];
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                        if (live) {
+                            for (int t = s0 - 1; t <= s1; ++t) {
+                                const float v = (t >= 0 && t < T_in) ? sw[t * RC + ci] : 0.f;
+                                if (t <= s1 - 2) a0 += v;
+                                if (t >= s0 && t < s1) a1 += v;
+                                if (t > s0) a2 += v;
+                            }
+                            const float inv = 1.0f / (float)(s1 - s0);
+                            a0 *= inv; a1 *= inv; a2 *= inv;
+                        }
+                        const int c0 = ci * 3, row = halo + i * W + w;
+                        Xs[(((c0) >> 2) * RBi + row) * 4 + ((c0) & 3)] = a0;
+                        Xs[(((c0 + 1) >> 2) * RBi + row) * 4 + ((c0 + 1) & 3)] = a1;
+                        Xs[(((c0 + 2) >> 2) * RBi + row) * 4 + ((c0 + 2) & 3)] = a2;
+                    }
+                } else {
+                    for (int e = tid; e < per_raw; e += NT) {
+                        const int t = e / CIN, c = e - t * CIN;
+                        Xs[((c >> 2) * RBi + halo + t * W + w) * 4 + (c & 3)] = live ? sw[e] : 0.f;
+                    }
+                }
+            }
+            umma::fence_smem_to_async();                              // staging is read; the next bulk copy may overwrite it
+            __syncthreads();
+            const int nxt = tile + (int)gridDim.x;
+            if (nxt < ntiles) prefetch(nxt);
+        } else if constexpr (POOLLIN) {
+            // masked / zero input: the pooled taps of zeros (a live input always takes the staged path: the host plans
+            // the staging buffer with this encoder)
+            for (int e = tid; e < CI4 * rows; e += NT) {
+                const int c4 = e / rows, r = e - c4 * rows;
+                reinterpret_cast<float4*>(Xs)[c4 * RBi + halo + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else if (CLn > 1) {
             // frames [t_off - halo, t_off + rows + halo) of the one window; zero outside [0, T)
             const int wi = win0;
             const size_t base = (wi < A.B) ? (A.win_start ? (size_t)A.win_start[wi] * CIN : (size_t)wi * T_in * CIN) : 0;
@@ -308,7 +401,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
         }
         if constexpr (ENC == ENC_NONE) {
             // nothing: Xs is the backbone input
-        } else if constexpr (ENC == ENC_CONV_POOL) {
+        } else if constexpr (CONVP) {
             // conv over the T_in input rows, no activation; optional adaptive pooling T_in -> T
             for (int r = tid; r < rows_in; r += NT) {
                 float a[CP];
@@ -421,11 +514,22 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
             float z[S], dz[S];
             load_row<S>(Zs, RB, halo, r, z);
             const int lo = t_lo[t + t_off], hi = t_hi[t + t_off];
+            // a frame lies in one pooling bin, or in two where ATen's adaptive bins overlap: vector rows of DP instead of a
+            // scalar loop per channel (that loop was 11 - 16 % of the FoG kernels' instructions)
+            float dsum[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) dsum[s] = 0.f;
+            for (int b = lo; b <= hi; ++b) {
+                const float4* dp4 = reinterpret_cast<const float4*>(DPs + w * NF + b * S);
+#pragma unroll
+                for (int s4 = 0; s4 < S4; ++s4) {
+                    const float4 v = dp4[s4];
+                    dsum[s4 * 4] += v.x; dsum[s4 * 4 + 1] += v.y; dsum[s4 * 4 + 2] += v.z; dsum[s4 * 4 + 3] += v.w;
+                }
+            }
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                float d = 0.f;
-                for (int b = lo; b <= hi; ++b) d += DPs[w * NF + b * S + s];
-                dz[s] = z[s] > 0.f ? d : 0.f;
+                dz[s] = z[s] > 0.f ? dsum[s] : 0.f;
                 g_bb[s] += dz[s];
             }
             store_row<S>(Zs, RB, halo, r, dz);
@@ -454,7 +558,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
                     for (int c = 0; c < CBP; ++c) if (c < CIN) dst[c] = dxr[c];
                 }
             }
-        } else if constexpr (ENC == ENC_CONV_POOL) {
+        } else if constexpr (CONVP) {
             for (int r = tid; r < rows; r += NT) {
                 float df[CP];
                 if (A.dfeat_in) load_dfeat(r, df);
@@ -574,7 +678,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
         g_w2.flush(stage, out + go.w2, (A.skip_identity ? nullptr : out + go.wsk), H, C, tid);
         flush_rowacc<CP>(g_b2, C, stage, out + go.b2, (A.skip_identity ? nullptr : out + go.bsk), tid);
     }
-    if constexpr (ENC != ENC_CONV_POOL && ENC != ENC_NONE) {
+    if constexpr (!CONVP && ENC != ENC_NONE) {
         flush_rowacc<CP>(g_lng, C, stage, out + go.lng, nullptr, tid);
         flush_rowacc<CP>(g_lnb, C, stage, out + go.lnb, nullptr, tid);
     }
