@@ -11,7 +11,10 @@ namespace gaitk {
 
 // out[o] = bias[o] + sum_{tap, ci} in[row + (tap - KT/2) * W][ci] * wf[tap][ci][o]
 // `in` is a chunked buffer with RBx rows per chunk; wf/bias live in shared memory.
-template <int KT, int CI4, int CO>
+// CIR / COR: REAL input / output channels (<= the padded CI4 * 4 / CO): the unrolled loops drop the multiply-adds of the
+// padding (the weights there are zero); a padded output keeps its bias (zero).  FoG widths (6 -> 8, 21 -> 24) spent a
+// quarter of their multiply-adds on padding.
+template <int KT, int CI4, int CO, int CIR = CI4 * 4, int COR = CO>
 __device__ __forceinline__ void conv_row(const float* __restrict__ in, int RBx, int halo, int W, int r,
                                          const float* __restrict__ wf, const float* __restrict__ bias,
                                          float (&acc)[CO]) {
@@ -23,18 +26,21 @@ __device__ __forceinline__ void conv_row(const float* __restrict__ in, int RBx, 
         const float4* xp = reinterpret_cast<const float4*>(in) + (halo + r + (tap - KT / 2) * W);
 #pragma unroll
         for (int c4 = 0; c4 < CI4; ++c4) {
+            if (c4 * 4 >= CIR) continue;
             const float4 x = xp[c4 * RBx];
             const float4* wp = reinterpret_cast<const float4*>(wf + (size_t)(tap * CI4 * 4 + c4 * 4) * CO);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+                if (c4 * 4 + e >= CIR) continue;
                 const float xe = f4get(x, e);
 #pragma unroll
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    if (o4 * 4 >= COR) continue;
                     const float4 w = wp[e * (CO / 4) + o4];
                     acc[o4 * 4 + 0] = fmaf(xe, w.x, acc[o4 * 4 + 0]);
-                    acc[o4 * 4 + 1] = fmaf(xe, w.y, acc[o4 * 4 + 1]);
-                    acc[o4 * 4 + 2] = fmaf(xe, w.z, acc[o4 * 4 + 2]);
-                    acc[o4 * 4 + 3] = fmaf(xe, w.w, acc[o4 * 4 + 3]);
+                    if (o4 * 4 + 1 < COR) acc[o4 * 4 + 1] = fmaf(xe, w.y, acc[o4 * 4 + 1]);
+                    if (o4 * 4 + 2 < COR) acc[o4 * 4 + 2] = fmaf(xe, w.z, acc[o4 * 4 + 2]);
+                    if (o4 * 4 + 3 < COR) acc[o4 * 4 + 3] = fmaf(xe, w.w, acc[o4 * 4 + 3]);
                 }
             }
         }
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
         if constexpr (ENC == ENC_INSOLE) {
             for (int r = tid; r < rows; r += NT) {
                 float a1[O1], ha[O1], d1[O1];
-                conv_row<KT1, CI4, O1>(Xs, RBi, halo, W, r, w1f, b1s, a1);
+                conv_row<KT1, CI4, O1, CIN, H>(Xs, RBi, halo, W, r, w1f, b1s, a1);
 #pragma unroll
                 for (int c = 0; c < O1; ++c) { if (c < H) gelu_fwd(a1[c], ha[c], d1[c]); else { ha[c] = 0.f; d1[c] = 0.f; } }
                 store_row<O1>(HAs, RB, halo, r, ha);
@@ -405,7 +411,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
             // conv over the T_in input rows, no activation; optional adaptive pooling T_in -> T
             for (int r = tid; r < rows_in; r += NT) {
                 float a[CP];
-                conv_row<KT1, CI4, CP>(Xs, RBi, halo, W, r, w1f, b1s, a);
+                conv_row<KT1, CI4, CP, CIN, C>(Xs, RBi, halo, W, r, w1f, b1s, a);
                 store_row<CP>(A.pool_sensor ? As : Fs, A.pool_sensor ? RBi : RB, halo, r, a);
             }
             __syncthreads();
@@ -430,8 +436,8 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
         } else {
             for (int r = tid; r < rows; r += NT) {
                 float a[CP], g[CP], d[CP], xh[CP], f[CP]; float rstd;
-                if constexpr (ENC == ENC_INSOLE) conv_row<3, H4, CP>(HAs, RB, halo, W, r, w2f, b2s, a);
-                else conv_row<KT1, CI4, CP>(Xs, RBi, halo, W, r, w1f, b1s, a);
+                if constexpr (ENC == ENC_INSOLE) conv_row<3, H4, CP, H, C>(HAs, RB, halo, W, r, w2f, b2s, a);
+                else conv_row<KT1, CI4, CP, CIN, C>(Xs, RBi, halo, W, r, w1f, b1s, a);
                 if constexpr (ENC == ENC_LINEAR_LN_RELU) {
                     ln_fwd<CP, C>(a, xh, rstd);
 #pragma unroll
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
         if (!A.dfeat_in) {
         for (int r = tid; r < rows; r += NT) {
             float z[S];
-            conv_row<3, CB4, S>(BBin, RB, halo, W, r, wbf, bbs, z);
+            conv_row<3, CB4, S, CB, S>(BBin, RB, halo, W, r, wbf, bbs, z);
 #pragma unroll
             for (int s = 0; s < S; ++s) z[s] = fmaxf(z[s], 0.f);
             store_row<S>(Zs, RB, halo, r, z);
@@ -504,6 +510,19 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
                 head.run(A, hc, 0, lane, win0, train, inv_denom);
                 if (crank != 0) head.zero();                               // CTA 0 alone accounts for the head, loss and accuracy
             }
+        } else if (W == 1) {
+            // one window per tile (FoG / FBG clips): all four warps pool (same sums, same order as the head's own pooling),
+            // warp 0 runs head + loss -- instead of three warps waiting while one pools and runs the head
+            for (int j = tid; j < NF; j += NT) {
+                const int b = j / S, sch = j - b * S;
+                const int t0 = bin_s[b], t1 = bin_e[b];
+                float acc = 0.f;
+                for (int t = t0; t < t1; ++t) acc += Zs[((sch >> 2) * RB + halo + t) * 4 + (sch & 3)];
+                Ps[j] = acc / (float)(t1 - t0);
+            }
+            __syncthreads();
+            hc.Ps = Ps;
+            if (wrp == 0) head.run(A, hc, 0, lane, win0, train, inv_denom);
         } else
         if (wrp < W) head.run(A, hc, wrp, lane, win0, train, inv_denom);
         if (!train) { __syncthreads(); continue; }
@@ -552,7 +571,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
                     const int t = r / W, w = r - t * W, wi = win0 + w;
                     if (wi >= A.B) continue;
                     float dxr[CBP];
-                    conv_row<3, S4, CBP>(Zs, RB, halo, W, r, wbd, nullptr, dxr);
+                    conv_row<3, S4, CBP, S, CB>(Zs, RB, halo, W, r, wbd, nullptr, dxr);
                     float* dst = A.dx + ((size_t)wi * T + t) * CIN;
 #pragma unroll
                     for (int c = 0; c < CBP; ++c) if (c < CIN) dst[c] = dxr[c];
@@ -562,7 +581,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
             for (int r = tid; r < rows; r += NT) {
                 float df[CP];
                 if (A.dfeat_in) load_dfeat(r, df);
-                else conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
+                else conv_row<3, S4, CP, S, C>(Zs, RB, halo, W, r, wbd, nullptr, df);
                 if (A.pool_sensor) {
                     const float inv = 1.0f / (float)(ep_e[r] - ep_s[r]);
 #pragma unroll
@@ -597,7 +616,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
                 float df[CP], xh[CP], dxh[CP], dg[CP], da[CP];
                 if constexpr (PROJ > 0) {
                     float dl[CBP];
-                    conv_row<3, S4, CBP>(Zs, RB, halo, W, r, wbd, nullptr, dl);
+                    conv_row<3, S4, CBP, S, CB>(Zs, RB, halo, W, r, wbd, nullptr, dl);
 #pragma unroll
                     for (int j = 0; j < CBP; ++j) g_bp[j] += dl[j];
                     store_row<CBP>(DLs, RB, halo, r, dl);
@@ -609,7 +628,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
                         for (int cc = 0; cc < C; ++cc) df[cc] = fmaf(dl[j], wpd[j * CP + cc], df[cc]);
                 } else {
                     if (A.dfeat_in) load_dfeat(r, df);
-                    else conv_row<3, S4, CP>(Zs, RB, halo, W, r, wbd, nullptr, df);
+                    else conv_row<3, S4, CP, S, C>(Zs, RB, halo, W, r, wbd, nullptr, df);
                 }
                 load_row<CP>(XHs, RB, halo, r, xh);
                 const float rstd = RSTDs[r];
@@ -647,7 +666,7 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
                 g_w2.accumulate(HAs, RB, XHs, RB, halo, W, rows, tid);
                 for (int r = tid; r < rows; r += NT) {
                     float dh[O1], d1[O1];
-                    conv_row<3, C4, O1>(XHs, RB, halo, W, r, w2d, nullptr, dh);
+                    conv_row<3, C4, O1, C, H>(XHs, RB, halo, W, r, w2d, nullptr, dh);
                     load_row<O1>(D1s, RB, halo, r, d1);
 #pragma unroll
                     for (int c = 0; c < O1; ++c) { dh[c] *= d1[c]; g_b1[c] += dh[c]; }
