@@ -9,6 +9,18 @@
 
 namespace gaitk {
 
+// (d0, d1) += a * (b0, b1) as ONE instruction: Blackwell's packed fp32 FMA (PTX fma.rn.f32x2, SASS FFMA2 with a scalar-broadcast
+// operand).  Each lane is an IEEE fma.rn, so results are bit-identical to two fmaf; ptxas never forms FFMA2 on its own.  The
+// FMA pipe does the same work per clock either way -- what halves is the number of issue slots, and these kernels are issue-bound.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
+    unsigned long long d, aa, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a), "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b0), "f"(b1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 // out[o] = bias[o] + sum_{tap, ci} in[row + (tap - KT/2) * W][ci] * wf[tap][ci][o]
 // `in` is a chunked buffer with RBx rows per chunk; wf/bias live in shared memory.
 // CIR / COR: REAL input / output channels (<= the padded CI4 * 4 / CO): the unrolled loops drop the multiply-adds of the
@@ -37,10 +49,9 @@ __device__ __forceinline__ void conv_row(const float* __restrict__ in, int RBx, 
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
                     if (o4 * 4 >= COR) continue;
                     const float4 w = wp[e * (CO / 4) + o4];
-                    acc[o4 * 4 + 0] = fmaf(xe, w.x, acc[o4 * 4 + 0]);
-                    if (o4 * 4 + 1 < COR) acc[o4 * 4 + 1] = fmaf(xe, w.y, acc[o4 * 4 + 1]);
-                    if (o4 * 4 + 2 < COR) acc[o4 * 4 + 2] = fmaf(xe, w.z, acc[o4 * 4 + 2]);
-                    if (o4 * 4 + 3 < COR) acc[o4 * 4 + 3] = fmaf(xe, w.w, acc[o4 * 4 + 3]);
+                    // output pairs; a pair whose second output is padding (odd COR) is computed anyway (zero weights)
+                    fma2(acc[o4 * 4 + 0], acc[o4 * 4 + 1], xe, w.x, w.y);
+                    if (o4 * 4 + 2 < COR) fma2(acc[o4 * 4 + 2], acc[o4 * 4 + 3], xe, w.z, w.w);
                 }
             }
         }
@@ -80,10 +91,10 @@ struct Wgrad {
             for (int r = r0; r < r1; ++r) {
                 const float4 x = xp[r];
                 const float4 d = dp[r];
-                acc[0] = fmaf(x.x, d.x, acc[0]);  acc[1] = fmaf(x.x, d.y, acc[1]);  acc[2] = fmaf(x.x, d.z, acc[2]);  acc[3] = fmaf(x.x, d.w, acc[3]);
-                acc[4] = fmaf(x.y, d.x, acc[4]);  acc[5] = fmaf(x.y, d.y, acc[5]);  acc[6] = fmaf(x.y, d.z, acc[6]);  acc[7] = fmaf(x.y, d.w, acc[7]);
-                acc[8] = fmaf(x.z, d.x, acc[8]);  acc[9] = fmaf(x.z, d.y, acc[9]);  acc[10] = fmaf(x.z, d.z, acc[10]); acc[11] = fmaf(x.z, d.w, acc[11]);
-                acc[12] = fmaf(x.w, d.x, acc[12]); acc[13] = fmaf(x.w, d.y, acc[13]); acc[14] = fmaf(x.w, d.z, acc[14]); acc[15] = fmaf(x.w, d.w, acc[15]);
+                fma2(acc[0], acc[1], x.x, d.x, d.y);   fma2(acc[2], acc[3], x.x, d.z, d.w);
+                fma2(acc[4], acc[5], x.y, d.x, d.y);   fma2(acc[6], acc[7], x.y, d.z, d.w);
+                fma2(acc[8], acc[9], x.z, d.x, d.y);   fma2(acc[10], acc[11], x.z, d.z, d.w);
+                fma2(acc[12], acc[13], x.w, d.x, d.y); fma2(acc[14], acc[15], x.w, d.z, d.w);
             }
         }
     }
