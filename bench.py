@@ -509,9 +509,11 @@ def run_gpu(args):
         # DRAM traffic / tensor-pipe utilisation of the same kernel from the committed `ncu --set full` capture
         # (profiles/r1_ncu_full_final.json, made by scratch/ncu_summary.py); per launch, scaled to this batch
         traffic = tensor_pct = None; traffic_src = None
-        sig = {"walkway": "StreamCfg<0, 2,", "insole": "StreamCfg<1, 13,", "imu": "StreamCfg<0, 24,"}.get(dom)
+        sig = {"walkway": "StreamCfg<0, 2,", "insole": "StreamCfg<1, 13,", "imu": "StreamCfg<0, 24,",
+               "skeleton": "StreamCfg<2, 21,", "sensor": "StreamCfg<5, 18,"}.get(dom)
         pdir = ROOT / "profiles"
-        cands = {"tf32": ["r1_ncu_full_final.json"], "bf16x3": sorted(q.name for q in pdir.glob("r2_ncu_full_ws_*.json"))[::-1]}.get(wl["dtype"], [])
+        cands = {"tf32": ["r1_ncu_full_final.json"], "bf16x3": sorted(q.name for q in pdir.glob("r2_ncu_full_ws_*.json"))[::-1],
+                 "f32": sorted(q.name for q in pdir.glob("r3_ncu_full_fog*.json"))[::-1]}.get(wl["dtype"], [])
         for pf in cands:
             prof = pdir / pf
             if not (sig and prof.exists()) or traffic is not None:
@@ -524,10 +526,12 @@ def run_gpu(args):
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "tensor_pipe_pct_of_peak": tensor_pct, "peak_source": peak_src,
                 "ms_per_launch": per_stream[dom], "algorithmic_bytes_per_launch": alg,
-                "note": ("fp32 FFMA kernel, one 101-row clip per 128-thread CTA, 3 CTAs per SM: issue- and latency-bound "
-                         "(DESIGN.md 3.1d), DRAM traffic equals the algorithmic bytes (the next clip is bulk-prefetched while "
-                         "one is computed); the timed launch also contains the label histogram, the zero fill and the stream's "
-                         "reduce kernel" if wl["dtype"] == "f32" else
+                "note": ("fp32 FFMA2 kernel, one 101-row clip per 128-thread CTA, 3 CTAs per SM: bound by CTA barriers, shared-memory "
+                         "latency and dependent-instruction latency at 12 warps per SM (DESIGN.md 3.1d), not by HBM; DRAM traffic equals "
+                         "the algorithmic bytes (the next clip is bulk-prefetched while one is computed); the timed launch also contains "
+                         "the label histogram, the zero fill and the stream's reduce kernel" if args.workload == "fog" else
+                         "fp32 FFMA2 path (parity 1e-5): issue- and latency-bound, not HBM-bound (DESIGN.md 3.1 / 3.1d); the timed launch "
+                         "also contains the label histogram, the zero fill and the stream's reduce kernel" if wl["dtype"] == "f32" else
                          "not HBM-bound (DESIGN.md 3.1c): DRAM traffic equals the algorithmic bytes (inputs are read once); at the "
                          "reference's channel widths (N = 16 outputs) the kernel is bound by the tensor pipe's fixed per-instruction "
                          "cost (~40 clocks per M = 128 tcgen05.mma whatever N <= 32 is; 70 / 134 / 76 MMAs per tile) and the row warps' "

@@ -212,6 +212,32 @@ def test_fog_fused_step_matches_reference(gk, name):
                 close(sd[k[6:]].cpu().numpy(), v, 1e-5, f"step {st} param {k[6:]}")
 
 
+def test_fog_fused_step_matches_oracle_many_clips(gk):
+    """Seeded random FoG batch with MORE clips than the kernels' grids hold (B = 1001 > 3 CTAs x 148 SMs): every CTA runs
+    several clips through the bulk-prefetch ring, odd clips start on a 4-byte boundary only (101 x 21 floats), the sensor
+    stream runs in pooled-taps form (csrc/stream_common.cuh, ENC_POOL_LINEAR) -- losses, accuracy and the parameters after
+    two steps against the CPU oracle (which convolves all 426 rows and pools afterwards, as the reference does)."""
+    import gait_oracle as O
+    g = load_golden("fog_async_gcl"); meta = g["meta"]; prm = meta["params"]
+    m = fog_model(gk, g)
+    B = 1001
+    sk, se, y = O.synth_fog_batch(B, seed=4)
+    yt = np.random.default_rng(2).permutation(y)
+    step = gk.FusedTrainStep(m, fog_criteria(gk, meta), cagrad_c=meta["alpha"], private_mult=1.0)
+    p = {k: torch.tensor(v).requires_grad_(True) for k, v in sub(g, "state0").items()}; bufs = {}
+    for it in range(2):
+        loss, correct = step.step([dev(sk), dev(se)], [dev(y), dev(yt)])
+        ex = O.fog_train_step(p, bufs, torch.from_numpy(sk), torch.from_numpy(se), torch.from_numpy(y), torch.from_numpy(yt),
+                              sensor_length=prm["sensor_length"], synchronized=False, wm=meta["wm"],
+                              counts=[meta["sk_counts"], meta["se_counts"]], alpha=meta["alpha"], bdim=prm["backbone_dim"])
+        close(loss.cpu().numpy(), ex["losses"], 5e-5, "loss")
+        ref_correct = [int((l.argmax(1) == torch.from_numpy(v)).sum()) for l, v in zip(ex["logits"], (y, yt))]
+        assert correct.cpu().numpy().round().astype(int).tolist()[:2] == ref_correct
+    for k, v in m.state_dict().items():
+        if k in p:
+            close(v.cpu().numpy(), p[k].detach().numpy(), 2e-5, k)
+
+
 @pytest.mark.parametrize("name", ["fog_sync_gcl", "fog_sync_ce_nc"])
 def test_fog_sync_fused_step_matches_reference(gk, name):
     """Synchronised FoG in the FUSED step: shared head, and -- for wm = gcl -- the symmetric-KL consistency term

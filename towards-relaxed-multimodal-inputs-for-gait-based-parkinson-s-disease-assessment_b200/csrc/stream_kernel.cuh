@@ -335,36 +335,49 @@ __global__ void __launch_bounds__(NT, Cfg::MINB) stream_kernel(const StreamArgs 
             asm volatile("cp.async.wait_all;" ::: "memory");
             umma::mbar_wait(ldbar, ldphase); ldphase ^= 1u;
             __syncthreads();                                          // the 4-byte copies of the other threads
-            for (int w = 0; w < W; ++w) {
-                const int wi = win0 + w;
-                const bool live = wi < A.B;
-                const float* sw = STGs + w * SP.STGN + (live ? (int)((reinterpret_cast<uintptr_t>(win_src(wi)) >> 2) & 3) : 0);
-                if constexpr (POOLLIN) {
+            if constexpr (POOLLIN) {
+                for (int w = 0; w < W; ++w) {
+                    const int wi = win0 + w;
+                    const bool live = wi < A.B;
+                    const float* sw = STGs + w * SP.STGN + (live ? (int)((reinterpret_cast<uintptr_t>(win_src(wi)) >> 2) & 3) : 0);
                     // row i, channel ci * 3 + tap = mean over bin i of x[t + tap - 1][ci] (zero outside the clip)
                     for (int it = tid; it < T * RC; it += NT) {
                         const int i = it / RC, ci = it - i * RC;
                         const int s0 = ep_s[i], s1 = ep_e[i];
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
                         if (live) {
-                            for (int t = s0 - 1; t <= s1; ++t) {
-                                const float v = (t >= 0 && t < T_in) ? sw[t * RC + ci] : 0.f;
-                                if (t <= s1 - 2) a0 += v;
-                                if (t >= s0 && t < s1) a1 += v;
-                                if (t > s0) a2 += v;
+                            // bin [s0, s1): tap 0 sums frames [s0 - 1, s1 - 1), tap 1 [s0, s1), tap 2 [s0 + 1, s1 + 1) -- the three
+                            // windows share their middle frames (s0, s1 - 1), summed once
+                            const float* col = sw + ci;
+                            const float xm = s0 > 0 ? col[(s0 - 1) * RC] : 0.f, xe = s1 < T_in ? col[s1 * RC] : 0.f;
+                            const float x0 = col[s0 * RC];
+                            if (s1 - s0 == 1) { a0 = xm; a1 = x0; a2 = xe; }
+                            else {
+                                const float xl = col[(s1 - 1) * RC];
+                                float mid = 0.f;
+                                for (int t = s0 + 1; t < s1 - 1; ++t) mid += col[t * RC];
+                                const float inv = 1.0f / (float)(s1 - s0);
+                                a0 = (xm + x0 + mid) * inv; a1 = (x0 + mid + xl) * inv; a2 = (mid + xl + xe) * inv;
                             }
-                            const float inv = 1.0f / (float)(s1 - s0);
-                            a0 *= inv; a1 *= inv; a2 *= inv;
                         }
                         const int c0 = ci * 3, row = halo + i * W + w;
                         Xs[(((c0) >> 2) * RBi + row) * 4 + ((c0) & 3)] = a0;
                         Xs[(((c0 + 1) >> 2) * RBi + row) * 4 + ((c0 + 1) & 3)] = a1;
                         Xs[(((c0 + 2) >> 2) * RBi + row) * 4 + ((c0 + 2) & 3)] = a2;
                     }
-                } else {
-                    for (int e = tid; e < per_raw; e += NT) {
-                        const int t = e / CIN, c = e - t * CIN;
-                        Xs[((c >> 2) * RBi + halo + t * W + w) * 4 + (c & 3)] = live ? sw[e] : 0.f;
-                    }
+                }
+            } else {
+                // thread = row (frame t of window w): its CIN staged floats (stride CIN across the lanes: conflict-free for odd CIN)
+                // -> one 16-byte word per channel chunk.  (A loop over the window's elements with a division per element was 18 %
+                // of the skeleton kernel's instructions.)
+                for (int r = tid; r < rows_in; r += NT) {
+                    const int t = r / W, w = r - t * W, wi = win0 + w;
+                    const bool live = wi < A.B;
+                    const float* src = STGs + w * SP.STGN + (live ? (int)((reinterpret_cast<uintptr_t>(win_src(wi)) >> 2) & 3) : 0) + t * CIN;
+                    float v[CI4 * 4];
+#pragma unroll
+                    for (int c = 0; c < CI4 * 4; ++c) v[c] = (c < CIN && live) ? src[c] : 0.f;
+                    store_row<CI4 * 4>(Xs, RBi, halo, r, v);
                 }
             }
             umma::fence_smem_to_async();                              // staging is read; the next bulk copy may overwrite it
