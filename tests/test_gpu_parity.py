@@ -404,9 +404,14 @@ def test_fused_step_matches_oracle_random(gk):
         close(loss.cpu().numpy(), ex["losses"], 5e-5, "loss")
         ref_correct = [int((l.argmax(1) == torch.from_numpy(v)).sum()) for l, v in zip(ex["logits"], ys)]
         assert correct.cpu().numpy().round().astype(int).tolist() == ref_correct
+    bad = []                                               # every parameter, so that a failure names all of them
     for k, v in m.state_dict().items():
         if k in p:
-            close(v.cpu().numpy(), p[k].detach().numpy(), 2e-5, k)
+            try:
+                close(v.cpu().numpy(), p[k].detach().numpy(), 2e-5, k)
+            except AssertionError as e:
+                bad.append(str(e))
+    assert not bad, "; ".join(bad)
 
 
 def test_data_path_matches_reference(gk):
