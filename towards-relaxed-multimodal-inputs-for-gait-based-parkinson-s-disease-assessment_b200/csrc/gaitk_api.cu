@@ -683,9 +683,24 @@ extern "C" int gaitk_step_grads(gaitk_plan* pl, const float* params, const float
         if (fork) { int rc_ = ensure_side_streams(pl); if (rc_) return rc_; CUDA_TRY(cudaEventRecord(pl->ev_fork, st)); }
     }
     int n_forked = 0, n_launched = 0;
-    for (int s = 0; s < pl->n_streams; ++s) {
-        const size_t ws_floats = (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64;
-        float* my_part = part; part += ws_floats;
+    float* parts[GAITK_MAX_STREAMS];
+    for (int s = 0; s < pl->n_streams; ++s) { parts[s] = part; part += (stream_ws_floats(pl, pl->st[s], B) + 63) / 64 * 64; }
+    // launch order: the most expensive stream first.  Forked kernels that each fill the SMs run nearly back to back and only the
+    // LAST one's tail is exposed, so the long insole kernel should not be it (B = 32768: insole, IMU, walkway 0.891 ms per step;
+    // walkway, insole, IMU 0.905; GAITK_ORDER = e.g. "012" overrides).  Results do not depend on the order (per-stream partials).
+    int order[GAITK_MAX_STREAMS];
+    for (int q = 0; q < pl->n_streams; ++q) order[q] = q;
+    auto cost = [&](int s_) { const StreamPlan& sp = pl->st[s_]; return (sp.enc == ENC_INSOLE ? 1000 : 0) + sp.CIN * sp.KT1; };
+    std::stable_sort(order, order + pl->n_streams, [&](int a_, int b_) { return cost(a_) > cost(b_); });
+    static const char* order_env = getenv("GAITK_ORDER");
+    if (order_env && (int)strlen(order_env) == pl->n_streams) {
+        bool ok = true; int seen = 0;
+        for (int q = 0; q < pl->n_streams; ++q) { const int c = order_env[q] - '0'; if (c < 0 || c >= pl->n_streams || (seen >> c & 1)) ok = false; else seen |= 1 << c; }
+        if (ok) for (int q = 0; q < pl->n_streams; ++q) order[q] = order_env[q] - '0';
+    }
+    for (int q = 0; q < pl->n_streams; ++q) {
+        const int s = order[q];
+        float* my_part = parts[s];
         if (!(task_mask & (1u << s))) continue;
         StreamArgs a; fill_args(pl, s, params, x[s], win_start ? win_start[s] : nullptr, B, MODE_FUSED, !(enabled_mask & (1u << s)), a);
         set_loss(a, loss[s], pl->d.num_classes);
