@@ -950,6 +950,40 @@ def test_all_masks_from_one_pass_match_reference(gk):
         assert int((lg[s].argmax(1) == yy).sum()) == cnt[7 + s]
 
 
+def test_pipelined_resident_steps_equal_synchronous_ones(gk):
+    """FusedTrainStep.step_indices_async (two device slots, copy stream, results read one step late) against the blocking
+    step_indices on the same stores, indices and labels: identical per-step (loss, correct) and identical parameters."""
+    import gait_oracle as O
+    B, T, n_steps = 96, 64, 5
+    xs, _ = O.synth_weargait_batch(4 * B, seed=5)
+    stores = [dev(x.reshape(-1, x.shape[-1])) for x in xs]
+    rng = np.random.default_rng(7)
+    idx = [torch.from_numpy((rng.permutation(4 * B)[:B] * T).astype(np.int64)).pin_memory() for _ in range(n_steps)]
+    ys = [torch.from_numpy(rng.integers(0, 2, B).astype(np.int64)).pin_memory() for _ in range(n_steps)]
+    outs = {}
+    params = {}
+    for mode in ("sync", "async"):
+        torch.manual_seed(11)
+        m = gk.WearGaitThreeModal().cuda(); m.set_window(T)
+        crit = [gk.GCLLoss(cls_num_list=[40, 60], m=0.2, s=25.0, noise_mul=0.0) for _ in range(3)]
+        step = gk.FusedTrainStep(m, crit, cagrad_c=0.5, private_mult=2.0, dtype=gk.DTYPE_F32)
+        got = []
+        if mode == "sync":
+            for i in range(n_steps):
+                got.append(step.step_indices(stores, [idx[i]] * 3, [ys[i]] * 3).clone())
+        else:
+            pending = None
+            for i in range(n_steps):
+                h = step.step_indices_async(stores, [idx[i]] * 3, [ys[i]] * 3, slot=i % 2)
+                if pending is not None:
+                    got.append(pending.result())
+                pending = h
+            got.append(pending.result())
+        outs[mode] = torch.stack(got); params[mode] = m.flat_params().clone()
+    assert torch.equal(outs["sync"], outs["async"])
+    assert torch.equal(params["sync"], params["async"])
+
+
 def test_eval_one_epoch_on_resident_loader_matches_dense_torch(gk):
     dl = gk.dataloader_weargait
     rng = np.random.default_rng(5)

@@ -23,6 +23,18 @@ from .classification_losses import criterion_spec
 from .plan import FlatParamModule
 
 
+class _PendingResult:
+    """(loss[n], correct[n]) of one step on its way to a pinned host buffer (FusedTrainStep.step_indices_async)."""
+    __slots__ = ("_buf", "_ready")
+
+    def __init__(self, buf, ready):
+        self._buf = buf; self._ready = ready
+
+    def result(self) -> torch.Tensor:
+        self._ready.synchronize()
+        return self._buf.clone()
+
+
 class FusedTrainStep:
     def __init__(self, model: FlatParamModule, criterions: Sequence, *, cagrad_c: float, max_norm: float = 1.0,
                  lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, private_mult: float = 2.0,
@@ -36,7 +48,7 @@ class FusedTrainStep:
         self.dtype = int(getattr(model, 'compute_dtype', _lib.DTYPE_F32) if dtype is None else dtype)
         self._mom = None; self._gbuf = None; self._denom = None; self._diag = None
         self._pinned = {}; self._dev_in = {}
-        self._copy_stream = None; self._staged = {}; self._slot_free = {}
+        self._copy_stream = None; self._staged = {}; self._slot_free = {}; self._host_out = {}
         self.use_graph = bool(use_graph); self._graphs = {}
         # p2p: data-parallel exchange by gaitk_p2p_allreduce over symmetric (peer-mapped) memory instead of NCCL
         self.p2p = bool(p2p); self._p2p = None; self._red = None
@@ -383,6 +395,49 @@ class FusedTrainStep:
             ys = [self._to_dev(("yi", i), y, dev) for i, y in enumerate(ys_host)]
         loss, correct = self.step(list(stores), ys, win_start=ws, **kw)
         return torch.cat([loss, correct]).to("cpu", non_blocking=False)
+
+    def step_indices_async(self, stores: Sequence[torch.Tensor], win_start_host: Sequence[torch.Tensor],
+                           ys_host: Sequence[torch.Tensor], slot: int = 0, **kw):
+        """Pipelined step_indices: the (pinned) index / label vectors go to device slot `slot` on the copy stream, the step
+        is launched behind them, its (loss, correct) is copied to a pinned host buffer without blocking, and a handle is
+        returned; ``handle.result()`` waits for THIS step's numbers.  Reading step i - 1 after launching step i keeps the
+        host one step ahead of the device (no launch gap, the H2D copy runs under the previous step):
+
+            pending = None
+            for i in range(n):
+                h = step.step_indices_async(stores, w[i], y[i], slot=i % 2)
+                if pending is not None: log(pending.result())
+                pending = h
+            log(pending.result())
+
+        Two slots suffice as long as the result of the step that last used a slot has been read before it is reused."""
+        dev = stores[0].device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+        ev_free = self._slot_free.get(("idx", slot))
+        with torch.cuda.stream(self._copy_stream):
+            if ev_free is not None:
+                self._copy_stream.wait_event(ev_free)          # the step that last read this slot has finished
+            if all(w is win_start_host[0] for w in win_start_host):
+                w0 = self._to_dev((slot, "w", 0), win_start_host[0], dev); ws = [w0] * len(win_start_host)
+            else:
+                ws = [self._to_dev((slot, "w", i), w, dev) for i, w in enumerate(win_start_host)]
+            if all(y is ys_host[0] for y in ys_host):
+                y0 = self._to_dev((slot, "yi", 0), ys_host[0], dev); ys = [y0] * len(ys_host)
+            else:
+                ys = [self._to_dev((slot, "yi", i), y, dev) for i, y in enumerate(ys_host)]
+            ev = torch.cuda.Event(); ev.record(self._copy_stream)
+        cur.wait_event(ev)
+        loss, correct = self.step(list(stores), ys, win_start=ws, **kw)
+        done = torch.cuda.Event(); done.record(cur); self._slot_free[("idx", slot)] = done
+        res = torch.cat([loss, correct])
+        out = self._host_out.get(slot)
+        if out is None or out.shape != res.shape:
+            out = torch.empty(res.shape, dtype=res.dtype).pin_memory(); self._host_out[slot] = out
+        out.copy_(res, non_blocking=True)
+        ready = torch.cuda.Event(); ready.record(cur)
+        return _PendingResult(out, ready)
 
     def _to_dev(self, key, t, dev):
         buf = self._dev_in.get(key)
