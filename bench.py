@@ -512,7 +512,7 @@ def run_gpu(args):
         sig = {"walkway": "StreamCfg<0, 2,", "insole": "StreamCfg<1, 13,", "imu": "StreamCfg<0, 24,",
                "skeleton": "StreamCfg<2, 21,", "sensor": "StreamCfg<5, 18,"}.get(dom)
         pdir = ROOT / "profiles"
-        cands = {"tf32": ["r1_ncu_full_final.json"], "bf16x3": sorted(q.name for q in pdir.glob("r2_ncu_full_ws_*.json"))[::-1],
+        cands = {"tf32": ["r1_ncu_full_final.json"], "bf16x3": sorted(q.name for q in pdir.glob("r3_ncu_full_ws*.json"))[::-1] + sorted(q.name for q in pdir.glob("r2_ncu_full_ws_*.json"))[::-1],
                  "f32": sorted(q.name for q in pdir.glob("r3_ncu_full_fog*.json"))[::-1]}.get(wl["dtype"], [])
         for pf in cands:
             prof = pdir / pf
