@@ -164,9 +164,11 @@ static int plan_stream(gaitk_plan* pl, int s, int enc, int CIN, int KT1, int H, 
     const int stage_floats = 16 * std::max(std::max(NF, 256), std::max(nblk_max, NT));
     m.STAGE = take(stage_floats);
     // bulk-prefetch staging of the next tile's raw windows (stream_kernel.cuh): the FoG / FBG streams, whose kernels were
-    // bound by the synchronous global -> shared scatter; the pooled-taps kernel has no other load path
+    // bound by the synchronous global -> shared scatter (the pooled-taps kernel has no other load path), and the WearGait
+    // encoders of the fp32 path (GAITK_F32_PREFETCH = 2: FoG / FBG only, 0: off)
     static const int prefetch_mode = [] { const char* e = getenv("GAITK_F32_PREFETCH"); return e ? atoi(e) : 1; }();
-    if (sp.pooled_taps || (prefetch_mode && enc == ENC_LINEAR_LN_RELU && sp.cl == 1 && T_in * raw_cin >= 8)) {
+    const bool pf_enc = enc == ENC_LINEAR_LN_RELU || (prefetch_mode >= 1 && prefetch_mode != 2 && (enc == ENC_CONV_GELU_LN || enc == ENC_INSOLE));
+    if (sp.pooled_taps || (prefetch_mode && pf_enc && sp.cl == 1 && T_in == T && T_in * raw_cin >= 8)) {
         m.STGN = (T_in * raw_cin + 3) / 4 * 4 + 4;
         // the flush scratch is idle inside the tile loop (and no copy is in flight when the flush starts): the staging aliases it
         m.STG = sp.W * m.STGN <= stage_floats ? m.STAGE : take(sp.W * m.STGN);
